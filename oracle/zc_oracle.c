@@ -1,0 +1,584 @@
+/*
+ * zc_oracle.c -- CPU oracle for the zcordic hot path.  TEST INFRASTRUCTURE ONLY.
+ * See zc_oracle.h for the scope statement and how parity is pinned.
+ * Citations are file:line relative to /root/reference.
+ */
+#define _GNU_SOURCE
+#include "zc_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- bit helpers ------------------------------------------------------- */
+
+/* low w bits of v as two's complement (Verilog "signed [w-1:0]") */
+static inline int64_t sx(int64_t v, int w) {
+	uint64_t m = (w >= 64) ? ~0ull : ((1ull << w) - 1ull);
+	uint64_t u = (uint64_t)v & m;
+	if (w < 64 && (u >> (w - 1)) & 1ull)
+		u |= ~m;
+	return (int64_t)u;
+}
+
+static inline uint64_t ux(uint64_t v, int w) {
+	return (w >= 64) ? v : (v & ((1ull << w) - 1ull));
+}
+
+/* ---- sw/cordiclib.cpp -------------------------------------------------- */
+
+/* sw/cordiclib.cpp:66-80 */
+double zo_cordic_gain(int nstages) {
+	double gain = 1.0;
+	for (int k = 0; k < nstages; k++) {
+		double dgain = 1.0 + pow(2.0, -2. * (k + 1));
+		dgain = sqrt(dgain);
+		gain = gain * dgain;
+	}
+	return gain;
+}
+
+/* sw/cordiclib.cpp:82-109 */
+double zo_phase_variance(int nstages, int pw) {
+	double RAD_TO_PHASE = (double)(1ul << (pw - 1)) / M_PI;
+	double variance = 1. / 12.;
+	for (unsigned k = 0; k < (unsigned)nstages; k++) {
+		double x, err;
+		unsigned long phase_value;
+		x = atan2(1., pow(2, k + 1)) * RAD_TO_PHASE;
+		phase_value = (unsigned)x;
+		err = phase_value - x;
+		err *= err;
+		variance += err;
+	}
+	variance /= pow(RAD_TO_PHASE, 2.);
+	return variance;
+}
+
+/* sw/cordiclib.cpp:111-130 */
+double zo_quantization_variance(int nstages, int xtrabits, int dropped_bits) {
+	double v = pow(2, 2 * xtrabits) / 12.;
+	for (int k = 0; k < nstages; k++)
+		v = (1 + pow(4, -k - 1)) * v + 1. / 3.;
+	if (dropped_bits > 0)
+		v = pow(2, -2 * dropped_bits) * v + 1 / 12.;
+	return v;
+}
+
+/* sw/cordiclib.cpp:157-169 -- truncation, not rounding */
+uint32_t zo_angle(int k, int pw) {
+	double x = atan2(1., pow(2, k + 1));
+	x *= (4.0 * (double)(1ul << (pw - 2))) / (M_PI * 2.0);
+	return (uint32_t)(unsigned)x;
+}
+
+/* sw/cordiclib.cpp:214-229 */
+int zo_calc_stages_ww(int ww, int pw) {
+	unsigned n;
+	for (n = 0; n < 64; n++) {
+		if (zo_angle((int)n, pw) == 0)
+			break;
+		if (ww <= (int)n)
+			break;
+	}
+	return (int)n;
+}
+
+/* sw/cordiclib.cpp:231-244 */
+int zo_calc_stages(int pw) {
+	unsigned n;
+	for (n = 0; n < 64; n++)
+		if (zo_angle((int)n, pw) == 0)
+			break;
+	return (int)n;
+}
+
+/* sw/cordiclib.cpp:246-268 -- note (2^ow - 1), not (2^(ow-1) - 1) */
+int zo_calc_phase_bits(int ow) {
+	unsigned pb;
+	for (pb = 3; pb < 64; pb++) {
+		double a = (2.0 * M_PI / (double)(1ul << pb));
+		double ds = sin(a);
+		ds *= (double)((1ul << ow) - 1);
+		if (ds < 0.5)
+			break;
+	}
+	if (pb < 3)
+		pb = 3;
+	return (int)pb;
+}
+
+/* ---- parameter derivation ---------------------------------------------- */
+
+static void fill_angles(zo_params *p) {
+	memset(p->angle, 0, sizeof(p->angle));
+	for (int k = 0; k < p->nstages && k < ZO_MAX_STAGES; k++)
+		p->angle[k] = zo_angle(k, p->pw);
+}
+
+static int default_widths(int *iw, int *ow) {
+	/* sw/main.cpp:262-270 (p2r), :314-322 (r2p) */
+	if ((*iw <= 0) && (*ow > 0))
+		*iw = *ow;
+	if (*ow <= 0)
+		*ow = *iw;
+	if ((*iw <= 0) || (*ow <= 0)) {
+		*iw = 24;
+		*ow = 24;
+	}
+	return 0;
+}
+
+int zo_derive_p2r(int iw, int ow, int xtra_user, int pw, int nstages, zo_params *p) {
+	memset(p, 0, sizeof(*p));
+	default_widths(&iw, &ow);
+	int mx = (ow > iw) ? ow : iw;
+	int nxtra = xtra_user + 1;		/* sw/main.cpp:273 */
+	int ww_main = mx + nxtra;		/* sw/main.cpp:272-274 */
+	if (pw <= 0)
+		pw = zo_calc_phase_bits(ww_main);	/* :276 */
+	if (nstages <= 0)
+		nstages = zo_calc_stages_ww(ww_main, pw);	/* :278 */
+	if (nxtra < 1)				/* sw/basiccordic.cpp:67-68 */
+		nxtra = 1;
+	if (pw < 3 || pw > 32 || nstages > ZO_MAX_STAGES)
+		return -1;
+	p->iw = iw; p->ow = ow; p->nextra = nxtra;
+	p->ww = mx + nxtra;			/* sw/basiccordic.cpp:71-73 */
+	p->pw = pw; p->nstages = nstages; p->vectoring = 0;
+	if (p->ww > 32)
+		return -1;
+	fill_angles(p);
+	/* sw/basiccordic.cpp:471-496 */
+	p->qvar = zo_quantization_variance(nstages, p->ww - iw, p->ww - ow);
+	p->pvar_rad = zo_phase_variance(nstages, pw);
+	p->cordic_gain = zo_cordic_gain(nstages);
+	p->gain = p->cordic_gain;
+	{
+		double amplitude = (double)((1ul << (iw - 1))) - 1., sig, noise;
+		amplitude *= (double)(1ul << (p->ww - iw));
+		amplitude *= zo_cordic_gain(nstages);
+		amplitude *= pow(2.0, -(p->ww - ow));
+		sig = amplitude * amplitude;
+		noise = zo_quantization_variance(nstages, p->ww - iw, p->ww - ow);
+		noise += sig * zo_phase_variance(nstages, pw)
+			* pow(2, zo_cordic_gain(nstages));	/* (sic) :490-491 */
+		p->best_cnr = 10.0 * log(sig / noise) / log(10.0);
+	}
+	return 0;
+}
+
+int zo_derive_r2p(int iw, int ow, int xtra_user, int pw, int nstages, zo_params *p) {
+	memset(p, 0, sizeof(*p));
+	default_widths(&iw, &ow);
+	int mx = (ow > iw) ? ow : iw;
+	int nxtra = xtra_user + 2;		/* sw/main.cpp:323 */
+	int ww_main = mx + nxtra;
+	if (pw <= 0)
+		pw = zo_calc_phase_bits(ww_main);	/* :325-326 */
+	if (nstages <= 0)
+		nstages = zo_calc_stages(pw);		/* :327-328 */
+	if (nxtra < 2)				/* sw/topolar.cpp:67-68 */
+		nxtra = 2;
+	if (pw < 3 || pw > 32 || nstages > ZO_MAX_STAGES)
+		return -1;
+	p->iw = iw; p->ow = ow; p->nextra = nxtra;
+	p->ww = mx + nxtra + nxtra;		/* sw/topolar.cpp:71-75: added twice */
+	p->pw = pw; p->nstages = nstages; p->vectoring = 1;
+	if (p->ww > 32)
+		return -1;
+	fill_angles(p);
+	/* sw/topolar.cpp:434-440 */
+	p->qvar = zo_quantization_variance(nstages, p->ww - iw, p->ww - ow);
+	p->pvar_rad = zo_phase_variance(nstages, pw);
+	p->cordic_gain = zo_cordic_gain(nstages);
+	p->gain = p->cordic_gain * sqrt(2.0) / 2.;
+	p->best_cnr = 0.0;
+	return 0;
+}
+
+static int derive_lut(int iw, int pw, int ow, int qtr, int *pw_out, int *ow_out) {
+	/* sw/main.cpp:358-379 (tbl): (iw>=0)&&(phase_bits<=0);  :401-422 (qtr): phase_bits<0.
+	 * "not given" is -1 in main.cpp; callers pass <=0 which we map to -1 first. */
+	if (iw <= 0) iw = -1;
+	if (pw <= 0) pw = -1;
+	if (ow <= 0) ow = -1;
+	if ((iw >= 0) && (qtr ? (pw < 0) : (pw <= 0))) {
+		pw = iw;
+		iw = -1;
+	}
+	if ((pw > 3) && (ow <= 0)) {
+		for (int k = pw - 2; k < pw + 3; k++) {
+			if (zo_calc_phase_bits(k) == pw) {
+				ow = k;
+				break;
+			}
+		}
+	}
+	if (ow <= 0)
+		ow = 24;
+	if (pw <= 0)
+		pw = zo_calc_phase_bits(ow);
+	*pw_out = pw;
+	*ow_out = ow;
+	/* sw/sintable.cpp:62 (tbl >=24 refused), :190 (qtr >=26 refused), hexfile.cpp:52 */
+	if (qtr ? (pw >= 26 || pw <= 2) : (pw >= 24))
+		return -1;
+	if (ow >= 31)
+		return -1;
+	return 0;
+}
+
+int zo_derive_tbl(int iw, int pw, int ow, int *pw_out, int *ow_out) {
+	return derive_lut(iw, pw, ow, 0, pw_out, ow_out);
+}
+int zo_derive_qtr(int iw, int pw, int ow, int *pw_out, int *ow_out) {
+	return derive_lut(iw, pw, ow, 1, pw_out, ow_out);
+}
+
+/* ---- rotation core: rtl/cordic.v --------------------------------------- */
+
+/* rtl/cordic.v:85-86 (extend) and :131-188 (octant pre-rotation) */
+void zo_rotate_pre(const zo_params *p, int32_t ix, int32_t iy, uint32_t phase,
+		int32_t *x, int32_t *y, uint32_t *ph) {
+	const int WW = p->ww, IW = p->iw, PW = p->pw;
+	/* { sign, i_xval, (WW-IW-1) zeros }  (sw/basiccordic.cpp:137-145) */
+	int64_t ex = sx(sx(ix, IW) * ((int64_t)1 << (WW - IW - 1)), WW);
+	int64_t ey = sx(sx(iy, IW) * ((int64_t)1 << (WW - IW - 1)), WW);
+	uint64_t ip = ux(phase, PW);
+	uint64_t Q = 1ull << (PW - 2);
+	int64_t xv, yv;
+	uint64_t pv;
+	switch ((int)((ip >> (PW - 3)) & 7)) {
+	case 0: case 7:
+		xv = ex;  yv = ey;  pv = ip;		break;
+	case 1: case 2:
+		xv = -ey; yv = ex;  pv = ip - Q;	break;
+	case 3: case 4:
+		xv = -ex; yv = -ey; pv = ip - 2 * Q;	break;
+	default: /* 5, 6 */
+		xv = ey;  yv = -ex; pv = ip - 3 * Q;	break;
+	}
+	*x = (int32_t)sx(xv, WW);
+	*y = (int32_t)sx(yv, WW);
+	*ph = (uint32_t)ux(pv, PW);
+}
+
+/* rtl/cordic.v:253-280 */
+void zo_rotate_stage(const zo_params *p, int i, int32_t *x, int32_t *y, uint32_t *ph) {
+	const int WW = p->ww, PW = p->pw;
+	if (p->angle[i] == 0 || i >= WW)
+		return;
+	int64_t xv = *x, yv = *y;
+	uint64_t pv = *ph;
+	int64_t xs = xv >> (i + 1), ys = yv >> (i + 1);	/* >>> on signed regs */
+	if ((pv >> (PW - 1)) & 1) {	/* negative phase */
+		*x = (int32_t)sx(xv + ys, WW);
+		*y = (int32_t)sx(yv - xs, WW);
+		*ph = (uint32_t)ux(pv + p->angle[i], PW);
+	} else {
+		*x = (int32_t)sx(xv - ys, WW);
+		*y = (int32_t)sx(yv + xs, WW);
+		*ph = (uint32_t)ux(pv - p->angle[i], PW);
+	}
+}
+
+/* rtl/cordic.v:290-295,311-312 ; no-rounding branch sw/basiccordic.cpp:407-444 */
+int32_t zo_round_out(const zo_params *p, int32_t v) {
+	const int WW = p->ww, OW = p->ow, D = WW - OW;
+	int64_t x = v;
+	if (WW > OW + 1) {
+		int b = (int)((x >> D) & 1);
+		int64_t add = b ? ((int64_t)1 << (D - 1)) : (((int64_t)1 << (D - 1)) - 1);
+		x = sx(x + add, WW);
+	}
+	/* bits [WW-1:D] of the WW-bit word, as an OW-bit signed output */
+	return (int32_t)sx((int64_t)(ux((uint64_t)x, WW) >> D), OW);
+}
+
+void zo_rotate1(const zo_params *p, int32_t ix, int32_t iy, uint32_t phase,
+		int32_t *ox, int32_t *oy) {
+	int32_t x, y;
+	uint32_t ph;
+	zo_rotate_pre(p, ix, iy, phase, &x, &y, &ph);
+	for (int i = 0; i < p->nstages; i++)
+		zo_rotate_stage(p, i, &x, &y, &ph);
+	*ox = zo_round_out(p, x);
+	*oy = zo_round_out(p, y);
+}
+
+/* ---- vectoring core: rtl/topolar.v ------------------------------------- */
+
+/* rtl/topolar.v:83-84 (extend; variants sw/topolar.cpp:139-151), :122-152 (quadrant) */
+void zo_topolar_pre(const zo_params *p, int32_t ix, int32_t iy,
+		int32_t *x, int32_t *y, uint32_t *ph) {
+	const int WW = p->ww, IW = p->iw, PW = p->pw;
+	int64_t sxv = sx(ix, IW), syv = sx(iy, IW);
+	int64_t ex, ey;
+	if (WW - IW > 2) {
+		ex = sxv * ((int64_t)1 << (WW - IW - 2));
+		ey = syv * ((int64_t)1 << (WW - IW - 2));
+	} else if (WW - IW > 1) {
+		ex = sxv; ey = syv;
+	} else {
+		ex = sxv >> 1; ey = syv >> 1;
+	}
+	ex = sx(ex, WW); ey = sx(ey, WW);
+	uint64_t E = 1ull << (PW - 3);
+	int xneg = (sxv < 0), yneg = (syv < 0);
+	int64_t xv, yv;
+	uint64_t pv;
+	if (!xneg && yneg) {		/* 2'b01 */
+		xv = ex - ey;  yv = ex + ey;  pv = 7 * E;
+	} else if (xneg && !yneg) {	/* 2'b10 */
+		xv = -ex + ey; yv = -ex - ey; pv = 3 * E;
+	} else if (xneg && yneg) {	/* 2'b11 */
+		xv = -ex - ey; yv = ex - ey;  pv = 5 * E;
+	} else {			/* default */
+		xv = ex + ey;  yv = -ex + ey; pv = E;
+	}
+	*x = (int32_t)sx(xv, WW);
+	*y = (int32_t)sx(yv, WW);
+	*ph = (uint32_t)ux(pv, PW);
+}
+
+/* rtl/topolar.v:217-243 */
+void zo_topolar_stage(const zo_params *p, int i, int32_t *x, int32_t *y, uint32_t *ph) {
+	const int WW = p->ww, PW = p->pw;
+	if (p->angle[i] == 0 || i >= WW)
+		return;
+	int64_t xv = *x, yv = *y;
+	uint64_t pv = *ph;
+	int64_t xs = xv >> (i + 1), ys = yv >> (i + 1);
+	if (yv < 0) {		/* yv[WW-1]: below the axis */
+		*x = (int32_t)sx(xv - ys, WW);
+		*y = (int32_t)sx(yv + xs, WW);
+		*ph = (uint32_t)ux(pv - p->angle[i], PW);
+	} else {
+		*x = (int32_t)sx(xv + ys, WW);
+		*y = (int32_t)sx(yv - xs, WW);
+		*ph = (uint32_t)ux(pv + p->angle[i], PW);
+	}
+}
+
+/* rtl/topolar.v:253-255,268-269 */
+void zo_topolar1(const zo_params *p, int32_t ix, int32_t iy,
+		int32_t *omag, uint32_t *ophase) {
+	int32_t x, y;
+	uint32_t ph;
+	zo_topolar_pre(p, ix, iy, &x, &y, &ph);
+	for (int i = 0; i < p->nstages; i++)
+		zo_topolar_stage(p, i, &x, &y, &ph);
+	*omag = zo_round_out(p, x);
+	*ophase = ph;
+}
+
+/* ---- LUT cores --------------------------------------------------------- */
+
+/* sw/sintable.cpp:156-168 + sw/hexfile.cpp:78-89 (mask to OW bits) */
+int zo_sintable_build(int pw, int ow, uint32_t *tbl) {
+	if (pw >= 24 || pw < 1 || ow >= 31 || ow < 2)
+		return -1;
+	int tbl_entries = (1 << pw);
+	long maxv = (1l << (ow - 1)) - 1l;
+	long msk = (1l << ow) - 1l;
+	for (int k = 0; k < tbl_entries; k++) {
+		double ph = 2.0 * M_PI * (double)k / (double)tbl_entries;
+		long v = (long)((double)maxv * sin(ph));
+		tbl[k] = (uint32_t)(v & msk);
+	}
+	return 0;
+}
+
+/* sw/sintable.cpp:325-337 */
+int zo_quarterwav_build(int pw, int ow, uint32_t *tbl) {
+	if (pw >= 26 || pw <= 2 || ow >= 31 || ow < 2)
+		return -1;
+	int tbl_entries = (1 << pw);
+	long maxv = (1l << (ow - 1)) - 1l;
+	long msk = (1l << ow) - 1l;
+	for (int k = 0; k < tbl_entries / 4; k++) {
+		double ph = 2.0 * M_PI * (double)k / (double)tbl_entries;
+		ph += M_PI / (double)tbl_entries;
+		long v = (long)((double)maxv * sin(ph));
+		tbl[k] = (uint32_t)(v & msk);
+	}
+	return 0;
+}
+
+/* rtl/sintable.v:71-75 */
+int32_t zo_sintable_lookup1(int pw, int ow, const uint32_t *tbl, uint32_t phase32) {
+	uint32_t ip = phase32 >> (32 - pw);
+	return (int32_t)sx(tbl[ip], ow);
+}
+
+/* rtl/quarterwav.v:92-109 */
+int32_t zo_quarterwav_lookup1(int pw, int ow, const uint32_t *tbl, uint32_t phase32) {
+	uint32_t ip = phase32 >> (32 - pw);
+	uint32_t lowmask = (1u << (pw - 2)) - 1u;
+	int negate = (ip >> (pw - 1)) & 1;
+	uint32_t index = ((ip >> (pw - 2)) & 1) ? (~ip & lowmask) : (ip & lowmask);
+	uint64_t v = tbl[index];
+	if (negate)
+		v = ux((uint64_t)(-(int64_t)v), ow);
+	return (int32_t)sx((int64_t)v, ow);
+}
+
+/* ---- batched forms ----------------------------------------------------- */
+
+typedef struct job {
+	int kind;
+	const zo_params *p;
+	int32_t x0, y0;
+	const int32_t *xy_in;
+	const uint32_t *phase_in;
+	int32_t *out0;
+	uint32_t *out1;
+	uint32_t phase0, step;
+	uint64_t n0;
+	int pw, ow;
+	const uint32_t *tbl;
+	size_t lo, hi;
+} job;
+
+enum { K_ROTC, K_ROT, K_TOPOLAR, K_NCO, K_SIN, K_QWAV };
+
+static void run_range(const job *j) {
+	size_t i;
+	switch (j->kind) {
+	case K_ROTC:
+		for (i = j->lo; i < j->hi; i++)
+			zo_rotate1(j->p, j->x0, j->y0, j->phase_in[i],
+				&j->out0[2 * i], &j->out0[2 * i + 1]);
+		break;
+	case K_ROT:
+		for (i = j->lo; i < j->hi; i++)
+			zo_rotate1(j->p, j->xy_in[2 * i], j->xy_in[2 * i + 1], j->phase_in[i],
+				&j->out0[2 * i], &j->out0[2 * i + 1]);
+		break;
+	case K_TOPOLAR:
+		for (i = j->lo; i < j->hi; i++)
+			zo_topolar1(j->p, j->xy_in[2 * i], j->xy_in[2 * i + 1],
+				&j->out0[i], &j->out1[i]);
+		break;
+	case K_NCO:
+		for (i = j->lo; i < j->hi; i++) {
+			uint32_t ph32 = j->phase0 + (uint32_t)(j->n0 + i) * j->step;
+			zo_rotate1(j->p, j->x0, j->y0, ph32 >> (32 - j->p->pw),
+				&j->out0[2 * i], &j->out0[2 * i + 1]);
+		}
+		break;
+	case K_SIN:
+		for (i = j->lo; i < j->hi; i++)
+			j->out0[i] = zo_sintable_lookup1(j->pw, j->ow, j->tbl, j->phase_in[i]);
+		break;
+	case K_QWAV:
+		for (i = j->lo; i < j->hi; i++)
+			j->out0[i] = zo_quarterwav_lookup1(j->pw, j->ow, j->tbl, j->phase_in[i]);
+		break;
+	}
+}
+
+static void *thread_main(void *arg) {
+	run_range((const job *)arg);
+	return NULL;
+}
+
+static void run_parallel(job *proto, size_t n, int nthreads) {
+	if (nthreads <= 1 || n < 4096) {
+		proto->lo = 0; proto->hi = n;
+		run_range(proto);
+		return;
+	}
+	if (nthreads > 256)
+		nthreads = 256;
+	pthread_t tid[256];
+	job jobs[256];
+	size_t per = (n + (size_t)nthreads - 1) / (size_t)nthreads;
+	int started = 0;
+	for (int t = 0; t < nthreads; t++) {
+		size_t lo = per * (size_t)t, hi = lo + per;
+		if (lo >= n) break;
+		if (hi > n) hi = n;
+		jobs[t] = *proto;
+		jobs[t].lo = lo; jobs[t].hi = hi;
+		if (pthread_create(&tid[t], NULL, thread_main, &jobs[t]) != 0) {
+			run_range(&jobs[t]);	/* degrade to inline */
+			tid[t] = 0;
+		}
+		started = t + 1;
+	}
+	for (int t = 0; t < started; t++)
+		if (tid[t])
+			pthread_join(tid[t], NULL);
+}
+
+void zo_rotate_const(const zo_params *p, int32_t x0, int32_t y0,
+		const uint32_t *phase, int32_t *xy, size_t n, int nthreads) {
+	job j; memset(&j, 0, sizeof(j));
+	j.kind = K_ROTC; j.p = p; j.x0 = x0; j.y0 = y0; j.phase_in = phase; j.out0 = xy;
+	run_parallel(&j, n, nthreads);
+}
+
+void zo_rotate(const zo_params *p, const int32_t *xy_in, const uint32_t *phase,
+		int32_t *xy_out, size_t n, int nthreads) {
+	job j; memset(&j, 0, sizeof(j));
+	j.kind = K_ROT; j.p = p; j.xy_in = xy_in; j.phase_in = phase; j.out0 = xy_out;
+	run_parallel(&j, n, nthreads);
+}
+
+void zo_topolar(const zo_params *p, const int32_t *xy_in, int32_t *mag,
+		uint32_t *phase, size_t n, int nthreads) {
+	job j; memset(&j, 0, sizeof(j));
+	j.kind = K_TOPOLAR; j.p = p; j.xy_in = xy_in; j.out0 = mag; j.out1 = phase;
+	run_parallel(&j, n, nthreads);
+}
+
+void zo_nco_rotate(const zo_params *p, int32_t x0, int32_t y0, uint32_t phase0,
+		uint32_t step, uint64_t n0, int32_t *xy, size_t n, int nthreads) {
+	job j; memset(&j, 0, sizeof(j));
+	j.kind = K_NCO; j.p = p; j.x0 = x0; j.y0 = y0; j.phase0 = phase0; j.step = step;
+	j.n0 = n0; j.out0 = xy;
+	run_parallel(&j, n, nthreads);
+}
+
+void zo_lut_sin(int pw, int ow, const uint32_t *tbl, const uint32_t *phase32,
+		int32_t *out, size_t n, int nthreads) {
+	job j; memset(&j, 0, sizeof(j));
+	j.kind = K_SIN; j.pw = pw; j.ow = ow; j.tbl = tbl; j.phase_in = phase32; j.out0 = out;
+	run_parallel(&j, n, nthreads);
+}
+
+void zo_lut_qwav(int pw, int ow, const uint32_t *tbl, const uint32_t *phase32,
+		int32_t *out, size_t n, int nthreads) {
+	job j; memset(&j, 0, sizeof(j));
+	j.kind = K_QWAV; j.pw = pw; j.ow = ow; j.tbl = tbl; j.phase_in = phase32; j.out0 = out;
+	run_parallel(&j, n, nthreads);
+}
+
+/* ---- $readmemh fixture loader (format of sw/hexfile.cpp:78-89) ---------- */
+
+long zo_hex_load(const char *fname, uint32_t *words, long maxwords) {
+	FILE *fp = fopen(fname, "r");
+	if (!fp)
+		return -1;
+	long addr = 0, count = 0;
+	char tok[64];
+	while (fscanf(fp, "%63s", tok) == 1) {
+		if (tok[0] == '@') {
+			addr = strtol(tok + 1, NULL, 16);
+			continue;
+		}
+		if (addr >= maxwords) {
+			fclose(fp);
+			return -2;
+		}
+		words[addr++] = (uint32_t)strtoul(tok, NULL, 16);
+		if (addr > count)
+			count = addr;
+	}
+	fclose(fp);
+	return count;
+}

@@ -1,0 +1,114 @@
+/*
+ * zc_oracle.h -- CPU oracle for the zcordic hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This is a plain-C restatement of the arithmetic that ZipCPU/cordic's generated
+ * cores perform (rtl/cordic.v, rtl/topolar.v, rtl/sintable.v, rtl/quarterwav.v) and
+ * of the parameter derivation in its generator (sw/main.cpp, sw/cordiclib.cpp).
+ * Nothing under oracle/ is linked into, imported by, or executed from the product
+ * (cordic_b200/, include/).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may use it, and only as the checker or as
+ * the timed CPU baseline.
+ *
+ * Parity pinning (see DESIGN.md "Oracle"): parameters, angle tables, header
+ * constants and LUT words are pinned word-exactly against the reference's own
+ * generator built from /root/reference/sw (oracle/_ref/gencordic) and against the
+ * checked-in rtl/ artefacts (tests/golden/...).  The reference holds NO per-sample
+ * golden vectors for the CORDIC datapaths (its tests are statistical,
+ * bench/cpp/cordic_tb.cpp:285-337, bench/cpp/topolar_tb.cpp:303-315); the datapath
+ * restatement is pinned by (a) the RTL text, cited per function below, and (b) the
+ * reference's own unmodified test benches compiled against oracle/shim/ and run over
+ * this oracle (oracle/_ref/cordic_tb, oracle/_ref/topolar_tb print SUCCESS).
+ *
+ * All citations are relative to /root/reference.
+ */
+#ifndef ZC_ORACLE_H
+#define ZC_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZO_MAX_STAGES 64
+
+typedef struct zo_params {
+	int	iw, ow;		/* input / output widths			*/
+	int	nextra;		/* NEXTRA as printed in rtl/X.h (already bumped)	*/
+	int	ww;		/* working width				*/
+	int	pw;		/* phase width					*/
+	int	nstages;
+	int	vectoring;	/* 0: rtl/cordic.v (p2r), 1: rtl/topolar.v (r2p)	*/
+	uint32_t angle[ZO_MAX_STAGES];
+	double	gain;		/* GAIN constant of rtl/X.h			*/
+	double	cordic_gain;	/* raw prod sqrt(1+2^-2(k+1))			*/
+	double	qvar;		/* QUANTIZATION_VARIANCE			*/
+	double	pvar_rad;	/* PHASE_VARIANCE_RAD				*/
+	double	best_cnr;	/* BEST_POSSIBLE_CNR (p2r only)			*/
+} zo_params;
+
+/* sw/cordiclib.cpp */
+double	zo_cordic_gain(int nstages);				/* :66-80   */
+double	zo_phase_variance(int nstages, int pw);			/* :82-109  */
+double	zo_quantization_variance(int nstages, int xtra, int dropped); /* :111-130 */
+uint32_t zo_angle(int k, int pw);				/* :157-169 */
+int	zo_calc_stages_ww(int ww, int pw);			/* :214-229 */
+int	zo_calc_stages(int pw);					/* :231-244 */
+int	zo_calc_phase_bits(int ow);				/* :246-268 */
+
+/* sw/main.cpp:260-279 + sw/basiccordic.cpp:67-73,465-498.  Pass <=0 for "not given". */
+int	zo_derive_p2r(int iw, int ow, int xtra_user, int pw, int nstages, zo_params *p);
+/* sw/main.cpp:312-328 + sw/topolar.cpp:67-75,428-446 */
+int	zo_derive_r2p(int iw, int ow, int xtra_user, int pw, int nstages, zo_params *p);
+/* sw/main.cpp:358-379 (tbl) and :401-422 (qtr): resolves (pw, ow) from -i/-p/-o */
+int	zo_derive_tbl(int iw, int pw, int ow, int *pw_out, int *ow_out);
+int	zo_derive_qtr(int iw, int pw, int ow, int *pw_out, int *ow_out);
+
+/* rtl/cordic.v:85-86,131-188,253-280,290-295,311-312 -- one sample */
+void	zo_rotate1(const zo_params *p, int32_t ix, int32_t iy, uint32_t phase,
+		int32_t *ox, int32_t *oy);
+/* rtl/topolar.v:83-84,122-152,217-243,253-255,268-269 -- one sample */
+void	zo_topolar1(const zo_params *p, int32_t ix, int32_t iy,
+		int32_t *omag, uint32_t *ophase);
+
+/* Single pipeline-register steps, used by the cycle-accurate shim (oracle/shim) */
+void	zo_rotate_pre(const zo_params *p, int32_t ix, int32_t iy, uint32_t phase,
+		int32_t *x, int32_t *y, uint32_t *ph);
+void	zo_rotate_stage(const zo_params *p, int i, int32_t *x, int32_t *y, uint32_t *ph);
+void	zo_topolar_pre(const zo_params *p, int32_t ix, int32_t iy,
+		int32_t *x, int32_t *y, uint32_t *ph);
+void	zo_topolar_stage(const zo_params *p, int i, int32_t *x, int32_t *y, uint32_t *ph);
+int32_t	zo_round_out(const zo_params *p, int32_t v);
+
+/* Batched forms (xy interleaved).  nthreads<=1: scalar loop; else pthreads. */
+void	zo_rotate_const(const zo_params *p, int32_t x0, int32_t y0,
+		const uint32_t *phase, int32_t *xy, size_t n, int nthreads);
+void	zo_rotate(const zo_params *p, const int32_t *xy_in, const uint32_t *phase,
+		int32_t *xy_out, size_t n, int nthreads);
+void	zo_topolar(const zo_params *p, const int32_t *xy_in, int32_t *mag,
+		uint32_t *phase, size_t n, int nthreads);
+/* NCO: phase32_n = phase0 + (n0+i)*step mod 2^32 ; i_phase = phase32 >> (32-pw) */
+void	zo_nco_rotate(const zo_params *p, int32_t x0, int32_t y0, uint32_t phase0,
+		uint32_t step, uint64_t n0, int32_t *xy, size_t n, int nthreads);
+
+/* LUTs: sw/sintable.cpp:156-168 (full wave), :325-337 (quarter wave).
+ * Tables hold the OW-bit words as $readmemh would load them (masked to OW bits). */
+int	zo_sintable_build(int pw, int ow, uint32_t *tbl /* 2^pw */);
+int	zo_quarterwav_build(int pw, int ow, uint32_t *tbl /* 2^(pw-2) */);
+/* rtl/sintable.v:71-75 ; rtl/quarterwav.v:92-109.  Return o_val sign-extended from OW.
+ * phase is a 32-bit NCO word; the core sees i_phase = phase >> (32-pw). */
+int32_t	zo_sintable_lookup1(int pw, int ow, const uint32_t *tbl, uint32_t phase32);
+int32_t	zo_quarterwav_lookup1(int pw, int ow, const uint32_t *tbl, uint32_t phase32);
+void	zo_lut_sin(int pw, int ow, const uint32_t *tbl, const uint32_t *phase32,
+		int32_t *out, size_t n, int nthreads);
+void	zo_lut_qwav(int pw, int ow, const uint32_t *tbl, const uint32_t *phase32,
+		int32_t *out, size_t n, int nthreads);
+
+/* sw/hexfile.cpp:78-89 -- parse a $readmemh file written by hextable(). Returns #words. */
+long	zo_hex_load(const char *fname, uint32_t *words, long maxwords);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,387 @@
+"""cordic_b200 -- host-side Python mirror of libzcordic's C ABI (include/zcordic.h).
+
+The product is the shared library (hand-written sm_100a kernels behind a C ABI); this
+module only binds it with ctypes and moves pointers around.  PyTorch is used for device
+memory and streams, nothing else.  There is no CPU implementation here: every compute
+call goes to the CUDA kernels and raises ``ZcError`` if the library or a GPU is missing.
+
+Vocabulary follows the reference (ZipCPU/cordic): a *core* is configured with the
+generator's flags (``-i -o -x -p -n``, sw/main.cpp:139-232) and exposes the generated
+header constants (``IW OW NEXTRA WW PW NSTAGES GAIN ...``, rtl/cordic.h:46-59).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzcordic.so")
+ZC_MAX_STAGES = 64
+
+F_DEFAULT = 0
+F_FORCE_GENERIC = 1
+F_NO_SEED = 2
+F_FORCE_SEED = 4
+
+MODE_P2R, MODE_R2P = 0, 1
+
+
+class ZcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("zcordic error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Params(ctypes.Structure):
+    """zc_params (include/zcordic.h)."""
+    _fields_ = [
+        ("mode", ctypes.c_int32), ("iw", ctypes.c_int32), ("ow", ctypes.c_int32),
+        ("nextra", ctypes.c_int32), ("ww", ctypes.c_int32), ("pw", ctypes.c_int32),
+        ("nstages", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("angle", ctypes.c_uint32 * ZC_MAX_STAGES),
+        ("gain", ctypes.c_double), ("cordic_gain", ctypes.c_double), ("qvar", ctypes.c_double),
+        ("pvar_rad", ctypes.c_double), ("best_cnr", ctypes.c_double),
+    ]
+
+    def angles(self):
+        return [int(self.angle[k]) for k in range(self.nstages)]
+
+    def header(self):
+        """The constant set of the generated rtl/X.h, by the reference's names."""
+        h = dict(IW=self.iw, OW=self.ow, NEXTRA=self.nextra, WW=self.ww, PW=self.pw,
+                 NSTAGES=self.nstages, QUANTIZATION_VARIANCE=self.qvar,
+                 PHASE_VARIANCE_RAD=self.pvar_rad, GAIN=self.gain)
+        if self.mode == MODE_P2R:
+            h["BEST_POSSIBLE_CNR"] = self.best_cnr
+        return h
+
+
+_lib = None
+
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "zc_version": (ctypes.c_int, []),
+    "zc_strerror": (ctypes.c_char_p, [ctypes.c_int]),
+    "zc_last_error": (ctypes.c_char_p, []),
+    "zc_device_count": (ctypes.c_int, []),
+    "zc_launch_count": (ctypes.c_uint64, []),
+    "zc_derive_p2r": (ctypes.c_int, [ctypes.c_int] * 5 + [ctypes.POINTER(Params)]),
+    "zc_derive_r2p": (ctypes.c_int, [ctypes.c_int] * 5 + [ctypes.POINTER(Params)]),
+    "zc_derive_tbl": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 2),
+    "zc_derive_qtr": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 2),
+    "zc_lut_build_sintable": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "zc_lut_build_quarterwav": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "zc_rotate_const": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                       ctypes.c_void_p]),
+    "zc_rotate_const_ex": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_uint32]),
+    "zc_rotate": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                 ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "zc_rotate_ex": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32]),
+    "zc_topolar": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "zc_topolar_ex": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32]),
+    "zc_nco_rotate": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32,
+                                     ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t,
+                                     ctypes.c_int, ctypes.c_void_p]),
+    "zc_nco_rotate_ex": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32,
+                                        ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t,
+                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32]),
+    "zc_lut_sin": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "zc_lut_qwav": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "zc_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
+    "zc_host_free": (None, [ctypes.c_void_p]),
+    "zc_rotate_const_host": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
+    "zc_rotate_host": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_size_t, ctypes.c_int]),
+    "zc_topolar_host": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_size_t, ctypes.c_int]),
+    "zc_nco_rotate_host": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32,
+                                          ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t,
+                                          ctypes.c_int]),
+    "zc_lut_sin_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
+    "zc_lut_qwav_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
+}
+
+EXPORTED_SYMBOLS = sorted(_SIGNATURES)
+
+
+def lib():
+    """Loads libzcordic.so (building it with nvcc first if it is not there). Never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            from . import build as _build
+            _build.build()
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise ZcError(rc, (lib().zc_last_error() or b"").decode() or lib().zc_strerror(rc).decode())
+
+
+def launch_count():
+    return int(lib().zc_launch_count())
+
+
+# ---- configuration ------------------------------------------------------------------------
+
+def derive_p2r(iw=0, ow=0, xtra=2, pw=0, nstages=0):
+    """``gencordic -t p2r -i iw -o ow -x xtra [-p pw] [-n nstages]`` (sw/main.cpp:260-279)."""
+    p = Params()
+    _check(lib().zc_derive_p2r(iw or 0, ow or 0, xtra, pw or 0, nstages or 0, ctypes.byref(p)))
+    return p
+
+
+def derive_r2p(iw=0, ow=0, xtra=2, pw=0, nstages=0):
+    """``gencordic -t r2p ...`` (sw/main.cpp:312-328, sw/topolar.cpp:67-75)."""
+    p = Params()
+    _check(lib().zc_derive_r2p(iw or 0, ow or 0, xtra, pw or 0, nstages or 0, ctypes.byref(p)))
+    return p
+
+
+def derive_tbl(iw=0, pw=0, ow=0):
+    a, b = ctypes.c_int(), ctypes.c_int()
+    _check(lib().zc_derive_tbl(iw or 0, pw or 0, ow or 0, ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
+
+
+def derive_qtr(iw=0, pw=0, ow=0):
+    a, b = ctypes.c_int(), ctypes.c_int()
+    _check(lib().zc_derive_qtr(iw or 0, pw or 0, ow or 0, ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
+
+
+def build_sintable(pw, ow):
+    """The words of sintable.hex (sw/sintable.cpp:156-168) as a uint32 numpy array."""
+    tbl = np.empty(1 << pw, dtype=np.uint32) if 0 < pw < 31 else np.empty(1, dtype=np.uint32)
+    _check(lib().zc_lut_build_sintable(pw, ow, tbl.ctypes.data))
+    return tbl
+
+
+def build_quarterwav(pw, ow):
+    """The words of quarterwav.hex (sw/sintable.cpp:325-337) as a uint32 numpy array."""
+    tbl = np.empty(1 << (pw - 2), dtype=np.uint32) if 2 < pw < 31 else np.empty(1, dtype=np.uint32)
+    _check(lib().zc_lut_build_quarterwav(pw, ow, tbl.ctypes.data))
+    return tbl
+
+
+# ---- buffers --------------------------------------------------------------------------------
+
+def _torch():
+    import torch
+    return torch
+
+
+def _is_tensor(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _dev_ptr(t, nwords=None):
+    torch = _torch()
+    if not (_is_tensor(t) and t.is_cuda):
+        raise ZcError(-1, "expected a CUDA tensor")
+    if t.element_size() != 4 or not t.is_contiguous():
+        raise ZcError(-1, "expected a contiguous 32-bit tensor, got %s" % (t.dtype,))
+    if nwords is not None and t.numel() != nwords:
+        raise ZcError(-1, "tensor has %d words, expected %d" % (t.numel(), nwords))
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device_index, stream):
+    torch = _torch()
+    s = stream if stream is not None else torch.cuda.current_stream(device_index)
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def _host_ptr(a, nwords=None):
+    """numpy array or CPU (possibly pinned) torch tensor -> pointer."""
+    if _is_tensor(a):
+        if a.is_cuda or a.element_size() != 4 or not a.is_contiguous():
+            raise ZcError(-1, "expected a contiguous 32-bit CPU tensor")
+        if nwords is not None and a.numel() != nwords:
+            raise ZcError(-1, "tensor has %d words, expected %d" % (a.numel(), nwords))
+        return ctypes.c_void_p(a.data_ptr())
+    if not isinstance(a, np.ndarray) or a.dtype.itemsize != 4 or not a.flags["C_CONTIGUOUS"]:
+        raise ZcError(-1, "expected a C-contiguous 32-bit numpy array")
+    if nwords is not None and a.size != nwords:
+        raise ZcError(-1, "array has %d words, expected %d" % (a.size, nwords))
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class PinnedBuffer:
+    """Page-locked host memory from zc_host_alloc, exposed as a numpy array."""
+
+    def __init__(self, nwords, dtype=np.int32):
+        self.nbytes = int(nwords) * 4
+        self.ptr = lib().zc_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise ZcError(-5, (lib().zc_last_error() or b"").decode())
+        buf = (ctypes.c_char * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(nwords))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().zc_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---- cores ----------------------------------------------------------------------------------
+
+class Cordic:
+    """Rotation-mode core: the function of rtl/cordic.v (phase -> rotated (x, y))."""
+
+    def __init__(self, iw=0, ow=0, xtra=2, phase_bits=0, nstages=0):
+        self.params = derive_p2r(iw, ow, xtra, phase_bits, nstages)
+        for k, v in self.params.header().items():
+            setattr(self, k, v)
+
+    # device buffers -------------------------------------------------------------------
+    def rotate_const(self, x0, y0, phase, out=None, stream=None, flags=F_DEFAULT):
+        """(i_xval, i_yval) = (x0, y0) for every sample; ``phase``: CUDA tensor of n words.
+        Returns an int32 CUDA tensor [n, 2] of (o_xval, o_yval)."""
+        torch = _torch()
+        n = phase.numel()
+        dev = phase.device.index or 0
+        if out is None:
+            out = torch.empty((n, 2), dtype=torch.int32, device=phase.device)
+        _check(lib().zc_rotate_const_ex(ctypes.byref(self.params), int(x0), int(y0), _dev_ptr(phase),
+                                        _dev_ptr(out, 2 * n), n, dev, _stream_ptr(dev, stream), flags))
+        return out
+
+    def rotate(self, xy, phase, out=None, stream=None, flags=F_DEFAULT):
+        """Per-sample (i_xval, i_yval) = xy[i]; xy: int32 CUDA tensor [n, 2]."""
+        torch = _torch()
+        n = phase.numel()
+        dev = phase.device.index or 0
+        if out is None:
+            out = torch.empty((n, 2), dtype=torch.int32, device=phase.device)
+        _check(lib().zc_rotate_ex(ctypes.byref(self.params), _dev_ptr(xy, 2 * n), _dev_ptr(phase),
+                                  _dev_ptr(out, 2 * n), n, dev, _stream_ptr(dev, stream), flags))
+        return out
+
+    def nco(self, x0, y0, phase0, step, n, n0=0, out=None, device=None, stream=None, flags=F_DEFAULT):
+        """Streaming NCO: phase32 = phase0 + (n0+i)*step, i_phase = phase32 >> (32-PW)."""
+        torch = _torch()
+        if out is None:
+            out = torch.empty((n, 2), dtype=torch.int32, device=device if device is not None else "cuda")
+        dev = out.device.index or 0
+        _check(lib().zc_nco_rotate_ex(ctypes.byref(self.params), int(x0), int(y0), int(phase0) & 0xFFFFFFFF,
+                                      int(step) & 0xFFFFFFFF, int(n0), _dev_ptr(out, 2 * n), n, dev,
+                                      _stream_ptr(dev, stream), flags))
+        return out
+
+    # host buffers (end to end) -----------------------------------------------------------
+    def rotate_const_host(self, x0, y0, phase, out, device=0):
+        n = phase.size if isinstance(phase, np.ndarray) else phase.numel()
+        _check(lib().zc_rotate_const_host(ctypes.byref(self.params), int(x0), int(y0), _host_ptr(phase),
+                                          _host_ptr(out, 2 * n), n, device))
+        return out
+
+    def rotate_host(self, xy, phase, out, device=0):
+        n = phase.size if isinstance(phase, np.ndarray) else phase.numel()
+        _check(lib().zc_rotate_host(ctypes.byref(self.params), _host_ptr(xy, 2 * n), _host_ptr(phase),
+                                    _host_ptr(out, 2 * n), n, device))
+        return out
+
+    def nco_host(self, x0, y0, phase0, step, out, n0=0, device=0):
+        n = (out.size if isinstance(out, np.ndarray) else out.numel()) // 2
+        _check(lib().zc_nco_rotate_host(ctypes.byref(self.params), int(x0), int(y0), int(phase0) & 0xFFFFFFFF,
+                                        int(step) & 0xFFFFFFFF, int(n0), _host_ptr(out), n, device))
+        return out
+
+
+class Topolar:
+    """Vectoring-mode core: the function of rtl/topolar.v ((x, y) -> magnitude, phase)."""
+
+    def __init__(self, iw=0, ow=0, xtra=2, phase_bits=0, nstages=0):
+        self.params = derive_r2p(iw, ow, xtra, phase_bits, nstages)
+        for k, v in self.params.header().items():
+            setattr(self, k, v)
+
+    def topolar(self, xy, mag=None, phase=None, stream=None, flags=F_DEFAULT):
+        torch = _torch()
+        n = xy.numel() // 2
+        dev = xy.device.index or 0
+        if mag is None:
+            mag = torch.empty(n, dtype=torch.int32, device=xy.device)
+        if phase is None:
+            phase = torch.empty(n, dtype=torch.int32, device=xy.device)
+        _check(lib().zc_topolar_ex(ctypes.byref(self.params), _dev_ptr(xy, 2 * n), _dev_ptr(mag, n),
+                                   _dev_ptr(phase, n), n, dev, _stream_ptr(dev, stream), flags))
+        return mag, phase
+
+    def topolar_host(self, xy, mag, phase, device=0):
+        n = (xy.size if isinstance(xy, np.ndarray) else xy.numel()) // 2
+        _check(lib().zc_topolar_host(ctypes.byref(self.params), _host_ptr(xy), _host_ptr(mag, n),
+                                     _host_ptr(phase, n), n, device))
+        return mag, phase
+
+
+class _Lut:
+    QUARTER = False
+
+    def __init__(self, iw=0, phase_bits=0, ow=0):
+        derive = derive_qtr if self.QUARTER else derive_tbl
+        self.PW, self.OW = derive(iw, phase_bits, ow)
+        build = build_quarterwav if self.QUARTER else build_sintable
+        self.table = build(self.PW, self.OW)          # host copy == the $readmemh words
+        self._dev = {}
+
+    def _table_on(self, device):
+        torch = _torch()
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = torch.from_numpy(self.table.view(np.int32)).to(device)
+        return self._dev[key]
+
+    def lookup(self, phase32, out=None, stream=None):
+        """phase32: CUDA tensor of 32-bit NCO phase words; i_phase = phase32 >> (32-PW)."""
+        torch = _torch()
+        n = phase32.numel()
+        dev = phase32.device.index or 0
+        if out is None:
+            out = torch.empty(n, dtype=torch.int32, device=phase32.device)
+        fn = lib().zc_lut_qwav if self.QUARTER else lib().zc_lut_sin
+        _check(fn(self.PW, self.OW, _dev_ptr(self._table_on(phase32.device)), _dev_ptr(phase32),
+                  _dev_ptr(out, n), n, dev, _stream_ptr(dev, stream)))
+        return out
+
+    def lookup_host(self, phase32, out, device=0):
+        n = phase32.size if isinstance(phase32, np.ndarray) else phase32.numel()
+        fn = lib().zc_lut_qwav_host if self.QUARTER else lib().zc_lut_sin_host
+        _check(fn(self.PW, self.OW, self.table.ctypes.data, _host_ptr(phase32), _host_ptr(out, n), n, device))
+        return out
+
+
+class SinTable(_Lut):
+    """rtl/sintable.v: o_val = tbl[i_phase] (``gencordic -t tbl``)."""
+    QUARTER = False
+
+
+class QuarterWav(_Lut):
+    """rtl/quarterwav.v: quarter-wave table with index fold and negate (``gencordic -t qtr``)."""
+    QUARTER = True

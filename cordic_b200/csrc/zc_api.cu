@@ -1,0 +1,633 @@
+// zc_api.cu -- the C ABI of libzcordic (include/zcordic.h): argument checking, constant
+// preparation, kernel selection and launch, and the host-buffer pipelines.
+#include "zc_internal.h"
+#include "zc_kernels.cuh"
+#include "zc_seeded.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace zc {
+
+// ---- errors -----------------------------------------------------------------------------
+static thread_local char g_errbuf[512] = "";
+
+int set_error(int code, const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_errbuf, sizeof(g_errbuf), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define ZC_CUDA(call)                                                                      \
+	do {                                                                               \
+		cudaError_t e_ = (call);                                                   \
+		if (e_ != cudaSuccess)                                                     \
+			return set_error(ZC_ECUDA, "%s failed: %s (%s:%d)", #call,         \
+				cudaGetErrorString(e_), __FILE__, __LINE__);                \
+	} while (0)
+
+static std::atomic<uint64_t> g_launches{0};
+
+// ---- device bookkeeping -------------------------------------------------------------------
+struct DeviceInfo { int sms; bool ok; };
+static DeviceInfo g_dev[64];
+static std::mutex g_dev_mu;
+
+static int device_info(int device, DeviceInfo &out) {
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count <= 0) {
+		cudaGetLastError();
+		return set_error(ZC_ENODEV, "no usable CUDA device (%s); libzcordic has no CPU path",
+			e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+	}
+	if (device < 0 || device >= count || device >= 64)
+		return set_error(ZC_ENODEV, "device ordinal %d out of range [0,%d)", device, count);
+	std::lock_guard<std::mutex> lk(g_dev_mu);
+	if (!g_dev[device].ok) {
+		cudaDeviceProp prop;
+		ZC_CUDA(cudaGetDeviceProperties(&prop, device));
+		if (prop.major < 10)
+			return set_error(ZC_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only",
+				device, prop.major, prop.minor);
+		g_dev[device].sms = prop.multiProcessorCount;
+		g_dev[device].ok = true;
+	}
+	out = g_dev[device];
+	return ZC_OK;
+}
+
+// Makes `device` current for the scope and restores the caller's device afterwards.
+struct DeviceScope {
+	int prev = -1;
+	bool changed = false;
+	int enter(int device) {
+		ZC_CUDA(cudaGetDevice(&prev));
+		if (prev != device) {
+			ZC_CUDA(cudaSetDevice(device));
+			changed = true;
+		}
+		return ZC_OK;
+	}
+	~DeviceScope() { if (changed) cudaSetDevice(prev); }
+};
+
+// ---- parameter checks -----------------------------------------------------------------------
+int check_params(const zc_params *p, int want_mode) {
+	if (!p) return set_error(ZC_EINVAL, "NULL zc_params");
+	if (p->mode != want_mode)
+		return set_error(ZC_EINVAL, "zc_params.mode=%d but this entry point needs %s", p->mode,
+			want_mode == ZC_MODE_P2R ? "ZC_MODE_P2R (zc_derive_p2r)" : "ZC_MODE_R2P (zc_derive_r2p)");
+	if (p->pw < 3 || p->pw > 32 || p->ww < 2 || p->ww > 32 || p->iw < 1 || p->ow < 1 ||
+	    p->iw > p->ww || p->ow >= p->ww || p->nstages < 0 || p->nstages > ZC_MAX_STAGES)
+		return set_error(ZC_ERANGE, "unsupported configuration IW=%d OW=%d WW=%d PW=%d NSTAGES=%d",
+			p->iw, p->ow, p->ww, p->pw, p->nstages);
+	if (want_mode == ZC_MODE_P2R ? (p->ww - p->iw < 1) : (p->ww - p->iw < 2))
+		return set_error(ZC_ERANGE, "working width %d too small for IW=%d", p->ww, p->iw);
+	return ZC_OK;
+}
+
+// Stages i with cordic_angle[i]==0 or i>=WW are pass-through (rtl/cordic.v:253).  The angle
+// table is non-increasing, so the live stages are a prefix; its length is what we unroll.
+static int live_stages(const zc_params *p) {
+	int n = 0;
+	while (n < p->nstages && n < p->ww && p->angle[n] != 0) n++;
+	return n;
+}
+
+// True when 32-bit non-wrapping arithmetic provably equals the RTL's WW-bit wrapping
+// arithmetic for EVERY in-range input: the vector norm entering stage 0 is at most
+// sqrt(2)*2^(WW-2) (p2r: |e| <= 2^(WW-2) per axis; r2p: |e| <= 2^(WW-3) per axis, then the
+// 45-degree turn), each stage scales it by at most sqrt(1+4^-k) (total < 1.1645) and adds at
+// most sqrt(2) of truncation error, and the rounding add contributes 2^(D-1).
+static bool fast_path_is_exact(const zc_params *p) {
+	if (p->ww == 32) return true;	// int32 arithmetic *is* the WW-bit arithmetic
+	const double limit = (double)(1ull << (p->ww - 1)) - 1.0;
+	const double r0 = (p->mode == ZC_MODE_P2R ? 1.41421356237309515 : 1.0) * (double)(1ull << (p->ww - 2));
+	const int D = p->ww - p->ow;
+	const double bound = r0 * 1.1645 + 1.7 * (double)p->nstages + 2.0 + (double)(1ull << (D - 1));
+	return bound <= limit;
+}
+
+static void fill_consts(const zc_params *p, CoreConsts &c) {
+	std::memset(&c, 0, sizeof(c));
+	const int neff = live_stages(p);
+	c.neff = neff;
+	c.pshift = 32 - p->pw;
+	for (int k = 0; k < neff && k < 32; k++) {
+		c.pa[k] = p->angle[k] << c.pshift;
+		c.na[k] = (int32_t)(0u - c.pa[k]);
+	}
+	const int lsh = (p->mode == ZC_MODE_P2R) ? (p->ww - p->iw - 1) : (p->ww - p->iw - 2);
+	c.in_shl = 32 - p->iw;
+	c.in_shr = 32 - p->iw - lsh;
+	c.D = p->ww - p->ow;
+	c.do_round = (p->ww > p->ow + 1) ? 1 : 0;
+	c.rc = c.do_round ? (int32_t)((1u << (c.D - 1)) - 1u) : 0;
+	c.wsh = 32 - p->ww;
+	if (p->mode == ZC_MODE_R2P) {
+		// rtl/topolar.v:122-152; index = {i_xval[IW-1], i_yval[IW-1]}
+		const uint32_t E = 1u << (p->pw - 3);
+		c.e_phase[0] = (1u * E) << c.pshift;	// 2'b00 (default)
+		c.e_phase[1] = (7u * E) << c.pshift;	// 2'b01
+		c.e_phase[2] = (3u * E) << c.pshift;	// 2'b10
+		c.e_phase[3] = (5u * E) << c.pshift;	// 2'b11
+	}
+}
+
+static inline int wrap_to(int64_t v, int w) {
+	const int sh = 64 - w;
+	return (int)((int64_t)((uint64_t)v << sh) >> sh);
+}
+
+// The four quarter-turn pre-rotations of the extended constant input (rtl/cordic.v:85-86,131-188).
+static void fill_const_xy(const zc_params *p, int32_t x0, int32_t y0, CoreConsts &c) {
+	const int lsh = p->ww - p->iw - 1;
+	const int64_t ex = (int64_t)wrap_to(x0, p->iw) * ((int64_t)1 << lsh);
+	const int64_t ey = (int64_t)wrap_to(y0, p->iw) * ((int64_t)1 << lsh);
+	const int64_t xs[4] = {ex, -ey, -ex, ey}, ys[4] = {ey, ex, -ey, -ex};
+	for (int q = 0; q < 4; q++) {
+		c.cx[q] = wrap_to(xs[q], p->ww);
+		c.cy[q] = wrap_to(ys[q], p->ww);
+	}
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int grid_for(size_t work, const DeviceInfo &di, int per_sm) {
+	size_t blocks = (work + 255) / 256;
+	const size_t cap = (size_t)di.sms * (size_t)per_sm;
+	if (blocks > cap) blocks = cap;
+	if (blocks < 1) blocks = 1;
+	return (int)blocks;
+}
+
+static int post_launch(const char *what) {
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+		return set_error(ZC_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+	g_launches.fetch_add(1, std::memory_order_relaxed);
+	return ZC_OK;
+}
+
+// ---- rotation-mode launcher -------------------------------------------------------------------
+template <int SRC, int N>
+struct RotTable {
+	static void launch(int neff, int grid, cudaStream_t st, const int4 *ph, const int4 *xin, int4 *out,
+			size_t groups, const CoreConsts &c) {
+		if (neff == N) k_rotate<N, SRC><<<grid, 256, 0, st>>>(ph, xin, out, groups, c);
+		else RotTable<SRC, N - 1>::launch(neff, grid, st, ph, xin, out, groups, c);
+	}
+};
+template <int SRC>
+struct RotTable<SRC, 0> {
+	static void launch(int, int, cudaStream_t, const int4 *, const int4 *, int4 *, size_t, const CoreConsts &) {}
+};
+
+template <int N>
+struct VecTable {
+	static void launch(int neff, int grid, cudaStream_t st, const int4 *xin, int4 *mag, int4 *ph,
+			size_t groups, const CoreConsts &c) {
+		if (neff == N) k_topolar<N><<<grid, 256, 0, st>>>(xin, mag, ph, groups, c);
+		else VecTable<N - 1>::launch(neff, grid, st, xin, mag, ph, groups, c);
+	}
+};
+template <>
+struct VecTable<0> {
+	static void launch(int, int, cudaStream_t, const int4 *, int4 *, int4 *, size_t, const CoreConsts &) {}
+};
+
+template <int SRC>
+static int launch_rotate(const zc_params *p, CoreConsts &c, const uint32_t *phase, const int32_t *xy_in,
+		int32_t *xy_out, size_t n, int device, void *stream, uint32_t flags) {
+	DeviceInfo di;
+	int rc = device_info(device, di);
+	if (rc != ZC_OK) return rc;
+	if (n == 0) return ZC_OK;
+	DeviceScope scope;
+	if ((rc = scope.enter(device)) != ZC_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+
+	const bool vec_ok = aligned16(xy_out) && (SRC == SRC_NCO || aligned16(phase)) &&
+		(SRC != SRC_XY || aligned16(xy_in));
+	const bool fast = !(flags & ZC_F_FORCE_GENERIC) && fast_path_is_exact(p) && vec_ok &&
+		c.neff >= 1 && c.neff <= 32;
+	size_t done = 0;
+	if (fast) {
+		const size_t groups = n / 4;
+		if (groups) {
+			bool seeded = false;
+			if (SRC != SRC_XY && !(flags & ZC_F_NO_SEED)) {
+				rc = seeded_rotate_try<SRC>(p, c, phase, xy_out, groups, device, di.sms, st, flags, seeded);
+				if (rc != ZC_OK) return rc;
+				if (seeded) g_launches.fetch_add(1, std::memory_order_relaxed);
+			}
+			if (!seeded) {
+				RotTable<SRC, 32>::launch(c.neff, grid_for(groups, di, 16), st, (const int4 *)phase,
+					(const int4 *)xy_in, (int4 *)xy_out, groups, c);
+				if ((rc = post_launch("k_rotate")) != ZC_OK) return rc;
+			}
+			done = groups * 4;
+		}
+	}
+	if (done < n) {
+		CoreConsts t = c;
+		t.nco_n0 = c.nco_n0 + (uint32_t)done;
+		const size_t rest = n - done;
+		k_rotate_generic<SRC><<<grid_for(rest, di, 16), 256, 0, st>>>(
+			phase ? phase + done : nullptr, xy_in ? xy_in + 2 * done : nullptr,
+			xy_out + 2 * done, rest, t);
+		if ((rc = post_launch("k_rotate_generic")) != ZC_OK) return rc;
+	}
+	return ZC_OK;
+}
+
+static int launch_topolar(const zc_params *p, const int32_t *xy_in, int32_t *mag, uint32_t *phase,
+		size_t n, int device, void *stream, uint32_t flags) {
+	int rc = check_params(p, ZC_MODE_R2P);
+	if (rc != ZC_OK) return rc;
+	if (n && (!xy_in || !mag || !phase)) return set_error(ZC_EINVAL, "NULL buffer");
+	DeviceInfo di;
+	if ((rc = device_info(device, di)) != ZC_OK) return rc;
+	if (n == 0) return ZC_OK;
+	DeviceScope scope;
+	if ((rc = scope.enter(device)) != ZC_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	CoreConsts c;
+	fill_consts(p, c);
+	const bool fast = !(flags & ZC_F_FORCE_GENERIC) && fast_path_is_exact(p) && aligned16(xy_in) &&
+		aligned16(mag) && aligned16(phase) && c.neff >= 1 && c.neff <= 32;
+	size_t done = 0;
+	if (fast) {
+		const size_t groups = n / 4;
+		if (groups) {
+			VecTable<32>::launch(c.neff, grid_for(groups, di, 16), st, (const int4 *)xy_in, (int4 *)mag,
+				(int4 *)phase, groups, c);
+			if ((rc = post_launch("k_topolar")) != ZC_OK) return rc;
+			done = groups * 4;
+		}
+	}
+	if (done < n) {
+		const size_t rest = n - done;
+		k_topolar_generic<<<grid_for(rest, di, 16), 256, 0, st>>>(xy_in + 2 * done, mag + done,
+			phase + done, rest, c);
+		if ((rc = post_launch("k_topolar_generic")) != ZC_OK) return rc;
+	}
+	return ZC_OK;
+}
+
+template <bool QUARTER>
+static int launch_lut(int pw, int ow, const uint32_t *tbl, const uint32_t *phase32, int32_t *out,
+		size_t n, int device, void *stream) {
+	int rc = check_lut(QUARTER, pw, ow);
+	if (rc != ZC_OK) return rc;
+	if (!tbl || (n && (!phase32 || !out))) return set_error(ZC_EINVAL, "NULL buffer");
+	DeviceInfo di;
+	if ((rc = device_info(device, di)) != ZC_OK) return rc;
+	if (n == 0) return ZC_OK;
+	DeviceScope scope;
+	if ((rc = scope.enter(device)) != ZC_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	LutConsts c;
+	c.pshift = 32 - pw; c.osh = 32 - ow; c.pw = pw;
+	c.lowmask = QUARTER ? ((1u << (pw - 2)) - 1u) : 0u;
+	size_t done = 0;
+	if (aligned16(phase32) && aligned16(out) && n >= 4) {
+		const size_t groups = n / 4;
+		k_lut<QUARTER><<<grid_for(groups, di, 32), 256, 0, st>>>((const int4 *)phase32, (int4 *)out, tbl, groups, c);
+		if ((rc = post_launch("k_lut")) != ZC_OK) return rc;
+		done = groups * 4;
+	}
+	if (done < n) {
+		const size_t rest = n - done;
+		k_lut_scalar<QUARTER><<<grid_for(rest, di, 32), 256, 0, st>>>(phase32 + done, out + done, tbl, rest, c);
+		if ((rc = post_launch("k_lut_scalar")) != ZC_OK) return rc;
+	}
+	return ZC_OK;
+}
+
+// ---- host-buffer pipeline ---------------------------------------------------------------------
+// Streams chunks H2D -> kernel -> D2H through NBUF device buffers on three streams so copies in
+// both directions overlap compute.  `launch(chunk_index_offset, count, din0, din1, dout0, dout1,
+// stream)` enqueues the device entry point for one chunk.
+struct Lane { size_t bytes_per_sample; const char *host_in; char *host_out; };
+
+template <class Launch>
+static int host_pipeline(int device, size_t n, const Lane in[2], const Lane out[2], Launch launch) {
+	DeviceInfo di;
+	int rc = device_info(device, di);
+	if (rc != ZC_OK) return rc;
+	if (n == 0) return ZC_OK;
+	DeviceScope scope;
+	if ((rc = scope.enter(device)) != ZC_OK) return rc;
+	constexpr int NBUF = 3;
+	const size_t chunk = (n < ((size_t)4 << 20)) ? ((n + 3) & ~(size_t)3) : ((size_t)4 << 20);
+	size_t per_buf = 0;
+	for (int k = 0; k < 2; k++) per_buf += (in[k].bytes_per_sample + out[k].bytes_per_sample) * chunk;
+	// every sub-buffer 256-byte aligned
+	per_buf += 4 * 256;
+	char *pool = nullptr;
+	cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+	cudaEvent_t ev_in[NBUF] = {}, ev_k[NBUF] = {}, ev_out[NBUF] = {};
+	auto cleanup = [&]() {
+		for (int b = 0; b < NBUF; b++) {
+			if (ev_in[b]) cudaEventDestroy(ev_in[b]);
+			if (ev_k[b]) cudaEventDestroy(ev_k[b]);
+			if (ev_out[b]) cudaEventDestroy(ev_out[b]);
+		}
+		if (s_in) cudaStreamDestroy(s_in);
+		if (s_k) cudaStreamDestroy(s_k);
+		if (s_out) cudaStreamDestroy(s_out);
+		if (pool) cudaFree(pool);
+	};
+#define ZC_PIPE(call)                                                                          \
+	do {                                                                                   \
+		cudaError_t e_ = (call);                                                       \
+		if (e_ != cudaSuccess) {                                                       \
+			cudaDeviceSynchronize();                                               \
+			cleanup();                                                             \
+			return set_error(ZC_ECUDA, "%s failed: %s (%s:%d)", #call,             \
+				cudaGetErrorString(e_), __FILE__, __LINE__);                    \
+		}                                                                              \
+	} while (0)
+	ZC_PIPE(cudaMalloc((void **)&pool, per_buf * NBUF));
+	ZC_PIPE(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+	ZC_PIPE(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+	ZC_PIPE(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+	for (int b = 0; b < NBUF; b++) {
+		ZC_PIPE(cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming));
+		ZC_PIPE(cudaEventCreateWithFlags(&ev_k[b], cudaEventDisableTiming));
+		ZC_PIPE(cudaEventCreateWithFlags(&ev_out[b], cudaEventDisableTiming));
+	}
+	auto sub = [&](int b, int which) -> char * {	// which: 0,1 = in ; 2,3 = out
+		size_t off = 0;
+		const size_t sizes[4] = {in[0].bytes_per_sample * chunk, in[1].bytes_per_sample * chunk,
+			out[0].bytes_per_sample * chunk, out[1].bytes_per_sample * chunk};
+		for (int k = 0; k < which; k++) off += (sizes[k] + 255) & ~(size_t)255;
+		return pool + per_buf * b + off;
+	};
+	size_t ci = 0;
+	for (size_t off = 0; off < n; off += chunk, ci++) {
+		const int b = (int)(ci % NBUF);
+		const size_t cnt = (n - off < chunk) ? (n - off) : chunk;
+		if (ci >= NBUF) {	// the buffer's previous contents must have left the device
+			ZC_PIPE(cudaStreamWaitEvent(s_in, ev_out[b], 0));
+		}
+		for (int k = 0; k < 2; k++)
+			if (in[k].bytes_per_sample)
+				ZC_PIPE(cudaMemcpyAsync(sub(b, k), in[k].host_in + off * in[k].bytes_per_sample,
+					cnt * in[k].bytes_per_sample, cudaMemcpyHostToDevice, s_in));
+		ZC_PIPE(cudaEventRecord(ev_in[b], s_in));
+		ZC_PIPE(cudaStreamWaitEvent(s_k, ev_in[b], 0));
+		if (ci >= NBUF) ZC_PIPE(cudaStreamWaitEvent(s_k, ev_out[b], 0));
+		rc = launch(off, cnt, sub(b, 0), sub(b, 1), sub(b, 2), sub(b, 3), s_k);
+		if (rc != ZC_OK) {
+			cudaDeviceSynchronize();
+			cleanup();
+			return rc;
+		}
+		ZC_PIPE(cudaEventRecord(ev_k[b], s_k));
+		ZC_PIPE(cudaStreamWaitEvent(s_out, ev_k[b], 0));
+		for (int k = 0; k < 2; k++)
+			if (out[k].bytes_per_sample)
+				ZC_PIPE(cudaMemcpyAsync(out[k].host_out + off * out[k].bytes_per_sample, sub(b, 2 + k),
+					cnt * out[k].bytes_per_sample, cudaMemcpyDeviceToHost, s_out));
+		ZC_PIPE(cudaEventRecord(ev_out[b], s_out));
+	}
+	ZC_PIPE(cudaStreamSynchronize(s_out));
+	ZC_PIPE(cudaStreamSynchronize(s_k));
+	ZC_PIPE(cudaStreamSynchronize(s_in));
+#undef ZC_PIPE
+	cleanup();
+	return ZC_OK;
+}
+
+} // namespace zc
+
+using namespace zc;
+
+// =============================== extern "C" ===================================================
+extern "C" {
+
+int zc_version(void) { return ZC_VERSION_MAJOR * 1000 + ZC_VERSION_MINOR; }
+
+const char *zc_strerror(int status) {
+	switch (status) {
+	case ZC_OK: return "ok";
+	case ZC_EINVAL: return "invalid argument";
+	case ZC_ERANGE: return "configuration out of range";
+	case ZC_ECUDA: return "CUDA error";
+	case ZC_ENODEV: return "no usable CUDA device";
+	case ZC_ENOMEM: return "out of memory";
+	default: return "unknown status";
+	}
+}
+
+const char *zc_last_error(void) { return g_errbuf; }
+
+int zc_device_count(void) {
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		return set_error(ZC_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+	}
+	return count;
+}
+
+uint64_t zc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int zc_derive_p2r(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *out) {
+	return derive_p2r(iw, ow, xtra_user, pw, nstages, out);
+}
+int zc_derive_r2p(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *out) {
+	return derive_r2p(iw, ow, xtra_user, pw, nstages, out);
+}
+int zc_derive_tbl(int iw, int pw, int ow, int *pw_out, int *ow_out) {
+	return derive_lut(false, iw, pw, ow, pw_out, ow_out);
+}
+int zc_derive_qtr(int iw, int pw, int ow, int *pw_out, int *ow_out) {
+	return derive_lut(true, iw, pw, ow, pw_out, ow_out);
+}
+int zc_lut_build_sintable(int pw, int ow, uint32_t *tbl) { return build_sintable(pw, ow, tbl); }
+int zc_lut_build_quarterwav(int pw, int ow, uint32_t *tbl) { return build_quarterwav(pw, ow, tbl); }
+
+int zc_rotate_const_ex(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int32_t *xy,
+		size_t n, int device, void *stream, uint32_t flags) {
+	int rc = check_params(p, ZC_MODE_P2R);
+	if (rc != ZC_OK) return rc;
+	if (n && (!phase || !xy)) return set_error(ZC_EINVAL, "NULL buffer");
+	CoreConsts c;
+	fill_consts(p, c);
+	fill_const_xy(p, x0, y0, c);
+	return launch_rotate<SRC_CONST>(p, c, phase, nullptr, xy, n, device, stream, flags);
+}
+int zc_rotate_const(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int32_t *xy,
+		size_t n, int device, void *stream) {
+	return zc_rotate_const_ex(p, x0, y0, phase, xy, n, device, stream, ZC_F_DEFAULT);
+}
+
+int zc_rotate_ex(const zc_params *p, const int32_t *xy_in, const uint32_t *phase, int32_t *xy_out,
+		size_t n, int device, void *stream, uint32_t flags) {
+	int rc = check_params(p, ZC_MODE_P2R);
+	if (rc != ZC_OK) return rc;
+	if (n && (!phase || !xy_in || !xy_out)) return set_error(ZC_EINVAL, "NULL buffer");
+	CoreConsts c;
+	fill_consts(p, c);
+	return launch_rotate<SRC_XY>(p, c, phase, xy_in, xy_out, n, device, stream, flags);
+}
+int zc_rotate(const zc_params *p, const int32_t *xy_in, const uint32_t *phase, int32_t *xy_out,
+		size_t n, int device, void *stream) {
+	return zc_rotate_ex(p, xy_in, phase, xy_out, n, device, stream, ZC_F_DEFAULT);
+}
+
+int zc_topolar_ex(const zc_params *p, const int32_t *xy_in, int32_t *mag, uint32_t *phase, size_t n,
+		int device, void *stream, uint32_t flags) {
+	return launch_topolar(p, xy_in, mag, phase, n, device, stream, flags);
+}
+int zc_topolar(const zc_params *p, const int32_t *xy_in, int32_t *mag, uint32_t *phase, size_t n,
+		int device, void *stream) {
+	return launch_topolar(p, xy_in, mag, phase, n, device, stream, ZC_F_DEFAULT);
+}
+
+int zc_nco_rotate_ex(const zc_params *p, int32_t x0, int32_t y0, uint32_t phase0, uint32_t step,
+		uint64_t n0, int32_t *xy, size_t n, int device, void *stream, uint32_t flags) {
+	int rc = check_params(p, ZC_MODE_P2R);
+	if (rc != ZC_OK) return rc;
+	if (n && !xy) return set_error(ZC_EINVAL, "NULL buffer");
+	CoreConsts c;
+	fill_consts(p, c);
+	fill_const_xy(p, x0, y0, c);
+	c.nco_phase0 = phase0; c.nco_step = step; c.nco_n0 = (uint32_t)n0;	// arithmetic is mod 2^32
+	return launch_rotate<SRC_NCO>(p, c, nullptr, nullptr, xy, n, device, stream, flags);
+}
+int zc_nco_rotate(const zc_params *p, int32_t x0, int32_t y0, uint32_t phase0, uint32_t step,
+		uint64_t n0, int32_t *xy, size_t n, int device, void *stream) {
+	return zc_nco_rotate_ex(p, x0, y0, phase0, step, n0, xy, n, device, stream, ZC_F_DEFAULT);
+}
+
+int zc_lut_sin(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int32_t *out, size_t n,
+		int device, void *stream) {
+	return launch_lut<false>(pw, ow, tbl_dev, phase32, out, n, device, stream);
+}
+int zc_lut_qwav(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int32_t *out, size_t n,
+		int device, void *stream) {
+	return launch_lut<true>(pw, ow, tbl_dev, phase32, out, n, device, stream);
+}
+
+// ---- host buffers --------------------------------------------------------------------------
+void *zc_host_alloc(size_t bytes) {
+	void *p = nullptr;
+	cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		set_error(ZC_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+		return nullptr;
+	}
+	return p;
+}
+void zc_host_free(void *ptr) {
+	if (ptr) cudaFreeHost(ptr);
+}
+
+int zc_rotate_const_host(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int32_t *xy,
+		size_t n, int device) {
+	int rc = check_params(p, ZC_MODE_P2R);
+	if (rc != ZC_OK) return rc;
+	if (n && (!phase || !xy)) return set_error(ZC_EINVAL, "NULL buffer");
+	const Lane in[2] = {{4, (const char *)phase, nullptr}, {0, nullptr, nullptr}};
+	const Lane out[2] = {{8, nullptr, (char *)xy}, {0, nullptr, nullptr}};
+	return host_pipeline(device, n, in, out,
+		[&](size_t, size_t cnt, char *i0, char *, char *o0, char *, cudaStream_t st) {
+			return zc_rotate_const_ex(p, x0, y0, (const uint32_t *)i0, (int32_t *)o0, cnt, device, st, ZC_F_DEFAULT);
+		});
+}
+
+int zc_rotate_host(const zc_params *p, const int32_t *xy_in, const uint32_t *phase, int32_t *xy_out,
+		size_t n, int device) {
+	int rc = check_params(p, ZC_MODE_P2R);
+	if (rc != ZC_OK) return rc;
+	if (n && (!phase || !xy_in || !xy_out)) return set_error(ZC_EINVAL, "NULL buffer");
+	const Lane in[2] = {{4, (const char *)phase, nullptr}, {8, (const char *)xy_in, nullptr}};
+	const Lane out[2] = {{8, nullptr, (char *)xy_out}, {0, nullptr, nullptr}};
+	return host_pipeline(device, n, in, out,
+		[&](size_t, size_t cnt, char *i0, char *i1, char *o0, char *, cudaStream_t st) {
+			return zc_rotate_ex(p, (const int32_t *)i1, (const uint32_t *)i0, (int32_t *)o0, cnt, device, st, ZC_F_DEFAULT);
+		});
+}
+
+int zc_topolar_host(const zc_params *p, const int32_t *xy_in, int32_t *mag, uint32_t *phase, size_t n,
+		int device) {
+	int rc = check_params(p, ZC_MODE_R2P);
+	if (rc != ZC_OK) return rc;
+	if (n && (!xy_in || !mag || !phase)) return set_error(ZC_EINVAL, "NULL buffer");
+	const Lane in[2] = {{8, (const char *)xy_in, nullptr}, {0, nullptr, nullptr}};
+	const Lane out[2] = {{4, nullptr, (char *)mag}, {4, nullptr, (char *)phase}};
+	return host_pipeline(device, n, in, out,
+		[&](size_t, size_t cnt, char *i0, char *, char *o0, char *o1, cudaStream_t st) {
+			return zc_topolar_ex(p, (const int32_t *)i0, (int32_t *)o0, (uint32_t *)o1, cnt, device, st, ZC_F_DEFAULT);
+		});
+}
+
+int zc_nco_rotate_host(const zc_params *p, int32_t x0, int32_t y0, uint32_t phase0, uint32_t step,
+		uint64_t n0, int32_t *xy, size_t n, int device) {
+	int rc = check_params(p, ZC_MODE_P2R);
+	if (rc != ZC_OK) return rc;
+	if (n && !xy) return set_error(ZC_EINVAL, "NULL buffer");
+	const Lane in[2] = {{0, nullptr, nullptr}, {0, nullptr, nullptr}};
+	const Lane out[2] = {{8, nullptr, (char *)xy}, {0, nullptr, nullptr}};
+	return host_pipeline(device, n, in, out,
+		[&](size_t off, size_t cnt, char *, char *, char *o0, char *, cudaStream_t st) {
+			return zc_nco_rotate_ex(p, x0, y0, phase0, step, n0 + off, (int32_t *)o0, cnt, device, st, ZC_F_DEFAULT);
+		});
+}
+
+static int lut_host(bool quarter, int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32,
+		int32_t *out, size_t n, int device) {
+	int rc = check_lut(quarter, pw, ow);
+	if (rc != ZC_OK) return rc;
+	if (!tbl_host || (n && (!phase32 || !out))) return set_error(ZC_EINVAL, "NULL buffer");
+	DeviceInfo di;
+	if ((rc = device_info(device, di)) != ZC_OK) return rc;
+	if (n == 0) return ZC_OK;
+	uint32_t *tbl_dev = nullptr;
+	const size_t words = quarter ? ((size_t)1 << (pw - 2)) : ((size_t)1 << pw);
+	{
+		DeviceScope scope;
+		if ((rc = scope.enter(device)) != ZC_OK) return rc;
+		ZC_CUDA(cudaMalloc((void **)&tbl_dev, words * 4));
+		cudaError_t e = cudaMemcpy(tbl_dev, tbl_host, words * 4, cudaMemcpyHostToDevice);
+		if (e != cudaSuccess) {
+			cudaFree(tbl_dev);
+			return set_error(ZC_ECUDA, "table upload failed: %s", cudaGetErrorString(e));
+		}
+	}
+	const Lane in[2] = {{4, (const char *)phase32, nullptr}, {0, nullptr, nullptr}};
+	const Lane outl[2] = {{4, nullptr, (char *)out}, {0, nullptr, nullptr}};
+	rc = host_pipeline(device, n, in, outl,
+		[&](size_t, size_t cnt, char *i0, char *, char *o0, char *, cudaStream_t st) {
+			return quarter ? zc_lut_qwav(pw, ow, tbl_dev, (const uint32_t *)i0, (int32_t *)o0, cnt, device, st)
+				       : zc_lut_sin(pw, ow, tbl_dev, (const uint32_t *)i0, (int32_t *)o0, cnt, device, st);
+		});
+	{
+		DeviceScope scope;
+		if (scope.enter(device) == ZC_OK) cudaFree(tbl_dev);
+	}
+	return rc;
+}
+
+int zc_lut_sin_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int32_t *out,
+		size_t n, int device) {
+	return lut_host(false, pw, ow, tbl_host, phase32, out, n, device);
+}
+int zc_lut_qwav_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int32_t *out,
+		size_t n, int device) {
+	return lut_host(true, pw, ow, tbl_host, phase32, out, n, device);
+}
+
+} // extern "C"

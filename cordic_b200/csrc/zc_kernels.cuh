@@ -1,0 +1,353 @@
+// zc_kernels.cuh -- device code of the zcordic engine (sm_100a).
+//
+// One sample per lane; the micro-rotation stages are fully unrolled in registers; the
+// arctan table and every other per-configuration constant travel in the kernel parameter
+// block, i.e. the constant bank, so stage operands are read as c[0x0][..] immediates.
+// The arithmetic is integer shift-add (rtl/cordic.v:253-280, rtl/topolar.v:217-243): there
+// is no contraction here for tensor cores to do.
+//
+// Representation (why the fast kernels are exact):
+//   * phase is kept LEFT-justified in 32 bits (phase << (32-PW)), as are the angles, so
+//     PW-bit modular arithmetic is plain u32 arithmetic and the "negative phase" test
+//     ph[PW-1] (rtl/cordic.v:265) is the sign bit;
+//   * x/y are kept right-justified, sign-extended in int32.  The RTL registers are WW bits
+//     and wrap; the host only selects a fast kernel when it has proved that no in-range
+//     input can exceed WW bits (zc_api.cu: fast_path_is_exact), otherwise the generic
+//     kernel below, which wraps after every operation, is used.
+#ifndef ZC_KERNELS_CUH
+#define ZC_KERNELS_CUH
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace zc {
+
+enum Source { SRC_CONST = 0, SRC_XY = 1, SRC_NCO = 2 };
+
+// Per-launch constants (kernel parameter => constant bank).
+struct CoreConsts {
+	int32_t  na[32];	// -(cordic_angle[k] << (32-PW)) for the stages that are not pass-through
+	uint32_t pa[32];	//  (cordic_angle[k] << (32-PW))
+	int32_t  cx[4], cy[4];	// SRC_CONST/NCO: extended (x0,y0) after each of the 4 quarter-turn pre-rotations
+	uint32_t e_phase[4];	// topolar: pre-rotation phases 1E,3E,5E,7E left-justified, indexed by {xneg,yneg}
+	int32_t  pshift;	// 32-PW
+	int32_t  in_shl;	// 32-IW: discards the bits above the IW-bit port
+	int32_t  in_shr;	// arithmetic shift that sign-extends and leaves the (WW-IW-1|2) zero LSBs
+	int32_t  D;		// WW-OW
+	int32_t  rc;		// 2^(D-1)-1 when the core rounds (WW > OW+1), else 0
+	int32_t  do_round;
+	int32_t  neff;		// number of live stages (generic kernel)
+	int32_t  wsh;		// 32-WW (generic kernel: wrap)
+	uint32_t nco_phase0, nco_step, nco_n0;
+};
+
+__device__ __forceinline__ int imad(int a, int b, int c) {
+	int r;
+	asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+	return r;
+}
+
+// ---- one micro-rotation, rotation mode (rtl/cordic.v:263-279) ---------------------------
+// d = +1 when the residual phase is >= 0, else -1.  x' = x - d*(y>>>k); y' = y + d*(x>>>k);
+// p' = p - d*angle.  Both updates read the OLD x and y.  Written so that the two multiplies
+// by +-1 go to the FMA pipe (IMAD) and the shifts/sign tests to the ALU pipe.
+template <int K, int FORM>
+__device__ __forceinline__ void rot_step(int &x, int &y, int &p, const int na) {
+	constexpr int S = (K + 1 > 31) ? 31 : (K + 1);
+	const int md = p >> 31;
+	int d, nd;
+	if (FORM == 0) {
+		d = md | 1;
+		nd = ~md | 1;
+	} else {
+		d = imad(md, 2, 1);
+		nd = imad(md, -2, -1);
+	}
+	const int sy = y >> S, sx = x >> S;
+	const int x1 = imad(sy, nd, x);
+	const int y1 = imad(sx, d, y);
+	p = imad(d, na, p);
+	x = x1;
+	y = y1;
+}
+
+// ---- one micro-rotation, vectoring mode (rtl/topolar.v:227-243) --------------------------
+// s = -1 when y is below the axis (yv[WW-1]), else +1 (y == 0 counts as above).
+// x' = x + s*(y>>>k); y' = y - s*(x>>>k); ph' = ph + s*angle.
+template <int K, int FORM>
+__device__ __forceinline__ void vec_step(int &x, int &y, uint32_t &ph, const int pa) {
+	constexpr int S = (K + 1 > 31) ? 31 : (K + 1);
+	const int md = y >> 31;
+	int s, ns;
+	if (FORM == 0) {
+		s = md | 1;
+		ns = ~md | 1;
+	} else {
+		s = imad(md, 2, 1);
+		ns = imad(md, -2, -1);
+	}
+	const int sy = y >> S, sx = x >> S;
+	const int x1 = imad(sy, s, x);
+	const int y1 = imad(sx, ns, y);
+	ph = (uint32_t)imad(s, pa, (int)ph);
+	x = x1;
+	y = y1;
+}
+
+template <int N, int K = 0>
+struct Unroll {
+	static __device__ __forceinline__ void rot(int &x, int &y, int &p, const CoreConsts &c) {
+		rot_step<K, (K & 1)>(x, y, p, c.na[K]);
+		Unroll<N, K + 1>::rot(x, y, p, c);
+	}
+	static __device__ __forceinline__ void vec(int &x, int &y, uint32_t &ph, const CoreConsts &c) {
+		vec_step<K, (K & 1)>(x, y, ph, (int)c.pa[K]);
+		Unroll<N, K + 1>::vec(x, y, ph, c);
+	}
+};
+template <int N>
+struct Unroll<N, N> {
+	static __device__ __forceinline__ void rot(int &, int &, int &, const CoreConsts &) {}
+	static __device__ __forceinline__ void vec(int &, int &, uint32_t &, const CoreConsts &) {}
+};
+
+// Convergent rounding and truncation to OW bits (rtl/cordic.v:290-295,311-312).
+__device__ __forceinline__ int round_out(int v, const CoreConsts &c) {
+	const int b = (v >> c.D) & c.do_round;
+	return (v + c.rc + b) >> c.D;
+}
+
+// Octant pre-rotation of the phase (rtl/cordic.v:131-188): returns the quarter-turn count q
+// and leaves the residual phase in [-45,45) degrees, left-justified.
+__device__ __forceinline__ int octant(uint32_t P, int &p) {
+	const uint32_t t = P + 0x20000000u;
+	p = (int)((t & 0x3fffffffu) - 0x20000000u);
+	return (int)(t >> 30);
+}
+
+__device__ __forceinline__ void quarter_turn(int q, int ex, int ey, int &x, int &y) {
+	// q=0:(ex,ey) 1:(-ey,ex) 2:(-ex,-ey) 3:(ey,-ex)
+	const int a = (q & 1) ? -ey : ex;
+	const int b = (q & 1) ? ex : ey;
+	x = (q & 2) ? -a : a;
+	y = (q & 2) ? -b : b;
+}
+
+__device__ __forceinline__ int4 ldg_stream(const int4 *p) {
+	int4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+		: "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ void stg_stream(int4 *p, const int4 v) {
+	asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
+		:: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---- rotation mode, fast path: 4 samples per thread, 128-bit loads/stores ------------------
+template <int NEFF, int SRC>
+__global__ void __launch_bounds__(256)
+k_rotate(const int4 *__restrict__ phase4, const int4 *__restrict__ xyin4,
+		int4 *__restrict__ xyout4, size_t ngroups, const __grid_constant__ CoreConsts c) {
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+		uint32_t P[4];
+		int x[4], y[4];
+		if (SRC == SRC_NCO) {
+			const uint32_t base = c.nco_phase0 + (c.nco_n0 + (uint32_t)(g << 2)) * c.nco_step;
+			const uint32_t keep = ~((1u << c.pshift) - 1u);	// i_phase = phase32 >> (32-PW)
+#pragma unroll
+			for (int s = 0; s < 4; s++)
+				P[s] = (base + (uint32_t)s * c.nco_step) & keep;
+		} else {
+			const int4 pv = ldg_stream(phase4 + g);
+			P[0] = (uint32_t)pv.x << c.pshift; P[1] = (uint32_t)pv.y << c.pshift;
+			P[2] = (uint32_t)pv.z << c.pshift; P[3] = (uint32_t)pv.w << c.pshift;
+		}
+		int ex[4], ey[4];
+		if (SRC == SRC_XY) {
+			const int4 a = ldg_stream(xyin4 + 2 * g), b = ldg_stream(xyin4 + 2 * g + 1);
+			const int raw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+			for (int s = 0; s < 4; s++) {
+				ex[s] = (raw[2 * s] << c.in_shl) >> c.in_shr;
+				ey[s] = (raw[2 * s + 1] << c.in_shl) >> c.in_shr;
+			}
+		}
+		int ox[4], oy[4];
+#pragma unroll
+		for (int s = 0; s < 4; s++) {
+			int p;
+			const int q = octant(P[s], p);
+			if (SRC == SRC_XY) {
+				quarter_turn(q, ex[s], ey[s], x[s], y[s]);
+			} else {
+				const int xa = (q & 1) ? c.cx[1] : c.cx[0], ya = (q & 1) ? c.cy[1] : c.cy[0];
+				const int xb = (q & 1) ? c.cx[3] : c.cx[2], yb = (q & 1) ? c.cy[3] : c.cy[2];
+				x[s] = (q & 2) ? xb : xa;
+				y[s] = (q & 2) ? yb : ya;
+			}
+			Unroll<NEFF>::rot(x[s], y[s], p, c);
+			ox[s] = round_out(x[s], c);
+			oy[s] = round_out(y[s], c);
+		}
+		stg_stream(xyout4 + 2 * g, make_int4(ox[0], oy[0], ox[1], oy[1]));
+		stg_stream(xyout4 + 2 * g + 1, make_int4(ox[2], oy[2], ox[3], oy[3]));
+	}
+}
+
+// ---- vectoring mode, fast path ---------------------------------------------------------------
+template <int NEFF>
+__global__ void __launch_bounds__(256)
+k_topolar(const int4 *__restrict__ xyin4, int4 *__restrict__ mag4, int4 *__restrict__ ph4,
+		size_t ngroups, const __grid_constant__ CoreConsts c) {
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+		const int4 a = ldg_stream(xyin4 + 2 * g), b = ldg_stream(xyin4 + 2 * g + 1);
+		const int raw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+		int om[4], op[4];
+#pragma unroll
+		for (int s = 0; s < 4; s++) {
+			// rtl/topolar.v:83-84: two sign bits, the input, WW-IW-2 zeros
+			const int ex = (raw[2 * s] << c.in_shl) >> c.in_shr;
+			const int ey = (raw[2 * s + 1] << c.in_shl) >> c.in_shr;
+			// rtl/topolar.v:122-152: a +-45 degree turn selected by the two input signs
+			const int xn = ex >> 31, yn = ey >> 31;		// 0 / -1
+			const int sum = ex + ey, dif = ex - ey;
+			//  {x>=0,y>=0}: ( sum, -dif)  {x>=0,y<0}: ( dif,  sum)
+			//  {x<0, y>=0}: (-dif, -sum)  {x<0, y<0}: (-sum,  dif)
+			int x = yn ? dif : sum;
+			int y = yn ? sum : -dif;
+			x = xn ? -((yn) ? sum : dif) : x;
+			y = xn ? ((yn) ? dif : -sum) : y;
+			uint32_t ph = c.e_phase[(xn & 2) | (yn & 1)];
+			Unroll<NEFF>::vec(x, y, ph, c);
+			om[s] = round_out(x, c);
+			op[s] = (int)(ph >> c.pshift);
+		}
+		stg_stream(mag4 + g, make_int4(om[0], om[1], om[2], om[3]));
+		stg_stream(ph4 + g, make_int4(op[0], op[1], op[2], op[3]));
+	}
+}
+
+// ---- generic kernels: any configuration, any alignment, WW-bit wrap modelled ----------------
+__device__ __forceinline__ int wrapw(int v, int wsh) { return (int)((uint32_t)v << wsh) >> wsh; }
+
+template <int SRC>
+__global__ void __launch_bounds__(256)
+k_rotate_generic(const uint32_t *__restrict__ phase, const int32_t *__restrict__ xyin,
+		int32_t *__restrict__ xyout, size_t n, const __grid_constant__ CoreConsts c) {
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		uint32_t P;
+		if (SRC == SRC_NCO) {
+			const uint32_t keep = ~((1u << c.pshift) - 1u);
+			P = (c.nco_phase0 + (c.nco_n0 + (uint32_t)i) * c.nco_step) & keep;
+		} else {
+			P = phase[i] << c.pshift;
+		}
+		int p;
+		const int q = octant(P, p);
+		int x, y;
+		if (SRC == SRC_XY) {
+			const int ex = (xyin[2 * i] << c.in_shl) >> c.in_shr;
+			const int ey = (xyin[2 * i + 1] << c.in_shl) >> c.in_shr;
+			quarter_turn(q, ex, ey, x, y);
+			x = wrapw(x, c.wsh); y = wrapw(y, c.wsh);
+		} else {
+			x = c.cx[q]; y = c.cy[q];
+		}
+		for (int k = 0; k < c.neff; k++) {
+			const int sh = (k + 1 > 31) ? 31 : (k + 1);
+			const int sy = y >> sh, sx = x >> sh;
+			if (p < 0) {
+				x = wrapw(x + sy, c.wsh); y = wrapw(y - sx, c.wsh); p += (int)c.pa[k];
+			} else {
+				x = wrapw(x - sy, c.wsh); y = wrapw(y + sx, c.wsh); p -= (int)c.pa[k];
+			}
+		}
+		const int bx = (x >> c.D) & c.do_round, by = (y >> c.D) & c.do_round;
+		xyout[2 * i] = wrapw(x + c.rc + bx, c.wsh) >> c.D;
+		xyout[2 * i + 1] = wrapw(y + c.rc + by, c.wsh) >> c.D;
+	}
+}
+
+__global__ void __launch_bounds__(256)
+k_topolar_generic(const int32_t *__restrict__ xyin, int32_t *__restrict__ mag,
+		uint32_t *__restrict__ phout, size_t n, const __grid_constant__ CoreConsts c) {
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const int ex = (xyin[2 * i] << c.in_shl) >> c.in_shr;
+		const int ey = (xyin[2 * i + 1] << c.in_shl) >> c.in_shr;
+		const int xn = ex < 0, yn = ey < 0;
+		int x, y;
+		if (!xn && yn)      { x = ex - ey;  y = ex + ey; }
+		else if (xn && !yn) { x = -ex + ey; y = -ex - ey; }
+		else if (xn && yn)  { x = -ex - ey; y = ex - ey; }
+		else                { x = ex + ey;  y = -ex + ey; }
+		x = wrapw(x, c.wsh); y = wrapw(y, c.wsh);
+		uint32_t ph = c.e_phase[(xn << 1) | yn];
+		for (int k = 0; k < c.neff; k++) {
+			const int sh = (k + 1 > 31) ? 31 : (k + 1);
+			const int sy = y >> sh, sx = x >> sh;
+			if (y < 0) {
+				x = wrapw(x - sy, c.wsh); y = wrapw(y + sx, c.wsh); ph -= c.pa[k];
+			} else {
+				x = wrapw(x + sy, c.wsh); y = wrapw(y - sx, c.wsh); ph += c.pa[k];
+			}
+		}
+		const int b = (x >> c.D) & c.do_round;
+		mag[i] = wrapw(x + c.rc + b, c.wsh) >> c.D;
+		phout[i] = ph >> c.pshift;
+	}
+}
+
+// ---- LUT cores (rtl/sintable.v:71-75, rtl/quarterwav.v:92-109) --------------------------------
+struct LutConsts {
+	int32_t pshift;		// 32-pw
+	int32_t osh;		// 32-ow : sign-extension of the OW-bit table word
+	uint32_t lowmask;	// quarterwav: 2^(pw-2)-1
+	int32_t pw;
+};
+
+template <bool QUARTER>
+__device__ __forceinline__ int lut_one(uint32_t phase32, const uint32_t *__restrict__ tbl, const LutConsts &c) {
+	const uint32_t ip = phase32 >> c.pshift;
+	if (!QUARTER) {
+		return (int)(__ldg(tbl + ip) << c.osh) >> c.osh;
+	} else {
+		const uint32_t fold = 0u - ((ip >> (c.pw - 2)) & 1u);	// all-ones when i_phase[PW-2]
+		const uint32_t idx = (ip ^ fold) & c.lowmask;
+		const int neg = -(int)((ip >> (c.pw - 1)) & 1u);	// -1 when i_phase[PW-1]
+		const int v = (int)__ldg(tbl + idx);
+		return (((v ^ neg) - neg) << c.osh) >> c.osh;
+	}
+}
+
+template <bool QUARTER>
+__global__ void __launch_bounds__(256)
+k_lut(const int4 *__restrict__ phase4, int4 *__restrict__ out4, const uint32_t *__restrict__ tbl,
+		size_t ngroups, const __grid_constant__ LutConsts c) {
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+		const int4 pv = ldg_stream(phase4 + g);
+		int4 o;
+		o.x = lut_one<QUARTER>((uint32_t)pv.x, tbl, c);
+		o.y = lut_one<QUARTER>((uint32_t)pv.y, tbl, c);
+		o.z = lut_one<QUARTER>((uint32_t)pv.z, tbl, c);
+		o.w = lut_one<QUARTER>((uint32_t)pv.w, tbl, c);
+		stg_stream(out4 + g, o);
+	}
+}
+
+template <bool QUARTER>
+__global__ void __launch_bounds__(256)
+k_lut_scalar(const uint32_t *__restrict__ phase, int32_t *__restrict__ out,
+		const uint32_t *__restrict__ tbl, size_t n, const __grid_constant__ LutConsts c) {
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+		out[i] = lut_one<QUARTER>(phase[i], tbl, c);
+}
+
+} // namespace zc
+#endif

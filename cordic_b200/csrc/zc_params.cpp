@@ -1,0 +1,203 @@
+// zc_params.cpp -- host-side configuration of the zcordic engine: the same parameter
+// surface as the ZipCPU/cordic core generator (phase width, output width, stage count,
+// extra bits, CORDIC gain), derived with the same double-precision libm calls so every
+// integer constant matches what the generator prints.  Citations: /root/reference.
+#include "zc_internal.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace zc {
+
+// sw/cordiclib.cpp:157-169.  The double is truncated (not rounded) to an unsigned.
+static uint32_t angle_word(int k, int pw) {
+	const double turns_to_units = (4.0 * (double)(1ul << (pw - 2))) / (M_PI * 2.0);
+	double a = std::atan2(1., std::pow(2, k + 1)) * turns_to_units;
+	return (uint32_t)(unsigned)a;
+}
+
+// sw/cordiclib.cpp:66-80
+static double cordic_gain(int nstages) {
+	double g = 1.0;
+	for (int k = 0; k < nstages; k++)
+		g = g * std::sqrt(1.0 + std::pow(2.0, -2. * (k + 1)));
+	return g;
+}
+
+// sw/cordiclib.cpp:82-109
+static double phase_variance(int nstages, int pw) {
+	const double rad_to_phase = (double)(1ul << (pw - 1)) / M_PI;
+	double var = 1. / 12.;
+	for (unsigned k = 0; k < (unsigned)nstages; k++) {
+		double x = std::atan2(1., std::pow(2, k + 1)) * rad_to_phase;
+		unsigned long q = (unsigned)x;
+		double e = q - x;
+		var += e * e;
+	}
+	return var / std::pow(rad_to_phase, 2.);
+}
+
+// sw/cordiclib.cpp:111-130
+static double quantization_variance(int nstages, int xtrabits, int dropped) {
+	double v = std::pow(2, 2 * xtrabits) / 12.;
+	for (int k = 0; k < nstages; k++)
+		v = (1 + std::pow(4, -k - 1)) * v + 1. / 3.;
+	if (dropped > 0)
+		v = std::pow(2, -2 * dropped) * v + 1 / 12.;
+	return v;
+}
+
+// sw/cordiclib.cpp:246-268: smallest pb>=3 with sin(2pi/2^pb)*(2^ow - 1) < 1/2
+static int calc_phase_bits(int ow) {
+	unsigned pb = 3;
+	for (; pb < 64; pb++) {
+		double step = 2.0 * M_PI / (double)(1ul << pb);
+		if (std::sin(step) * (double)((1ul << ow) - 1) < 0.5)
+			break;
+	}
+	return (int)pb;
+}
+
+// sw/cordiclib.cpp:214-229 (bounded by the working width) and :231-244 (unbounded)
+static int calc_stages(int pw, int ww_bound /* <0: none */) {
+	int n = 0;
+	for (; n < 64; n++) {
+		if (angle_word(n, pw) == 0)
+			break;
+		if (ww_bound >= 0 && ww_bound <= n)
+			break;
+	}
+	return n;
+}
+
+static void resolve_widths(int &iw, int &ow) {
+	// sw/main.cpp:262-270 / :314-322
+	if (iw <= 0 && ow > 0) iw = ow;
+	if (ow <= 0) ow = iw;
+	if (iw <= 0 || ow <= 0) iw = ow = 24;
+}
+
+static int finish(zc_params *o, int mode, int iw, int ow, int nxtra, int ww, int pw, int nstages) {
+	if (pw < 3 || pw > 32 || ww > 32 || ww < 2 || iw < 1 || ow < 1 ||
+	    nstages < 0 || nstages > ZC_MAX_STAGES || ow > ww || iw > ww)
+		return set_error(ZC_ERANGE, "configuration needs PW in [3,32], WW<=32, NSTAGES<=64 "
+			"(got IW=%d OW=%d WW=%d PW=%d NSTAGES=%d)", iw, ow, ww, pw, nstages);
+	std::memset(o, 0, sizeof(*o));
+	o->mode = mode;
+	o->iw = iw; o->ow = ow; o->nextra = nxtra; o->ww = ww; o->pw = pw; o->nstages = nstages;
+	for (int k = 0; k < nstages; k++)
+		o->angle[k] = angle_word(k, pw);
+	o->cordic_gain = cordic_gain(nstages);
+	o->qvar = quantization_variance(nstages, ww - iw, ww - ow);
+	o->pvar_rad = phase_variance(nstages, pw);
+	return ZC_OK;
+}
+
+int derive_p2r(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *o) {
+	if (!o) return set_error(ZC_EINVAL, "NULL zc_params");
+	resolve_widths(iw, ow);
+	const int wide = (ow > iw) ? ow : iw;
+	int nxtra = xtra_user + 1;				// sw/main.cpp:273
+	const int ww_cli = wide + nxtra;			// sw/main.cpp:272-274
+	if (ww_cli < 1 || ww_cli > 62)
+		return set_error(ZC_ERANGE, "working width %d out of range", ww_cli);
+	if (pw <= 0) pw = calc_phase_bits(ww_cli);		// :276
+	if (pw < 3 || pw > 32)
+		return set_error(ZC_ERANGE, "phase width %d outside [3,32]", pw);
+	if (nstages <= 0) nstages = calc_stages(pw, ww_cli);	// :278
+	if (nxtra < 1) nxtra = 1;				// sw/basiccordic.cpp:67-68
+	const int ww = wide + nxtra;				// sw/basiccordic.cpp:71-73
+	int rc = finish(o, ZC_MODE_P2R, iw, ow, nxtra, ww, pw, nstages);
+	if (rc != ZC_OK) return rc;
+	o->gain = o->cordic_gain;				// sw/basiccordic.cpp:477-478
+	// sw/basiccordic.cpp:479-496 (including the pow(2, gain) factor as written there)
+	double amp = (double)(1ul << (iw - 1)) - 1.;
+	amp *= (double)(1ul << (ww - iw));
+	amp *= o->cordic_gain;
+	amp *= std::pow(2.0, -(ww - ow));
+	const double sig = amp * amp;
+	const double noise = o->qvar + sig * o->pvar_rad * std::pow(2, o->cordic_gain);
+	o->best_cnr = 10.0 * std::log(sig / noise) / std::log(10.0);
+	return ZC_OK;
+}
+
+int derive_r2p(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *o) {
+	if (!o) return set_error(ZC_EINVAL, "NULL zc_params");
+	resolve_widths(iw, ow);
+	const int wide = (ow > iw) ? ow : iw;
+	int nxtra = xtra_user + 2;				// sw/main.cpp:323
+	const int ww_cli = wide + nxtra;
+	if (ww_cli < 1 || ww_cli > 62)
+		return set_error(ZC_ERANGE, "working width %d out of range", ww_cli);
+	if (pw <= 0) pw = calc_phase_bits(ww_cli);		// :325-326
+	if (pw < 3 || pw > 32)
+		return set_error(ZC_ERANGE, "phase width %d outside [3,32]", pw);
+	if (nstages <= 0) nstages = calc_stages(pw, -1);	// :327-328
+	if (nxtra < 2) nxtra = 2;				// sw/topolar.cpp:67-68
+	const int ww = wide + 2 * nxtra;			// sw/topolar.cpp:71-75 (added twice)
+	int rc = finish(o, ZC_MODE_R2P, iw, ow, nxtra, ww, pw, nstages);
+	if (rc != ZC_OK) return rc;
+	o->gain = o->cordic_gain * std::sqrt(2.0) / 2.;		// sw/topolar.cpp:439-440
+	o->best_cnr = 0.0;
+	return ZC_OK;
+}
+
+// sw/main.cpp:358-379 (tbl) / :401-422 (qtr).  In main() "not given" is -1; here <=0.
+int derive_lut(bool quarter, int iw, int pw, int ow, int *pw_out, int *ow_out) {
+	if (!pw_out || !ow_out) return set_error(ZC_EINVAL, "NULL output");
+	if (iw <= 0) iw = -1;
+	if (pw <= 0) pw = -1;
+	if (ow <= 0) ow = -1;
+	if (iw >= 0 && pw < 0) { pw = iw; iw = -1; }
+	if (pw > 3 && ow <= 0) {
+		for (int k = pw - 2; k < pw + 3; k++)
+			if (k > 0 && k < 63 && calc_phase_bits(k) == pw) { ow = k; break; }
+	}
+	if (ow <= 0) ow = 24;
+	if (pw <= 0) pw = calc_phase_bits(ow);
+	*pw_out = pw; *ow_out = ow;
+	return check_lut(quarter, pw, ow);
+}
+
+int check_lut(bool quarter, int pw, int ow) {
+	// sw/sintable.cpp:62-69 (tbl refuses >=24), :188-197 (qtr asserts >2, refuses >=26),
+	// sw/hexfile.cpp:52-55 (ow < 31)
+	if (ow < 2 || ow >= 31)
+		return set_error(ZC_ERANGE, "LUT output width %d outside [2,30]", ow);
+	if (quarter ? (pw <= 2 || pw >= 26) : (pw < 1 || pw >= 24))
+		return set_error(ZC_ERANGE, "LUT phase width %d outside the generator's limits", pw);
+	return ZC_OK;
+}
+
+// sw/sintable.cpp:156-168: tbl[k] = (long)(maxv*sin(2 pi k / 2^pw)), C truncation, & (2^ow - 1)
+int build_sintable(int pw, int ow, uint32_t *tbl) {
+	if (!tbl) return set_error(ZC_EINVAL, "NULL table");
+	int rc = check_lut(false, pw, ow);
+	if (rc != ZC_OK) return rc;
+	const long entries = 1l << pw;
+	const long maxv = (1l << (ow - 1)) - 1l, mask = (1l << ow) - 1l;
+	for (long k = 0; k < entries; k++) {
+		double ph = 2.0 * M_PI * (double)k / (double)entries;
+		long w = (long)(maxv * std::sin(ph));
+		tbl[k] = (uint32_t)(w & mask);
+	}
+	return ZC_OK;
+}
+
+// sw/sintable.cpp:325-337: half-sample offset, first quadrant only
+int build_quarterwav(int pw, int ow, uint32_t *tbl) {
+	if (!tbl) return set_error(ZC_EINVAL, "NULL table");
+	int rc = check_lut(true, pw, ow);
+	if (rc != ZC_OK) return rc;
+	const long entries = 1l << pw;
+	const long maxv = (1l << (ow - 1)) - 1l, mask = (1l << ow) - 1l;
+	for (long k = 0; k < entries / 4; k++) {
+		double ph = 2.0 * M_PI * (double)k / (double)entries;
+		ph += M_PI / (double)entries;
+		long w = (long)(maxv * std::sin(ph));
+		tbl[k] = (uint32_t)(w & mask);
+	}
+	return ZC_OK;
+}
+
+} // namespace zc

@@ -1,0 +1,163 @@
+/*
+ * zcordic.h -- C ABI of libzcordic: a Blackwell (sm_100a) batched CORDIC engine that
+ * evaluates, bit-exactly, the functions computed by the cores ZipCPU/cordic generates.
+ *
+ * The reference has no FFI of its own.  Its de-facto boundaries are (1) the port list
+ * of the generated cores as consumed through the Verilated model by TESTB<VA>
+ * (bench/cpp/testb.h:49-136) and (2) the generator's command line / generated header
+ * constants (sw/main.cpp:139-232, rtl/cordic.h:46-59).  Each entry point below cites
+ * the reference interface it replaces; citations are relative to the reference tree.
+ *
+ * Conventions
+ *   - plain C, caller-owned buffers, no torch / C++ types in any signature;
+ *   - every function returns ZC_OK (0) or a negative zc_status; nothing throws;
+ *   - a zc_params is a POD filled by zc_derive_*; it is immutable afterwards and may be
+ *     used from any thread and any device;
+ *   - "device" entry points take DEVICE pointers valid on CUDA device `device` and a
+ *     cudaStream_t passed as void* (NULL = the legacy default stream); they enqueue work
+ *     and return without synchronising;
+ *   - "_host" entry points take HOST pointers (pinned memory from zc_host_alloc gives full
+ *     PCIe overlap; pageable memory works, slower), run a chunked
+ *     H2D -> kernel -> D2H pipeline on `device`, and return when the outputs are complete;
+ *   - sample words: ix/iy/phase inputs are the raw port bit-vectors in the low IW / PW
+ *     bits of a 32-bit word (higher bits are ignored, exactly as the port would truncate
+ *     them); o_xval / o_yval / o_mag / o_val are returned SIGN-EXTENDED from OW bits to
+ *     int32; o_phase is returned zero-extended in PW bits;
+ *   - there is NO CPU fallback: without a usable CUDA device the compute entry points
+ *     fail with ZC_ENODEV / ZC_ECUDA.
+ */
+#ifndef ZCORDIC_H
+#define ZCORDIC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZC_VERSION_MAJOR 0
+#define ZC_VERSION_MINOR 1
+#define ZC_MAX_STAGES    64
+
+typedef enum zc_status {
+	ZC_OK       =  0,
+	ZC_EINVAL   = -1,	/* NULL pointer, bad size, bad argument                         */
+	ZC_ERANGE   = -2,	/* configuration outside what the engine (or the reference) supports */
+	ZC_ECUDA    = -3,	/* a CUDA runtime call failed; see zc_last_error()              */
+	ZC_ENODEV   = -4,	/* no CUDA device / bad device ordinal                          */
+	ZC_ENOMEM   = -5
+} zc_status;
+
+enum { ZC_MODE_P2R = 0, ZC_MODE_R2P = 1 };
+
+/* The generated-header constant set (rtl/cordic.h:46-59, rtl/topolar.h:46-58) plus the
+ * cordic_angle table printed into the Verilog (sw/cordiclib.cpp:157-169). */
+typedef struct zc_params {
+	int32_t	 mode;			/* ZC_MODE_P2R (rtl/cordic.v) or ZC_MODE_R2P (rtl/topolar.v) */
+	int32_t	 iw, ow;		/* IW, OW                                          */
+	int32_t	 nextra;		/* NEXTRA as printed (already incremented)          */
+	int32_t	 ww, pw, nstages;	/* WW, PW, NSTAGES                                  */
+	int32_t	 reserved;
+	uint32_t angle[ZC_MAX_STAGES];	/* cordic_angle[k], PW-bit, truncated               */
+	double	 gain;			/* GAIN                                             */
+	double	 cordic_gain;		/* prod sqrt(1+2^-2(k+1)) (== GAIN for p2r)         */
+	double	 qvar;			/* QUANTIZATION_VARIANCE                            */
+	double	 pvar_rad;		/* PHASE_VARIANCE_RAD                               */
+	double	 best_cnr;		/* BEST_POSSIBLE_CNR (p2r only, else 0)             */
+} zc_params;
+
+/* flags for the *_ex entry points */
+enum {
+	ZC_F_DEFAULT       = 0,
+	ZC_F_FORCE_GENERIC = 1,	/* runtime-parameter kernel that models the WW-bit wrap       */
+	ZC_F_NO_SEED       = 2,	/* rotate_const/nco: run every stage in registers (no table-seeded prefix) */
+	ZC_F_FORCE_SEED    = 4	/* rotate_const/nco: use the table-seeded prefix even for small n */
+};
+
+int         zc_version(void);				/* major*1000 + minor */
+const char *zc_strerror(int status);
+const char *zc_last_error(void);			/* thread-local detail of the last failure */
+int         zc_device_count(void);			/* >=0, or ZC_ECUDA */
+
+/* ---- configuration: replaces the generator command line ------------------------------ */
+
+/* gencordic -t p2r -i iw -o ow -x xtra_user [-p pw] [-n nstages]
+ *   sw/main.cpp:260-279 (width defaulting, nxtra+1, phase bits, stages),
+ *   sw/basiccordic.cpp:67-73 (working width), :465-498 (header constants).
+ * Pass <=0 for iw / ow / pw / nstages that were not given on the command line. */
+int zc_derive_p2r(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *out);
+/* gencordic -t r2p ...   sw/main.cpp:312-328, sw/topolar.cpp:67-75 (nxtra added twice), :428-446 */
+int zc_derive_r2p(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *out);
+/* gencordic -t tbl [-i n] [-p pw] [-o ow]   sw/main.cpp:358-379 ; limit sw/sintable.cpp:62 */
+int zc_derive_tbl(int iw, int pw, int ow, int *pw_out, int *ow_out);
+/* gencordic -t qtr ...                       sw/main.cpp:401-422 ; limit sw/sintable.cpp:190 */
+int zc_derive_qtr(int iw, int pw, int ow, int *pw_out, int *ow_out);
+
+/* The $readmemh table contents (host side; same libm as the generator so the words equal
+ * rtl/sintable.hex / rtl/quarterwav.hex).  Words are masked to OW bits as hextable() writes
+ * them (sw/hexfile.cpp:78-89).  sintable: 2^pw words (sw/sintable.cpp:156-168);
+ * quarterwav: 2^(pw-2) words (sw/sintable.cpp:325-337). */
+int zc_lut_build_sintable(int pw, int ow, uint32_t *tbl_host);
+int zc_lut_build_quarterwav(int pw, int ow, uint32_t *tbl_host);
+
+/* ---- the data path, device buffers --------------------------------------------------- */
+
+/* rtl/cordic.v with constant (i_xval,i_yval) = (x0,y0), one i_phase per sample
+ * (ports rtl/cordic.v:58-63; this is the sweep of bench/cpp/cordic_tb.cpp:127-178).
+ * xy[2*i] = o_xval, xy[2*i+1] = o_yval. */
+int zc_rotate_const(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase,
+		int32_t *xy, size_t n, int device, void *stream);
+int zc_rotate_const_ex(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase,
+		int32_t *xy, size_t n, int device, void *stream, uint32_t flags);
+/* rtl/cordic.v with per-sample (i_xval,i_yval) = (xy_in[2i], xy_in[2i+1]) */
+int zc_rotate(const zc_params *p, const int32_t *xy_in, const uint32_t *phase,
+		int32_t *xy_out, size_t n, int device, void *stream);
+int zc_rotate_ex(const zc_params *p, const int32_t *xy_in, const uint32_t *phase,
+		int32_t *xy_out, size_t n, int device, void *stream, uint32_t flags);
+/* rtl/topolar.v (ports :59-64; sweep of bench/cpp/topolar_tb.cpp:127-189):
+ * mag[i] = o_mag, phase[i] = o_phase */
+int zc_topolar(const zc_params *p, const int32_t *xy_in, int32_t *mag, uint32_t *phase,
+		size_t n, int device, void *stream);
+int zc_topolar_ex(const zc_params *p, const int32_t *xy_in, int32_t *mag, uint32_t *phase,
+		size_t n, int device, void *stream, uint32_t flags);
+/* NCO: a 32-bit phase accumulator feeding rtl/cordic.v.  Sample i (0<=i<n) uses
+ * phase32 = phase0 + (n0+i)*step (mod 2^32) and i_phase = phase32 >> (32-PW), the
+ * truncation bench/cpp/cordic_tb.cpp:128-138 applies for shift>=0.  No input stream. */
+int zc_nco_rotate(const zc_params *p, int32_t x0, int32_t y0, uint32_t phase0, uint32_t step,
+		uint64_t n0, int32_t *xy, size_t n, int device, void *stream);
+int zc_nco_rotate_ex(const zc_params *p, int32_t x0, int32_t y0, uint32_t phase0, uint32_t step,
+		uint64_t n0, int32_t *xy, size_t n, int device, void *stream, uint32_t flags);
+/* rtl/sintable.v:71-75 / rtl/quarterwav.v:92-109.  phase32 is a 32-bit NCO word; the core
+ * sees i_phase = phase32 >> (32-pw).  tbl_dev: the table of zc_lut_build_* in device memory. */
+int zc_lut_sin(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int32_t *out,
+		size_t n, int device, void *stream);
+int zc_lut_qwav(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int32_t *out,
+		size_t n, int device, void *stream);
+
+/* ---- the data path, host buffers (end-to-end) ---------------------------------------- */
+
+void *zc_host_alloc(size_t bytes);		/* pinned; NULL on failure */
+void  zc_host_free(void *ptr);
+
+int zc_rotate_const_host(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase,
+		int32_t *xy, size_t n, int device);
+int zc_rotate_host(const zc_params *p, const int32_t *xy_in, const uint32_t *phase,
+		int32_t *xy_out, size_t n, int device);
+int zc_topolar_host(const zc_params *p, const int32_t *xy_in, int32_t *mag, uint32_t *phase,
+		size_t n, int device);
+int zc_nco_rotate_host(const zc_params *p, int32_t x0, int32_t y0, uint32_t phase0,
+		uint32_t step, uint64_t n0, int32_t *xy, size_t n, int device);
+int zc_lut_sin_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32,
+		int32_t *out, size_t n, int device);
+int zc_lut_qwav_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32,
+		int32_t *out, size_t n, int device);
+
+/* Number of kernel launches this library has enqueued from the calling process so far
+ * (all devices); lets a benchmark report how many of OUR kernels ran in a timed region. */
+uint64_t zc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZCORDIC_H */

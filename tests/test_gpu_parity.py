@@ -1,0 +1,358 @@
+"""GPU tier: the CUDA path, called through the C ABI (cordic_b200 binds it with ctypes), against
+the CPU oracle on the same seeded inputs -- bit-exact, every word.  Marked ``gpu``."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cordic_b200 as zc
+from . import zo
+from .conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+SEED = 20261017
+KATS = json.load(open(os.path.join(ROOT, "tests", "golden", "survey_kats.json")))
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.cpu().numpy()
+
+
+def both_p2r(iw=0, ow=0, xtra=2, pw=0, n=0):
+    core = zc.Cordic(iw, ow, xtra, pw, n)
+    rc, op = zo.derive_p2r(iw, ow, xtra, pw, n)
+    assert rc == 0
+    return core, op
+
+
+def both_r2p(iw=0, ow=0, xtra=2, pw=0, n=0):
+    core = zc.Topolar(iw, ow, xtra, pw, n)
+    rc, op = zo.derive_r2p(iw, ow, xtra, pw, n)
+    assert rc == 0
+    return core, op
+
+
+P2R_CONFIGS = {
+    "shipped": dict(iw=13, ow=13, xtra=2),                      # rtl/cordic.h: WW16 PW20 N16
+    "cfg0": dict(iw=16, ow=16, xtra=2, pw=16),                  # BASELINE configs[0]
+    "cfg1": dict(iw=18, ow=18, xtra=2, pw=24, n=20),            # BASELINE configs[1]
+    "8_8_x0": dict(iw=8, ow=8, xtra=0),
+    "12_16_x1": dict(iw=12, ow=16, xtra=1),
+    "20_10_p18": dict(iw=20, ow=10, xtra=2, pw=18),
+    "manystages": dict(iw=6, ow=6, xtra=2, pw=10, n=30),         # zero-angle / i>=WW pass-through stages
+    "negx": dict(iw=10, ow=10, xtra=-5),                        # WW=IW+1: no zero padding, no rounding... D=1
+}
+
+
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED])
+@pytest.mark.parametrize("name", sorted(P2R_CONFIGS))
+def test_rotate_const_full_phase_sweep(name, flags):
+    """The sweep of bench/cpp/cordic_tb.cpp:127-178: every one of the 2^PW phases, full-scale
+    input (x,y) = (2^(IW-1)-1, 0) (:68-69).  Bit-exact against the oracle."""
+    core, op = both_p2r(**P2R_CONFIGS[name])
+    n = 1 << core.PW
+    phase = np.arange(n, dtype=np.uint32)
+    x0 = (1 << (core.IW - 1)) - 1
+    got = host(core.rotate_const(x0, 0, dev(phase), flags=flags))
+    want = zo.rotate_const(op, x0, 0, phase)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_FORCE_SEED])
+def test_rotate_const_other_vectors_and_random_phase(flags):
+    core, op = both_p2r(**P2R_CONFIGS["cfg1"])
+    rng = np.random.default_rng(SEED)
+    phase = rng.integers(0, 1 << 32, size=(1 << 20) + 3, dtype=np.uint64).astype(np.uint32)  # high bits are ignored
+    for x0, y0 in [(131071, 0), (-131072, -131072), (131071, 131071), (0, 0), (-1, 1), (12345, -54321),
+                   (0x7FFFFFFF, 0x40000)]:   # last: bits above IW must be dropped like the port would
+        got = host(core.rotate_const(x0, y0, dev(phase), flags=flags))
+        want = zo.rotate_const(op, x0, y0, phase)
+        assert np.array_equal(got, want), (x0, y0)
+
+
+@pytest.mark.parametrize("name", sorted(P2R_CONFIGS))
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_FORCE_GENERIC])
+def test_rotate_per_sample_inputs(name, flags):
+    core, op = both_p2r(**P2R_CONFIGS[name])
+    rng = np.random.default_rng(SEED + 1)
+    n = (1 << 19) + 1
+    lo, hi = -(1 << (core.IW - 1)), (1 << (core.IW - 1)) - 1
+    xy = rng.integers(lo, hi + 1, size=(n, 2), dtype=np.int64).astype(np.int32)
+    # edge vectors first: all four corners, axes, zero, +-1
+    edges = [(lo, lo), (lo, hi), (hi, lo), (hi, hi), (0, 0), (hi, 0), (0, hi), (lo, 0), (0, lo), (1, 0), (-1, 0), (0, -1)]
+    xy[:len(edges)] = edges
+    phase = rng.integers(0, 1 << core.PW, size=n, dtype=np.uint64).astype(np.uint32)
+    phase[:8] = [0, 1, (1 << core.PW) - 1, 1 << (core.PW - 1), 1 << (core.PW - 2), 1 << (core.PW - 3),
+                 (1 << (core.PW - 3)) - 1, 7 << (core.PW - 3)]
+    got = host(core.rotate(dev(xy), dev(phase), flags=flags))
+    want = zo.rotate(op, xy, phase)
+    assert np.array_equal(got, want)
+
+
+def test_rotate_extreme_inputs_every_octant_boundary():
+    """Corner inputs x every octant boundary +-2: where a missing guard bit or a wrong
+    pre-rotation constant (rtl/cordic.v:143-178) would show."""
+    core, op = both_p2r(**P2R_CONFIGS["cfg1"])
+    lo, hi = -(1 << 17), (1 << 17) - 1
+    corners = [(lo, lo), (lo, hi), (hi, lo), (hi, hi), (hi, 0), (lo, 0), (0, hi), (0, lo)]
+    ph = []
+    for o in range(8):
+        for d in (-2, -1, 0, 1, 2):
+            ph.append(((o << 21) + d) & 0xFFFFFF)
+    xy = np.array([c for c in corners for _ in ph], dtype=np.int32)
+    phase = np.array(ph * len(corners), dtype=np.uint32)
+    got = host(core.rotate(dev(xy), dev(phase)))
+    assert np.array_equal(got, zo.rotate(op, xy, phase))
+
+
+def test_rotate_narrow_core_wraps_like_the_rtl():
+    """WW=5 is too narrow for the CORDIC gain: the RTL registers wrap.  The engine must detect
+    that its non-wrapping fast path is not provably exact and reproduce the wrap."""
+    core, op = both_p2r(iw=4, ow=4, xtra=0, pw=8, n=6)
+    assert core.WW == 5
+    xs = np.arange(-8, 8, dtype=np.int32)
+    xy = np.array([(x, y) for x in xs for y in xs for _ in range(256)], dtype=np.int32)
+    phase = np.tile(np.arange(256, dtype=np.uint32), 256)
+    got = host(core.rotate(dev(xy), dev(phase)))
+    assert np.array_equal(got, zo.rotate(op, xy, phase))
+    got = host(core.rotate_const(-8, -8, dev(phase)))
+    assert np.array_equal(got, zo.rotate_const(op, -8, -8, phase))
+
+
+R2P_CONFIGS = {
+    "shipped": dict(iw=13, ow=13, xtra=2),              # rtl/topolar.h: WW21 PW21 N18
+    "cfg2": dict(iw=16, ow=16, xtra=2),                 # BASELINE configs[2]: WW24 PW24 N21
+    "8_8_x0": dict(iw=8, ow=8, xtra=0),
+    "12_16_x1": dict(iw=12, ow=16, xtra=1),
+    "10_10_p14_n20": dict(iw=10, ow=10, xtra=2, pw=14, n=20),
+}
+
+
+def tb_circle(iw, pw, n):
+    """Stimulus of bench/cpp/topolar_tb.cpp:133-147: a full-scale circle, two revolutions."""
+    i = np.arange(n, dtype=np.int64)
+    ip = ((i << 1) & 0xFFFFFFFF).astype(np.uint32).view(np.int32).astype(np.float64) if pw == 32 else \
+        ((i << 1)).astype(np.int32).astype(np.float64)
+    ph = ip * np.pi / float(1 << (pw - 1))
+    mg = float((1 << (iw - 1)) - 1)
+    return np.stack([(mg * np.cos(ph)).astype(np.int32), (mg * np.sin(ph)).astype(np.int32)], axis=1)
+
+
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_FORCE_GENERIC])
+@pytest.mark.parametrize("name", sorted(R2P_CONFIGS))
+def test_topolar_testbench_circle(name, flags):
+    core, op = both_r2p(**R2P_CONFIGS[name])
+    xy = tb_circle(core.IW, core.PW, 1 << core.PW)
+    mag, ph = core.topolar(dev(xy), flags=flags)
+    wm, wp = zo.topolar(op, xy)
+    assert np.array_equal(host(mag), wm)
+    assert np.array_equal(host(ph).view(np.uint32), wp)
+
+
+@pytest.mark.parametrize("name", sorted(R2P_CONFIGS))
+def test_topolar_random_and_edges(name):
+    core, op = both_r2p(**R2P_CONFIGS[name])
+    rng = np.random.default_rng(SEED + 2)
+    n = (1 << 20) + 2
+    lo, hi = -(1 << (core.IW - 1)), (1 << (core.IW - 1)) - 1
+    xy = rng.integers(lo, hi + 1, size=(n, 2), dtype=np.int64).astype(np.int32)
+    edges = [(0, 0), (1, 0), (-1, 0), (0, 1), (0, -1), (hi, 0), (lo, 0), (0, hi), (0, lo), (hi, hi), (lo, lo),
+             (hi, lo), (lo, hi), (1, 1), (-1, -1), (1, -1), (-1, 1)]
+    xy[:len(edges)] = edges
+    mag, ph = core.topolar(dev(xy))
+    wm, wp = zo.topolar(op, xy)
+    assert np.array_equal(host(mag), wm)
+    assert np.array_equal(host(ph).view(np.uint32), wp)
+
+
+def test_topolar_exhaustive_8bit():
+    core, op = both_r2p(iw=8, ow=8, xtra=0)
+    v = np.arange(-128, 128, dtype=np.int32)
+    xy = np.stack(np.meshgrid(v, v, indexing="ij"), axis=-1).reshape(-1, 2)
+    mag, ph = core.topolar(dev(xy))
+    wm, wp = zo.topolar(op, xy)
+    assert np.array_equal(host(mag), wm)
+    assert np.array_equal(host(ph).view(np.uint32), wp)
+
+
+@pytest.mark.parametrize("kind,pw,ow", [("tbl", 17, 13), ("tbl", 10, 8), ("tbl", 23, 16), ("tbl", 20, 30),
+                                        ("qtr", 18, 24), ("qtr", 12, 12), ("qtr", 25, 16), ("qtr", 3, 6)])
+def test_lut_modes(kind, pw, ow):
+    """rtl/sintable.v:71-75 and rtl/quarterwav.v:92-109 over every table index and random NCO words."""
+    cls = zc.QuarterWav if kind == "qtr" else zc.SinTable
+    core = cls(phase_bits=pw, ow=ow)
+    assert (core.PW, core.OW) == (pw, ow)
+    otbl = zo.quarterwav(pw, ow) if kind == "qtr" else zo.sintable(pw, ow)
+    assert np.array_equal(core.table, otbl)
+    rng = np.random.default_rng(SEED + 3)
+    sweep = (np.arange(1 << min(pw, 22), dtype=np.uint64) << (32 - min(pw, 22))).astype(np.uint32)
+    rnd = rng.integers(0, 1 << 32, size=(1 << 20) + 1, dtype=np.uint64).astype(np.uint32)
+    for phase in (sweep, rnd, rnd[:5], rnd[:3]):
+        got = host(core.lookup(dev(phase)))
+        want = (zo.lut_qwav if kind == "qtr" else zo.lut_sin)(pw, ow, otbl, phase)
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC])
+def test_nco_stream(flags):
+    core, op = both_p2r(**P2R_CONFIGS["cfg1"])
+    n = (1 << 20) + 5
+    for phase0, step, n0 in [(0, 0x01234567, 0), (0xDEADBEEF, 0xFFFFFFFF, 12345), (7, 1, (1 << 33) + 3)]:
+        got = host(core.nco(131071, 0, phase0, step, n, n0=n0, flags=flags))
+        want = zo.nco(op, 131071, 0, phase0, step, n, n0=n0)
+        assert np.array_equal(got, want), (phase0, step, n0)
+
+
+def test_nco_chunks_concatenate():
+    """Rank r of G computes n in [r*N/G, (r+1)*N/G) from phase0 + n*step alone."""
+    core, op = both_p2r(**P2R_CONFIGS["cfg1"])
+    n, parts = 1 << 18, 8
+    whole = host(core.nco(131071, 0, 99, 0x01234567, n))
+    pieces = [host(core.nco(131071, 0, 99, 0x01234567, n // parts, n0=r * (n // parts))) for r in range(parts)]
+    assert np.array_equal(np.concatenate(pieces), whole)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 7, 255, 1023, 4097])
+def test_ragged_sizes_and_misaligned_buffers(n):
+    core, op = both_p2r(**P2R_CONFIGS["cfg1"])
+    vcore, vop = both_r2p(**R2P_CONFIGS["cfg2"])
+    rng = np.random.default_rng(SEED + n)
+    phase = rng.integers(0, 1 << 24, size=n + 1, dtype=np.uint64).astype(np.uint32)
+    xy = rng.integers(-32768, 32768, size=(n + 1, 2), dtype=np.int64).astype(np.int32)
+    dphase, dxy = dev(phase), dev(xy)
+    for off in (0, 1):          # off=1: pointers 4 / 8 bytes past a 16-byte boundary
+        m = n + 1 - off if off else n
+        ph_h, xy_h = phase[off:off + m], xy[off:off + m]
+        ph_d, xy_d = dphase[off:off + m], dxy[off:off + m]
+        if m == 0:
+            assert core.rotate_const(131071, 0, ph_d).numel() == 0
+            continue
+        assert np.array_equal(host(core.rotate_const(131071, 0, ph_d)), zo.rotate_const(op, 131071, 0, ph_h))
+        assert np.array_equal(host(core.rotate(xy_d, ph_d)), zo.rotate(op, xy_h, ph_h))
+        mag, ph = vcore.topolar(xy_d)
+        wm, wp = zo.topolar(vop, xy_h)
+        assert np.array_equal(host(mag), wm) and np.array_equal(host(ph).view(np.uint32), wp)
+
+
+@pytest.mark.parametrize("name", [k for k in sorted(KATS) if not k.startswith("_")])
+def test_survey_known_answers_on_gpu(name):
+    """tests/golden/survey_kats.json straight through the CUDA path (no oracle involved)."""
+    c = KATS[name]
+    d = c["derive"]
+    if name.startswith("r2p"):
+        core = zc.Topolar(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"])
+        xy = np.array([[v[0], v[1]] for v in c["vectors"]], dtype=np.int32)
+        mag, ph = core.topolar(dev(xy))
+        assert host(mag).tolist() == [v[2] for v in c["vectors"]]
+        assert host(ph).view(np.uint32).tolist() == [int(v[3], 16) for v in c["vectors"]]
+        return
+    core = zc.Cordic(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"])
+    vec = c["vectors"]
+    if vec and len(vec[0]) == 3:
+        phase = np.array([int(v[0], 16) for v in vec], dtype=np.uint32)
+        got = host(core.rotate_const(c["x0"], c["y0"], dev(phase)))
+        assert got.tolist() == [[v[1], v[2]] for v in vec]
+    elif vec:
+        phase = np.array([int(v[2], 16) for v in vec], dtype=np.uint32)
+        xy = np.array([[v[0], v[1]] for v in vec], dtype=np.int32)
+        got = host(core.rotate(dev(xy), dev(phase)))
+        assert got.tolist() == [[v[3], v[4]] for v in vec]
+    if "sweep" in c:
+        n = 1 << core.PW
+        out = core.rotate_const(c["x0"], c["y0"], torch.arange(n, dtype=torch.int32, device="cuda"))
+        assert int(out[:, 0].sum(dtype=torch.int64)) == c["sweep"]["sum_x"]
+        assert int(out[:, 1].sum(dtype=torch.int64)) == c["sweep"]["sum_y"]
+
+
+def test_host_buffer_entry_points():
+    """The *_host ABI (H2D -> kernel -> D2H pipeline, several chunks) with pageable and pinned memory."""
+    core, op = both_p2r(**P2R_CONFIGS["cfg1"])
+    vcore, vop = both_r2p(**R2P_CONFIGS["cfg2"])
+    rng = np.random.default_rng(SEED + 4)
+    n = (9 << 20) + 3                                   # > 2 pipeline chunks, ragged tail
+    phase = rng.integers(0, 1 << 24, size=n, dtype=np.uint64).astype(np.uint32)
+    out = np.empty((n, 2), dtype=np.int32)
+    core.rotate_const_host(131071, 0, phase, out)
+    assert np.array_equal(out, zo.rotate_const(op, 131071, 0, phase))
+    # pinned
+    pin_in, pin_out = zc.PinnedBuffer(n, np.uint32), zc.PinnedBuffer(2 * n, np.int32)
+    pin_in.array[:] = phase
+    core.rotate_const_host(131071, 0, pin_in.array, pin_out.array)
+    assert np.array_equal(pin_out.array.reshape(n, 2), out)
+    pin_in.free(); pin_out.free()
+    m = (5 << 20) + 1
+    xy = rng.integers(-32768, 32768, size=(m, 2), dtype=np.int64).astype(np.int32)
+    out2 = np.empty((m, 2), dtype=np.int32)
+    core.rotate_host(xy, phase[:m], out2)
+    assert np.array_equal(out2, zo.rotate(op, xy, phase[:m]))
+    mag, ph = np.empty(m, dtype=np.int32), np.empty(m, dtype=np.uint32)
+    vcore.topolar_host(xy, mag, ph)
+    wm, wp = zo.topolar(vop, xy)
+    assert np.array_equal(mag, wm) and np.array_equal(ph, wp)
+    out3 = np.empty((m, 2), dtype=np.int32)
+    core.nco_host(131071, 0, 5, 0x01234567, out3, n0=77)
+    assert np.array_equal(out3, zo.nco(op, 131071, 0, 5, 0x01234567, m, n0=77))
+    lut = zc.SinTable(phase_bits=17, ow=13)
+    words = rng.integers(0, 1 << 32, size=m, dtype=np.uint64).astype(np.uint32)
+    o4 = np.empty(m, dtype=np.int32)
+    lut.lookup_host(words, o4)
+    assert np.array_equal(o4, zo.lut_sin(17, 13, zo.sintable(17, 13), words))
+    q = zc.QuarterWav(phase_bits=18, ow=24)
+    q.lookup_host(words, o4)
+    assert np.array_equal(o4, zo.lut_qwav(18, 24, zo.quarterwav(18, 24), words))
+
+
+def test_full_size_cfg1_properties():
+    """BASELINE configs[1] at its full size (2^30 samples = 64 sweeps of the 2^24 phases): every
+    sweep must reproduce the first one word for word, the first one must equal the oracle, and the
+    checksum of checksums is 64 x the single-sweep sums (-39316 each)."""
+    core, op = both_p2r(**P2R_CONFIGS["cfg1"])
+    n, period = 1 << 30, 1 << 24
+    phase = torch.arange(n, dtype=torch.int32, device="cuda").bitwise_and_(period - 1)
+    out = core.rotate_const(131071, 0, phase)
+    del phase
+    first = out[:period]
+    assert np.array_equal(host(first), zo.rotate_const(op, 131071, 0, np.arange(period, dtype=np.uint32)))
+    v = out.view(n // period, period, 2)
+    for k in range(1, n // period):
+        assert torch.equal(v[k], first), k
+    assert int(out[:, 0].sum(dtype=torch.int64)) == 64 * -39316
+    assert int(out[:, 1].sum(dtype=torch.int64)) == 64 * -39316
+    # x(phase + half turn) = -x(phase) up to the rounding asymmetry of the core (a few LSB)
+    half = period // 2
+    d = (first[:half].to(torch.int64) + first[half:].to(torch.int64)).abs().max()
+    assert int(d) <= 4
+    del out, v, first
+    torch.cuda.empty_cache()
+
+
+def test_full_size_cfg2_round_trip():
+    """BASELINE configs[2] at full size (2^28 complex samples): rotate a full-scale vector by a phase
+    sweep, feed the result to the vectoring core, and recover the phase to within the cores' noise;
+    a 2^24-sample slice is checked word for word against the oracle."""
+    core, op = both_p2r(iw=16, ow=16, xtra=2, pw=24)
+    vcore, vop = both_r2p(**R2P_CONFIGS["cfg2"])
+    n = 1 << 28
+    phase = torch.arange(n, dtype=torch.int32, device="cuda").mul_(16 + 1).bitwise_and_((1 << 24) - 1)
+    xy = core.rotate_const(16000, 0, phase)        # amplitude 16000*1.1644/2 fits 16 bits
+    mag, ph = vcore.topolar(xy)
+    sl = slice(123 << 16, (123 << 16) + (1 << 24))
+    wm, wp = zo.topolar(vop, host(xy[sl]))
+    assert np.array_equal(host(mag[sl]), wm) and np.array_equal(host(ph[sl]).view(np.uint32), wp)
+    err = (ph - phase).bitwise_and_((1 << 24) - 1)
+    err = torch.where(err >= (1 << 23), err - (1 << 24), err)
+    # 16-bit inputs at radius ~9300: angular resolution ~ 2^24/(2*pi*9300) = 287 phase units
+    assert int(err.abs().max()) < 600
+    m = mag.to(torch.float64)
+    assert abs(float(m.mean()) - 16000 * 1.16443534550574 / 2 * vcore.GAIN * 2 ** (16 - 1 - 16) * 2) < 2.0
+    del phase, xy, mag, ph, err, m
+    torch.cuda.empty_cache()

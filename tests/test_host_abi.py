@@ -1,0 +1,130 @@
+"""CPU tier: the product's host side -- parameter derivation and LUT construction against the
+real generator's output, the C ABI's symbol table against include/zcordic.h, and error
+behaviour.  No compute call is made (there is no GPU here and no CPU fallback to call)."""
+import ctypes
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cordic_b200 as zc
+from . import zo
+from .conftest import ROOT
+from .test_oracle_golden import LUTS, PARAMS, check_against_generator
+
+
+@pytest.mark.parametrize("name", sorted(PARAMS))
+def test_derive_matches_generator(name):
+    g = PARAMS[name]
+    a = g["args"]
+    derive = zc.derive_p2r if g["mode"] == "p2r" else zc.derive_r2p
+    p = derive(a["iw"], a["ow"], 2 if a["xtra"] is None else a["xtra"], a["pw"], a["nstages"])
+    assert p.mode == (zc.MODE_P2R if g["mode"] == "p2r" else zc.MODE_R2P)
+    check_against_generator(name, p, g["mode"])
+
+
+@pytest.mark.parametrize("name", sorted(PARAMS))
+def test_derive_matches_oracle_bitwise(name):
+    g = PARAMS[name]
+    a = g["args"]
+    x = 2 if a["xtra"] is None else a["xtra"]
+    if g["mode"] == "p2r":
+        p, (rc, o) = zc.derive_p2r(a["iw"], a["ow"], x, a["pw"], a["nstages"]), zo.derive_p2r(a["iw"], a["ow"], x, a["pw"], a["nstages"])
+    else:
+        p, (rc, o) = zc.derive_r2p(a["iw"], a["ow"], x, a["pw"], a["nstages"]), zo.derive_r2p(a["iw"], a["ow"], x, a["pw"], a["nstages"])
+    assert rc == 0
+    for f in ("iw", "ow", "nextra", "ww", "pw", "nstages"):
+        assert getattr(p, f) == getattr(o, f)
+    for f in ("gain", "cordic_gain", "qvar", "pvar_rad", "best_cnr"):
+        assert getattr(p, f) == getattr(o, f), f       # same libm, same order of operations
+    assert list(p.angle) == list(o.angle)
+
+
+@pytest.mark.parametrize("name", sorted(LUTS))
+def test_lut_build_matches_generator(name):
+    g = LUTS[name]
+    a = g["args"]
+    derive = zc.derive_qtr if g["mode"] == "qtr" else zc.derive_tbl
+    assert derive(a["iw"], a["pw"], a["ow"]) == (g["pw"], g["ow"])
+    tbl = (zc.build_quarterwav if g["mode"] == "qtr" else zc.build_sintable)(g["pw"], g["ow"])
+    assert tbl.size == g["nwords"]
+    assert hashlib.sha256(tbl.astype("<u4").tobytes()).hexdigest() == g["sha256_le_u32"]
+    assert [int(v) for v in tbl[::g["stride"]]] == g["samples"]
+
+
+def test_generator_limits_are_enforced():
+    # sw/sintable.cpp:62 refuses tables of 2^24 and up; :190 refuses quarter tables of 2^26 and up
+    with pytest.raises(zc.ZcError) as e:
+        zc.derive_tbl(pw=24, ow=12)
+    assert e.value.code == -2
+    with pytest.raises(zc.ZcError):
+        zc.derive_qtr(pw=26, ow=12)
+    with pytest.raises(zc.ZcError):
+        zc.derive_qtr(pw=2, ow=12)
+    # beyond what the engine's 32-bit lanes hold
+    with pytest.raises(zc.ZcError) as e:
+        zc.derive_p2r(iw=30, ow=30, xtra=4)
+    assert e.value.code == -2
+    with pytest.raises(zc.ZcError):
+        zc.derive_r2p(iw=28, ow=28, xtra=2)
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "zcordic.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(zc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_functions()
+    assert len(names) >= 25
+    L = ctypes.CDLL(zc.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), "libzcordic.so does not export %s" % n
+    # and the Python binding covers the same set
+    assert names == zc.EXPORTED_SYMBOLS
+
+
+def test_header_is_plain_c():
+    """The ABI header must compile as C (no torch / C++ types)."""
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c")
+        open(c, "w").write('#include "zcordic.h"\nint main(void){zc_params p; (void)p; return sizeof(zc_params)==%d?0:1;}\n'
+                           % ctypes.sizeof(zc.Params))
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), c,
+                               "-o", os.path.join(td, "t")])
+        assert subprocess.call([os.path.join(td, "t")]) == 0
+
+
+def test_argument_errors():
+    L = zc.lib()
+    p = zc.derive_p2r(18, 18, 2, 24, 20)
+    assert L.zc_derive_p2r(18, 18, 2, 24, 20, None) == -1
+    # a vectoring configuration handed to the rotation entry point
+    r = zc.derive_r2p(16, 16, 2)
+    assert L.zc_rotate_const(ctypes.byref(r), 1, 0, None, None, 0, 0, None) == -1
+    assert b"ZC_MODE_P2R" in L.zc_last_error()
+    # NULL buffers with n>0
+    assert L.zc_rotate_const(ctypes.byref(p), 1, 0, None, None, 16, 0, None) == -1
+    assert L.zc_strerror(-2) == b"configuration out of range"
+    assert L.zc_version() >= 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device the compute entry points must fail loudly, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = zc.lib()
+    p = zc.derive_p2r(18, 18, 2, 24, 20)
+    ph = np.zeros(16, dtype=np.uint32)
+    out = np.full(32, 12345, dtype=np.int32)
+    rc = L.zc_rotate_const_host(ctypes.byref(p), 131071, 0, ph.ctypes.data, out.ctypes.data, 16, 0)
+    assert rc in (-4, -3)
+    assert (out == 12345).all()
+    assert L.zc_device_count() <= 0 or rc != 0

@@ -219,20 +219,21 @@ static int launch_rotate(const zc_params *p, CoreConsts &c, const uint32_t *phas
 		c.neff >= 1 && c.neff <= 32;
 	size_t done = 0;
 	if (fast) {
-		const size_t groups = n / 4;
+		if constexpr (SRC != SRC_XY) if (!(flags & ZC_F_NO_SEED)) {
+			// 4-byte phase words and 8-byte (x,y) pairs: natural alignment is all this path needs
+			rc = seeded_rotate_try<SRC>(p, c, phase, xy_out, n, device, di.sms, st, flags, done);
+			if (rc != ZC_OK) return rc;
+			if (done) g_launches.fetch_add(1, std::memory_order_relaxed);
+		}
+		const size_t groups = (n - done) / 4;
 		if (groups) {
-			bool seeded = false;
-			if (SRC != SRC_XY && !(flags & ZC_F_NO_SEED)) {
-				rc = seeded_rotate_try<SRC>(p, c, phase, xy_out, groups, device, di.sms, st, flags, seeded);
-				if (rc != ZC_OK) return rc;
-				if (seeded) g_launches.fetch_add(1, std::memory_order_relaxed);
-			}
-			if (!seeded) {
-				RotTable<SRC, 32>::launch(c.neff, grid_for(groups, di, 16), st, (const int4 *)phase,
-					(const int4 *)xy_in, (int4 *)xy_out, groups, c);
-				if ((rc = post_launch("k_rotate")) != ZC_OK) return rc;
-			}
-			done = groups * 4;
+			CoreConsts t = c;
+			t.nco_n0 = c.nco_n0 + (uint32_t)done;
+			RotTable<SRC, 32>::launch(c.neff, grid_for(groups, di, 16), st,
+				(const int4 *)(phase ? phase + done : nullptr), (const int4 *)(xy_in ? xy_in + 2 * done : nullptr),
+				(int4 *)(xy_out + 2 * done), groups, t);
+			if ((rc = post_launch("k_rotate")) != ZC_OK) return rc;
+			done += groups * 4;
 		}
 	}
 	if (done < n) {

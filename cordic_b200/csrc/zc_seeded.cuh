@@ -1,14 +1,416 @@
-// zc_seeded.cuh -- table-seeded rotation kernel (constant input vector).  Placeholder until the
-// seeded path lands: reports "not used" so the caller runs every stage in registers.
+// zc_seeded.cuh -- rotation mode with a constant input vector (the sin/cos generator of
+// bench/cpp/cordic_tb.cpp:61-80 and the NCO): table-seeded prefix + register suffix.
+//
+// Why this is still bit-exact rtl/cordic.v.  In rotation mode the direction d_k of stage k depends
+// only on the phase (rtl/cordic.v:265), never on x/y.  With (i_xval,i_yval) fixed, the x/y registers
+// after the first M stages are therefore a function of (quarter turn q, d_0..d_{M-1}) only.  The map
+// phase -> (d_0..d_{M-1}) is a monotone step function of the residual phase whose steps sit at the
+// partial sums of +-angle[k]; we enumerate its R <= 2^M intervals on the host (phase arithmetic
+// only), let a setup KERNEL run the real stage arithmetic once per (q, interval) to fill the x/y
+// table, and at run time find a sample's interval with one bucket lookup: the reduced phase's top
+// bits select a bucket that contains at most one step (the plan refuses any geometry where that is
+// not true), and `entry + low_bits` carries into the interval number exactly when the sample lies
+// at or above that step.  The remaining NS = N-M stages run in registers exactly like the plain
+// kernel, except that their directions come from a second small table indexed by the residual
+// phase (again a function of the phase alone), which removes the phase recursion from the ALU.
+//
+// Shared-memory layout (one CTA of 1024 threads per SM, tables copied in by bulk-TMA):
+//   T1[2^LB]      u32   bucket -> (interval_at_bucket_start << lgW) + (W - offset_of_step_in_bucket)
+//   TS[R]         u32   interval -> partial angle sum, left-justified
+//   T2[R][4]      int2  (interval, q) -> (x, y) after M stages
+//   TD[NSP/4][nres] int4 residual -> d_M .. d_{M+NS-1} as +1/-1 words, in planes of four stages so that
+//                         consecutive residuals (a phase sweep) read consecutive 16-byte slots: no bank conflicts
+// Sample-to-lane mapping: a warp owns 128 consecutive samples per iteration and lane l takes samples
+// l, l+32, l+64, l+96 of them, so that for a phase sweep neighbouring lanes read neighbouring table rows
+// (or the same row: a broadcast) and every global access is a fully coalesced 128/256-byte row.
 #ifndef ZC_SEEDED_CUH
 #define ZC_SEEDED_CUH
+
+#include "zc_internal.h"
 #include "zc_kernels.cuh"
+
+#include <cstring>
+#include <mutex>
+#include <vector>
+
 namespace zc {
-template <int SRC>
-static int seeded_rotate_try(const zc_params *, const CoreConsts &, const uint32_t *, int32_t *, size_t,
-		int, int, cudaStream_t, uint32_t, bool &used) {
-	used = false;
+
+constexpr int SEED_MAX_NS = 16;
+constexpr size_t SEED_SMEM_LIMIT = 227 * 1024 - 64;	// opt-in maximum per CTA minus the mbarrier slot
+
+struct SeedConsts {
+	int32_t  M;		// stages folded into the table
+	int32_t  bsh;		// t >> bsh leaves bucket*4 in place (masked by bmask)
+	uint32_t bmask;
+	uint32_t wmask;		// W-1
+	int32_t  lgw;
+	uint32_t off_ts, off_t2, off_td;	// byte offsets of the tables in shared memory
+	int32_t  td_plane;	// bytes per TD plane (nres*16)
+	int32_t  td_bias;	// off_td - rmin*16
+	uint32_t total_bytes;	// multiple of 16
+	int32_t  sh[SEED_MAX_NS];	// arithmetic shift of suffix stage j: min(M+j+1, 31)
+	uint32_t R;
+};
+
+// ---- setup kernel: the x/y table, by running the real stages --------------------------------------
+__global__ void k_seed_fill_xy(const uint32_t *__restrict__ rep_phase /* left-justified, one per interval */,
+		int2 *__restrict__ t2, uint32_t R, int M, const __grid_constant__ CoreConsts c) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= 4u * R) return;
+	const uint32_t rank = i >> 2, q = i & 3u;
+	int p = (int)rep_phase[rank];
+	int x = c.cx[q], y = c.cy[q];
+	for (int k = 0; k < M; k++) {
+		const int sh = (k + 1 > 31) ? 31 : (k + 1);
+		const int sy = y >> sh, sx = x >> sh;
+		if (p < 0) { x = x + sy; y = y - sx; p += (int)c.pa[k]; }
+		else       { x = x - sy; y = y + sx; p -= (int)c.pa[k]; }
+	}
+	t2[i] = make_int2(x, y);
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ int2 lds64(uint32_t addr) {
+	int2 v;
+	asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ int4 lds128(uint32_t addr) {
+	int4 v;
+	asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+	return v;
+}
+
+template <int NS, int J = 0>
+struct Suffix {
+	static __device__ __forceinline__ void run(int &x, int &y, const int (&d)[SEED_MAX_NS], const SeedConsts &s) {
+		const int nd = -d[J];
+		const int sy = y >> s.sh[J], sx = x >> s.sh[J];
+		const int x1 = imad(sy, nd, x);
+		const int y1 = imad(sx, d[J], y);
+		x = x1; y = y1;
+		Suffix<NS, J + 1>::run(x, y, d, s);
+	}
+};
+template <int NS>
+struct Suffix<NS, NS> {
+	static __device__ __forceinline__ void run(int &, int &, const int (&)[SEED_MAX_NS], const SeedConsts &) {}
+};
+
+__device__ __forceinline__ uint32_t ldg_stream32(const uint32_t *p) {
+	uint32_t r;
+	asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ void stg_stream64(int2 *p, const int2 v) {
+	asm volatile("st.global.L1::no_allocate.v2.s32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// `nblocks` blocks of 128 consecutive samples; warp w of the grid takes blocks w, w+W, w+2W, ...
+template <int NS, int SRC>
+__global__ void __launch_bounds__(1024, 1)
+k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, size_t nblocks,
+		const __grid_constant__ CoreConsts c, const __grid_constant__ SeedConsts s,
+		const uint4 *__restrict__ tables) {
+	extern __shared__ __align__(128) unsigned char smem[];
+	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+	const uint32_t mbar = sbase + s.total_bytes;		// 8-byte slot after the tables
+
+	// ---- stage the tables: one thread issues bulk-TMA copies that complete on an mbarrier --------
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(s.total_bytes) : "memory");
+		const char *src = reinterpret_cast<const char *>(tables);
+		for (uint32_t off = 0; off < s.total_bytes; off += 32768u) {
+			const uint32_t len = (s.total_bytes - off < 32768u) ? (s.total_bytes - off) : 32768u;
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				:: "r"(sbase + off), "l"(src + off), "r"(len), "r"(mbar) : "memory");
+		}
+	}
+	__syncthreads();		// the mbarrier is initialised before anyone waits on it
+	{
+		uint32_t done = 0;
+		while (!done) {
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+				"selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar) : "memory");
+		}
+	}
+
+	const uint32_t a_ts = sbase + s.off_ts, a_t2 = sbase + s.off_t2;
+	const uint32_t lane = threadIdx.x & 31u;
+	const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+	size_t blk = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	uint32_t pin[4] = {0, 0, 0, 0};
+	if (SRC == SRC_CONST && blk < nblocks) {
+#pragma unroll
+		for (int k = 0; k < 4; k++) pin[k] = ldg_stream32(phase + (blk << 7) + (k << 5) + lane);
+	}
+	for (; blk < nblocks; blk += nwarps) {
+		uint32_t P[4];
+		if (SRC == SRC_NCO) {
+			const uint32_t base = c.nco_phase0 + (c.nco_n0 + (uint32_t)(blk << 7) + lane) * c.nco_step;
+			const uint32_t keep = ~((1u << c.pshift) - 1u);
+#pragma unroll
+			for (int k = 0; k < 4; k++) P[k] = (base + (uint32_t)(k << 5) * c.nco_step) & keep;
+		} else {
+#pragma unroll
+			for (int k = 0; k < 4; k++) P[k] = pin[k] << c.pshift;
+			const size_t nb = blk + nwarps;		// software prefetch of the next block
+			if (nb < nblocks) {
+#pragma unroll
+				for (int k = 0; k < 4; k++) pin[k] = ldg_stream32(phase + (nb << 7) + (k << 5) + lane);
+			}
+		}
+		int2 *const dst = xyout + (blk << 7) + lane;
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const uint32_t t = P[k] + 0x20000000u;		// octant fold (rtl/cordic.v:131-188)
+			const uint32_t e = lds32(sbase + ((t >> s.bsh) & s.bmask));
+			const uint32_t v = e + ((t >> c.pshift) & s.wmask);	// carries past the step, if any
+			const uint32_t rank = v >> s.lgw;
+			const uint32_t w = __funnelshift_l(t, rank, 2);		// rank*4 + quarter turn
+			const uint32_t S = lds32(a_ts + (rank << 2));
+			const int2 xy = lds64(a_t2 + (w << 3));
+			const int p = (int)((t & 0x3fffffffu) - 0x20000000u - S);	// residual after M stages
+			int x = xy.x, y = xy.y;
+			if (NS > 0) {
+				const uint32_t a_td = sbase + (uint32_t)imad(p >> c.pshift, 16, s.td_bias);
+				int d[SEED_MAX_NS];
+#pragma unroll
+				for (int j = 0; j < NS; j += 4) {
+					const int4 dv = lds128(a_td + (uint32_t)(j >> 2) * (uint32_t)s.td_plane);
+					d[j] = dv.x;
+					if (j + 1 < SEED_MAX_NS) d[j + 1] = dv.y;
+					if (j + 2 < SEED_MAX_NS) d[j + 2] = dv.z;
+					if (j + 3 < SEED_MAX_NS) d[j + 3] = dv.w;
+				}
+				Suffix<NS>::run(x, y, d, s);
+			}
+			stg_stream64(dst + (k << 5), make_int2(round_out(x, c), round_out(y, c)));
+		}
+	}
+}
+
+// ---- host: plan construction and cache -----------------------------------------------------------
+struct SeedPlan {
+	zc_params p;
+	int32_t x0c[4], y0c[4];		// the pre-rotated constant vector (identifies x0,y0 modulo IW)
+	int device = -1;
+	int NS = 0;
+	SeedConsts s;
+	void *dev = nullptr;		// tables, laid out as in shared memory
+	bool usable = false;		// false: geometry does not fit; cached so we do not retry
+	uint64_t stamp = 0;
+};
+
+struct Interval { int64_t lo, hi, S; };
+
+// Enumerates the intervals of constant (d_0..d_{M-1}) over the reduced phase range
+// [-2^(PW-3), 2^(PW-3)), in ascending order.  Phase arithmetic only (rtl/cordic.v:265-279).
+static void seed_intervals(const zc_params *p, int M, std::vector<Interval> &iv) {
+	const int64_t half = (int64_t)1 << (p->pw - 3);
+	iv.assign(1, Interval{-half, half, 0});
+	std::vector<Interval> next;
+	for (int k = 0; k < M; k++) {
+		next.clear();
+		const int64_t a = p->angle[k];
+		for (const Interval &it : iv) {
+			// residual = phase - S ; negative residual -> rotate clockwise, S' = S - angle
+			if (it.lo < it.S) next.push_back(Interval{it.lo, it.hi < it.S ? it.hi : it.S, it.S - a});
+			if (it.hi > it.S) next.push_back(Interval{it.lo > it.S ? it.lo : it.S, it.hi, it.S + a});
+		}
+		iv.swap(next);
+	}
+}
+
+static bool seed_geometry(const zc_params *p, int neff, int M, std::vector<Interval> &iv, SeedConsts &s,
+		int &NS, int64_t &rmin, int64_t &rmax) {
+	NS = neff - M;
+	if (NS < 0 || NS > SEED_MAX_NS) return false;
+	seed_intervals(p, M, iv);
+	int64_t wmin = INT64_MAX;
+	rmin = INT64_MAX; rmax = INT64_MIN;
+	for (const Interval &it : iv) {
+		if (it.hi - it.lo < wmin) wmin = it.hi - it.lo;
+		if (it.lo - it.S < rmin) rmin = it.lo - it.S;
+		if (it.hi - 1 - it.S > rmax) rmax = it.hi - 1 - it.S;
+	}
+	int lgw = 0;
+	while (((int64_t)2 << lgw) <= wmin) lgw++;		// largest W = 2^lgw <= wmin: at most one step per bucket
+	if (lgw < 2) return false;
+	if (lgw > 16) lgw = 16;
+	const int LB = p->pw - 2 - lgw;				// log2(number of buckets)
+	if (LB < 0 || LB > 15) return false;
+	const size_t R = iv.size();
+	const int nsp = (NS + 3) & ~3;
+	const size_t nres = (size_t)(rmax - rmin + 1);
+	const size_t b_t1 = (size_t)4 << LB, b_ts = (R * 4 + 15) & ~(size_t)15, b_t2 = R * 32,
+		     b_td = nres * (size_t)nsp * 4;
+	const size_t total = b_t1 + b_ts + b_t2 + b_td;
+	if (total + 16 > SEED_SMEM_LIMIT) return false;
+	if ((R << lgw) >= ((uint64_t)1 << 32)) return false;
+	std::memset(&s, 0, sizeof(s));
+	s.M = M; s.lgw = lgw; s.R = (uint32_t)R;
+	// t holds the reduced phase, offset-binary, in bits [29:0]; its top LB bits are the bucket
+	s.bsh = 30 - LB - 2;
+	s.bmask = (((uint32_t)1 << LB) - 1u) << 2;
+	if (s.bsh < 0) return false;
+	s.wmask = ((uint32_t)1 << lgw) - 1u;
+	s.off_ts = (uint32_t)b_t1;
+	s.off_t2 = (uint32_t)(b_t1 + b_ts);
+	s.off_td = (uint32_t)(b_t1 + b_ts + b_t2);
+	s.td_plane = (int32_t)(nres * 16);
+	s.td_bias = (int32_t)((int64_t)s.off_td - rmin * 16);
+	s.total_bytes = (uint32_t)((total + 15) & ~(size_t)15);
+	for (int j = 0; j < SEED_MAX_NS; j++) s.sh[j] = (M + j + 1 > 31) ? 31 : (M + j + 1);
+	return true;
+}
+
+static std::mutex g_seed_mu;
+static std::vector<SeedPlan> g_seed_cache;
+static uint64_t g_seed_clock = 0;
+
+static void seed_release(SeedPlan &pl) {
+	if (pl.dev) {
+		int prev = -1;
+		cudaGetDevice(&prev);
+		cudaSetDevice(pl.device);
+		cudaFree(pl.dev);
+		if (prev >= 0) cudaSetDevice(prev);
+		pl.dev = nullptr;
+	}
+}
+
+// Builds (or finds) the plan for (p, constant vector, device).  Called with the device current.
+static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, cudaStream_t st,
+		SeedPlan &out) {
+	std::lock_guard<std::mutex> lk(g_seed_mu);
+	for (SeedPlan &pl : g_seed_cache) {
+		if (pl.device == device && std::memcmp(&pl.p, p, sizeof(*p)) == 0 &&
+		    std::memcmp(pl.x0c, c.cx, sizeof(pl.x0c)) == 0 && std::memcmp(pl.y0c, c.cy, sizeof(pl.y0c)) == 0) {
+			pl.stamp = ++g_seed_clock;
+			out = pl;
+			return ZC_OK;
+		}
+	}
+	SeedPlan pl;
+	pl.p = *p; pl.device = device; pl.stamp = ++g_seed_clock;
+	std::memcpy(pl.x0c, c.cx, sizeof(pl.x0c));
+	std::memcpy(pl.y0c, c.cy, sizeof(pl.y0c));
+	std::vector<Interval> iv;
+	int64_t rmin = 0, rmax = 0;
+	bool ok = false;
+	const int neff = c.neff;
+	for (int M = (neff < 13 ? neff : 13); M >= 6 && !ok; M--)
+		ok = seed_geometry(p, neff, M, iv, pl.s, pl.NS, rmin, rmax);
+	if (ok) {
+		const SeedConsts &s = pl.s;
+		const int pshift = c.pshift;
+		const size_t R = iv.size();
+		std::vector<uint32_t> host(s.total_bytes / 4 + R, 0u);		// tables + representative phases
+		uint32_t *t1 = host.data(), *ts = host.data() + s.off_ts / 4, *td = host.data() + s.off_td / 4;
+		uint32_t *rep = host.data() + s.total_bytes / 4;
+		const int64_t half = (int64_t)1 << (p->pw - 3), W = (int64_t)1 << s.lgw;
+		const size_t nb = (size_t)1 << (p->pw - 2 - s.lgw);
+		size_t r = 0;
+		for (size_t b = 0; b < nb && ok; b++) {
+			const int64_t b0 = -half + (int64_t)b * W;
+			while (r + 1 < R && iv[r + 1].lo <= b0) r++;
+			int64_t off = W;					// no step inside this bucket
+			if (r + 1 < R && iv[r + 1].lo < b0 + W) {
+				off = iv[r + 1].lo - b0;			// in [1, W-1]
+				if (r + 2 < R && iv[r + 2].lo < b0 + W) ok = false;	// two steps: refuse
+			}
+			t1[b] = (uint32_t)((r << s.lgw) + (uint64_t)(W - off));
+		}
+		for (size_t k = 0; k < R && ok; k++) {
+			ts[k] = (uint32_t)((uint64_t)iv[k].S << pshift);
+			rep[k] = (uint32_t)((uint64_t)iv[k].lo << pshift);
+		}
+		const size_t nres = (size_t)(rmax - rmin + 1);
+		for (int64_t res = rmin; res <= rmax && ok; res++) {
+			int64_t ph = res;
+			for (int j = 0; j < pl.NS; j++) {			// rtl/cordic.v:265-279, phase only
+				const bool neg = ph < 0;
+				td[((size_t)(j >> 2) * nres + (size_t)(res - rmin)) * 4 + (j & 3)] = (uint32_t)(neg ? -1 : 1);
+				ph += neg ? (int64_t)p->angle[s.M + j] : -(int64_t)p->angle[s.M + j];
+			}
+		}
+		if (ok) {
+			cudaError_t e = cudaMalloc(&pl.dev, host.size() * 4);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(pl.dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st);
+			if (e == cudaSuccess) {
+				const uint32_t nthreads = 4u * (uint32_t)R;
+				k_seed_fill_xy<<<(nthreads + 255) / 256, 256, 0, st>>>(
+					reinterpret_cast<const uint32_t *>(pl.dev) + s.total_bytes / 4,
+					reinterpret_cast<int2 *>(reinterpret_cast<char *>(pl.dev) + s.off_t2), (uint32_t)R, s.M, c);
+				e = cudaGetLastError();
+			}
+			if (e == cudaSuccess) e = cudaStreamSynchronize(st);	// tables complete before any stream uses them
+			if (e != cudaSuccess) {
+				seed_release(pl);
+				return set_error(ZC_ECUDA, "seed table setup failed: %s", cudaGetErrorString(e));
+			}
+		}
+	}
+	pl.usable = ok;
+	if (g_seed_cache.size() >= 16) {		// evict the least recently used plan
+		size_t victim = 0;
+		for (size_t k = 1; k < g_seed_cache.size(); k++)
+			if (g_seed_cache[k].stamp < g_seed_cache[victim].stamp) victim = k;
+		seed_release(g_seed_cache[victim]);
+		g_seed_cache.erase(g_seed_cache.begin() + victim);
+	}
+	g_seed_cache.push_back(pl);
+	out = pl;
 	return ZC_OK;
 }
+
+template <int SRC, int NS>
+struct SeedTable {
+	static cudaError_t launch(int ns, int grid, size_t smem, cudaStream_t st, const uint32_t *ph, int2 *out, size_t nblocks,
+			const CoreConsts &c, const SeedConsts &s, const uint4 *tables) {
+		if (ns == NS) {
+			cudaError_t e = cudaFuncSetAttribute(k_rotate_seeded<NS, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (e != cudaSuccess) return e;
+			k_rotate_seeded<NS, SRC><<<grid, 1024, smem, st>>>(ph, out, nblocks, c, s, tables);
+			return cudaGetLastError();
+		}
+		return SeedTable<SRC, NS - 1>::launch(ns, grid, smem, st, ph, out, nblocks, c, s, tables);
+	}
+};
+template <int SRC>
+struct SeedTable<SRC, -1> {
+	static cudaError_t launch(int, int, size_t, cudaStream_t, const uint32_t *, int2 *, size_t, const CoreConsts &,
+			const SeedConsts &, const uint4 *) { return cudaErrorInvalidValue; }
+};
+
+// Tries the seeded path on the first floor(n/128)*128 samples.  done=0 means "not applicable here".
+template <int SRC>
+static int seeded_rotate_try(const zc_params *p, const CoreConsts &c, const uint32_t *phase, int32_t *xy_out,
+		size_t n, int device, int sms, cudaStream_t st, uint32_t flags, size_t &done) {
+	done = 0;
+	const size_t nblocks = n >> 7;
+	if (nblocks == 0) return ZC_OK;
+	if (!(flags & ZC_F_FORCE_SEED) && n < ((size_t)1 << 20)) return ZC_OK;	// not worth the table load
+	if (c.neff < 6 || p->pw < 12) return ZC_OK;
+	SeedPlan pl;
+	int rc = seed_plan_get(p, c, device, st, pl);
+	if (rc != ZC_OK) return rc;
+	if (!pl.usable) return ZC_OK;
+	const size_t smem = pl.s.total_bytes + 16;
+	cudaError_t e = SeedTable<SRC, SEED_MAX_NS>::launch(pl.NS, sms, smem, st, phase, (int2 *)xy_out, nblocks,
+		c, pl.s, (const uint4 *)pl.dev);
+	if (e != cudaSuccess)
+		return set_error(ZC_ECUDA, "launch of k_rotate_seeded failed: %s", cudaGetErrorString(e));
+	done = nblocks << 7;
+	return ZC_OK;
+}
+
 } // namespace zc
 #endif

@@ -16,7 +16,7 @@
 //
 // Shared-memory layout (one CTA of 1024 threads per SM, tables copied in by bulk-TMA):
 //   T1[2^LB]      u32   bucket -> (interval_at_bucket_start << lgW) + (W - offset_of_step_in_bucket)
-//   TS[R]         u32   interval -> partial angle sum, left-justified
+//   TS[R]         i32   interval -> partial angle sum + 2^(PW-3) + rmin, so that u - TS = row of TD
 //   T2[R][4]      int2  (interval, q) -> (x, y) after M stages
 //   TD[NSP/4][nres] int4 residual -> d_M .. d_{M+NS-1} as +1/-1 words, in planes of four stages so that
 //                         consecutive residuals (a phase sweep) read consecutive 16-byte slots: no bank conflicts
@@ -40,13 +40,14 @@ constexpr size_t SEED_SMEM_LIMIT = 227 * 1024 - 64;	// opt-in maximum per CTA mi
 
 struct SeedConsts {
 	int32_t  M;		// stages folded into the table
-	int32_t  bsh;		// t >> bsh leaves bucket*4 in place (masked by bmask)
-	uint32_t bmask;
+	uint32_t mul_q;		// 2^(32-PW): phase*mul_q + 2^29 puts the quarter turn in bits 31:30
+	uint32_t mul_u;		// 2^(34-PW): phase*mul_u + 2^31 left-justifies the reduced phase u (PW-2 bits)
+	int32_t  bsh;		// u_left >> bsh = bucket number (32-LB)
+	int32_t  ush;		// u_left >> ush = u, the reduced phase in LSBs, offset binary (34-PW)
 	uint32_t wmask;		// W-1
 	int32_t  lgw;
 	uint32_t off_ts, off_t2, off_td;	// byte offsets of the tables in shared memory
-	int32_t  td_plane;	// bytes per TD plane (nres*16)
-	int32_t  td_bias;	// off_td - rmin*16
+	int32_t  td_plane;	// int4 slots per TD plane (nres)
 	uint32_t total_bytes;	// multiple of 16
 	int32_t  sh[SEED_MAX_NS];	// arithmetic shift of suffix stage j: min(M+j+1, 31)
 	uint32_t R;
@@ -141,7 +142,10 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 		}
 	}
 
-	const uint32_t a_ts = sbase + s.off_ts, a_t2 = sbase + s.off_t2;
+	const uint32_t *const T1 = reinterpret_cast<const uint32_t *>(smem);
+	const int32_t *const TS = reinterpret_cast<const int32_t *>(smem + s.off_ts);
+	const int2 *const T2 = reinterpret_cast<const int2 *>(smem + s.off_t2);
+	const int4 *const TD = reinterpret_cast<const int4 *>(smem + s.off_td);
 	const uint32_t lane = threadIdx.x & 31u;
 	const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
 	size_t blk = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -151,15 +155,14 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 		for (int k = 0; k < 4; k++) pin[k] = ldg_stream32(phase + (blk << 7) + (k << 5) + lane);
 	}
 	for (; blk < nblocks; blk += nwarps) {
-		uint32_t P[4];
+		uint32_t ph[4];
 		if (SRC == SRC_NCO) {
 			const uint32_t base = c.nco_phase0 + (c.nco_n0 + (uint32_t)(blk << 7) + lane) * c.nco_step;
-			const uint32_t keep = ~((1u << c.pshift) - 1u);
 #pragma unroll
-			for (int k = 0; k < 4; k++) P[k] = (base + (uint32_t)(k << 5) * c.nco_step) & keep;
+			for (int k = 0; k < 4; k++) ph[k] = (base + (uint32_t)(k << 5) * c.nco_step) >> c.pshift;
 		} else {
 #pragma unroll
-			for (int k = 0; k < 4; k++) P[k] = pin[k] << c.pshift;
+			for (int k = 0; k < 4; k++) ph[k] = pin[k];
 			const size_t nb = blk + nwarps;		// software prefetch of the next block
 			if (nb < nblocks) {
 #pragma unroll
@@ -169,21 +172,19 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 		int2 *const dst = xyout + (blk << 7) + lane;
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			const uint32_t t = P[k] + 0x20000000u;		// octant fold (rtl/cordic.v:131-188)
-			const uint32_t e = lds32(sbase + ((t >> s.bsh) & s.bmask));
-			const uint32_t v = e + ((t >> c.pshift) & s.wmask);	// carries past the step, if any
+			// octant fold (rtl/cordic.v:131-188): phase + 45 degrees; bits above PW fall off the top
+			const uint32_t tq = (uint32_t)imad((int)ph[k], (int)s.mul_q, 0x20000000);	// [q:2][u:PW-2][0...]
+			const uint32_t tu = (uint32_t)imad((int)ph[k], (int)s.mul_u, (int)0x80000000u);	// [u:PW-2][0...]
+			const uint32_t v = T1[tu >> s.bsh] + (ph[k] & s.wmask);	// carries past the step, if any
 			const uint32_t rank = v >> s.lgw;
-			const uint32_t w = __funnelshift_l(t, rank, 2);		// rank*4 + quarter turn
-			const uint32_t S = lds32(a_ts + (rank << 2));
-			const int2 xy = lds64(a_t2 + (w << 3));
-			const int p = (int)((t & 0x3fffffffu) - 0x20000000u - S);	// residual after M stages
+			const int2 xy = T2[__funnelshift_l(tq, rank, 2)];		// row rank*4 + quarter turn
 			int x = xy.x, y = xy.y;
 			if (NS > 0) {
-				const uint32_t a_td = sbase + (uint32_t)imad(p >> c.pshift, 16, s.td_bias);
+				const int row = (int)(tu >> s.ush) - TS[rank];	// residual after M stages, minus rmin
 				int d[SEED_MAX_NS];
 #pragma unroll
 				for (int j = 0; j < NS; j += 4) {
-					const int4 dv = lds128(a_td + (uint32_t)(j >> 2) * (uint32_t)s.td_plane);
+					const int4 dv = TD[row + (j >> 2) * s.td_plane];
 					d[j] = dv.x;
 					if (j + 1 < SEED_MAX_NS) d[j + 1] = dv.y;
 					if (j + 2 < SEED_MAX_NS) d[j + 2] = dv.z;
@@ -256,16 +257,16 @@ static bool seed_geometry(const zc_params *p, int neff, int M, std::vector<Inter
 	if ((R << lgw) >= ((uint64_t)1 << 32)) return false;
 	std::memset(&s, 0, sizeof(s));
 	s.M = M; s.lgw = lgw; s.R = (uint32_t)R;
-	// t holds the reduced phase, offset-binary, in bits [29:0]; its top LB bits are the bucket
-	s.bsh = 30 - LB - 2;
-	s.bmask = (((uint32_t)1 << LB) - 1u) << 2;
-	if (s.bsh < 0) return false;
+	s.mul_q = (uint32_t)1 << (32 - p->pw);
+	s.mul_u = (uint32_t)1 << (34 - p->pw);
+	s.bsh = 32 - LB;
+	s.ush = 34 - p->pw;
+	if (LB < 1 || s.ush > 31) return false;
 	s.wmask = ((uint32_t)1 << lgw) - 1u;
 	s.off_ts = (uint32_t)b_t1;
 	s.off_t2 = (uint32_t)(b_t1 + b_ts);
 	s.off_td = (uint32_t)(b_t1 + b_ts + b_t2);
-	s.td_plane = (int32_t)(nres * 16);
-	s.td_bias = (int32_t)((int64_t)s.off_td - rmin * 16);
+	s.td_plane = (int32_t)nres;
 	s.total_bytes = (uint32_t)((total + 15) & ~(size_t)15);
 	for (int j = 0; j < SEED_MAX_NS; j++) s.sh[j] = (M + j + 1 > 31) ? 31 : (M + j + 1);
 	return true;
@@ -329,7 +330,7 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, cu
 			t1[b] = (uint32_t)((r << s.lgw) + (uint64_t)(W - off));
 		}
 		for (size_t k = 0; k < R && ok; k++) {
-			ts[k] = (uint32_t)((uint64_t)iv[k].S << pshift);
+			ts[k] = (uint32_t)(int32_t)(iv[k].S + half + rmin);
 			rep[k] = (uint32_t)((uint64_t)iv[k].lo << pshift);
 		}
 		const size_t nres = (size_t)(rmax - rmin + 1);

@@ -15,8 +15,9 @@
 // phase (again a function of the phase alone), which removes the phase recursion from the ALU.
 //
 // Shared-memory layout (one CTA of 1024 threads per SM, tables copied in by bulk-TMA):
-//   T1[2^LB]      u32   bucket -> (interval_at_bucket_start << lgW) + (W - offset_of_step_in_bucket)
-//   TS[R]         i32   interval -> partial angle sum + 2^(PW-3) + rmin, so that u - TS = row of TD
+//   T1[2^LB]      u32   bucket -> 16*((interval_at_bucket_start << lgW) + (W - offset_of_step_in_bucket) - (bucket << lgW)),
+//                         so that (T1[bucket] + 16*u) >> (lgW+4) is the interval of reduced phase u
+//   TS[R]         i32   interval -> 16*(partial angle sum + 2^(PW-3) + rmin), so that 16*u - TS = byte offset of the TD row
 //   T2[R][4]      int2  (interval, q) -> (x, y) after M stages
 //   TD[NSP/4][nres] int4 residual -> d_M .. d_{M+NS-1} as +1/-1 words, in planes of four stages so that
 //                         consecutive residuals (a phase sweep) read consecutive 16-byte slots: no bank conflicts
@@ -43,11 +44,12 @@ struct SeedConsts {
 	uint32_t mul_q;		// 2^(32-PW): phase*mul_q + 2^29 puts the quarter turn in bits 31:30
 	uint32_t mul_u;		// 2^(34-PW): phase*mul_u + 2^31 left-justifies the reduced phase u (PW-2 bits)
 	int32_t  bsh;		// u_left >> bsh = bucket number (32-LB)
-	int32_t  ush;		// u_left >> ush = u, the reduced phase in LSBs, offset binary (34-PW)
-	uint32_t wmask;		// W-1
+	int32_t  ush;		// u_left >> ush = 16*u, u = the reduced phase in LSBs, offset binary (30-PW)
+	int32_t  rsh;		// (T1 entry + 16*u) >> rsh = interval number (lgW+4)
 	int32_t  lgw;
+	float    rscale, rbias;	// float rounding: fma(2^23*1.5 + v, 2^-D, 2^23*1.5*(1-2^-D)) rounds v/2^D to nearest even
 	uint32_t off_ts, off_t2, off_td;	// byte offsets of the tables in shared memory
-	int32_t  td_plane;	// int4 slots per TD plane (nres)
+	int32_t  td_plane;	// bytes per TD plane (nres*16)
 	uint32_t total_bytes;	// multiple of 16
 	int32_t  sh[SEED_MAX_NS];	// arithmetic shift of suffix stage j: min(M+j+1, 31)
 	uint32_t R;
@@ -111,8 +113,17 @@ __device__ __forceinline__ void stg_stream64(int2 *p, const int2 v) {
 	asm volatile("st.global.L1::no_allocate.v2.s32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
+// Convergent rounding on the FMA pipe (the ALU pipe is this kernel's bottleneck).  For |v| < 2^22 the word
+// 0x4B400000+v IS the float 1.5*2^23+v; one fused multiply-add forms 1.5*2^23 + v/2^D exactly and rounds it
+// to the nearest integer, ties to even -- which is precisely rtl/cordic.v:290-295 (add 2^(D-1) when bit D is
+// set, 2^(D-1)-1 when it is clear, then drop D bits).  Only used when WW <= 23 and the core rounds (D >= 2).
+__device__ __forceinline__ int round_out_fma(int v, const SeedConsts &s) {
+	const float r = __fmaf_rn(__int_as_float(v + 0x4B400000), s.rscale, s.rbias);
+	return __float_as_int(r) - 0x4B400000;
+}
+
 // `nblocks` blocks of 128 consecutive samples; warp w of the grid takes blocks w, w+W, w+2W, ...
-template <int NS, int SRC>
+template <int NS, int SRC, bool RF>
 __global__ void __launch_bounds__(1024, 1)
 k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, size_t nblocks,
 		const __grid_constant__ CoreConsts c, const __grid_constant__ SeedConsts s,
@@ -145,7 +156,7 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 	const uint32_t *const T1 = reinterpret_cast<const uint32_t *>(smem);
 	const int32_t *const TS = reinterpret_cast<const int32_t *>(smem + s.off_ts);
 	const int2 *const T2 = reinterpret_cast<const int2 *>(smem + s.off_t2);
-	const int4 *const TD = reinterpret_cast<const int4 *>(smem + s.off_td);
+	const unsigned char *const TD = smem + s.off_td;
 	const uint32_t lane = threadIdx.x & 31u;
 	const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
 	size_t blk = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -175,16 +186,16 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 			// octant fold (rtl/cordic.v:131-188): phase + 45 degrees; bits above PW fall off the top
 			const uint32_t tq = (uint32_t)imad((int)ph[k], (int)s.mul_q, 0x20000000);	// [q:2][u:PW-2][0...]
 			const uint32_t tu = (uint32_t)imad((int)ph[k], (int)s.mul_u, (int)0x80000000u);	// [u:PW-2][0...]
-			const uint32_t v = T1[tu >> s.bsh] + (ph[k] & s.wmask);	// carries past the step, if any
-			const uint32_t rank = v >> s.lgw;
+			const uint32_t u16 = tu >> s.ush;				// 16 * reduced phase
+			const uint32_t rank = (T1[tu >> s.bsh] + u16) >> s.rsh;		// carries past the step, if any
 			const int2 xy = T2[__funnelshift_l(tq, rank, 2)];		// row rank*4 + quarter turn
 			int x = xy.x, y = xy.y;
 			if (NS > 0) {
-				const int row = (int)(tu >> s.ush) - TS[rank];	// residual after M stages, minus rmin
+				const unsigned char *row = TD + (int)(u16 - (uint32_t)TS[rank]);	// residual after M stages picks the row
 				int d[SEED_MAX_NS];
 #pragma unroll
 				for (int j = 0; j < NS; j += 4) {
-					const int4 dv = TD[row + (j >> 2) * s.td_plane];
+					const int4 dv = *reinterpret_cast<const int4 *>(row + (j >> 2) * s.td_plane);
 					d[j] = dv.x;
 					if (j + 1 < SEED_MAX_NS) d[j + 1] = dv.y;
 					if (j + 2 < SEED_MAX_NS) d[j + 2] = dv.z;
@@ -192,7 +203,9 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 				}
 				Suffix<NS>::run(x, y, d, s);
 			}
-			stg_stream64(dst + (k << 5), make_int2(round_out(x, c), round_out(y, c)));
+			const int ox = RF ? round_out_fma(x, s) : round_out(x, c);
+			const int oy = RF ? round_out_fma(y, s) : round_out(y, c);
+			stg_stream64(dst + (k << 5), make_int2(ox, oy));
 		}
 	}
 }
@@ -260,13 +273,18 @@ static bool seed_geometry(const zc_params *p, int neff, int M, std::vector<Inter
 	s.mul_q = (uint32_t)1 << (32 - p->pw);
 	s.mul_u = (uint32_t)1 << (34 - p->pw);
 	s.bsh = 32 - LB;
-	s.ush = 34 - p->pw;
-	if (LB < 1 || s.ush > 31) return false;
-	s.wmask = ((uint32_t)1 << lgw) - 1u;
+	s.ush = 30 - p->pw;
+	s.rsh = lgw + 4;
+	if (LB < 1 || s.ush < 0 || ((uint64_t)R << (lgw + 4)) >= ((uint64_t)1 << 31)) return false;
+	{
+		const int D = p->ww - p->ow;
+		s.rscale = 1.0f / (float)((uint32_t)1 << D);
+		s.rbias = 12582912.0f - 12582912.0f / (float)((uint32_t)1 << D);
+	}
 	s.off_ts = (uint32_t)b_t1;
 	s.off_t2 = (uint32_t)(b_t1 + b_ts);
 	s.off_td = (uint32_t)(b_t1 + b_ts + b_t2);
-	s.td_plane = (int32_t)nres;
+	s.td_plane = (int32_t)(nres * 16);
 	s.total_bytes = (uint32_t)((total + 15) & ~(size_t)15);
 	for (int j = 0; j < SEED_MAX_NS; j++) s.sh[j] = (M + j + 1 > 31) ? 31 : (M + j + 1);
 	return true;
@@ -327,10 +345,10 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, cu
 				off = iv[r + 1].lo - b0;			// in [1, W-1]
 				if (r + 2 < R && iv[r + 2].lo < b0 + W) ok = false;	// two steps: refuse
 			}
-			t1[b] = (uint32_t)((r << s.lgw) + (uint64_t)(W - off));
+			t1[b] = (uint32_t)(16u * (uint32_t)(((uint64_t)r << s.lgw) + (uint64_t)(W - off) - ((uint64_t)b << s.lgw)));
 		}
 		for (size_t k = 0; k < R && ok; k++) {
-			ts[k] = (uint32_t)(int32_t)(iv[k].S + half + rmin);
+			ts[k] = (uint32_t)(int32_t)(16 * (iv[k].S + half + rmin));
 			rep[k] = (uint32_t)((uint64_t)iv[k].lo << pshift);
 		}
 		const size_t nres = (size_t)(rmax - rmin + 1);
@@ -377,9 +395,12 @@ struct SeedTable {
 	static cudaError_t launch(int ns, int grid, size_t smem, cudaStream_t st, const uint32_t *ph, int2 *out, size_t nblocks,
 			const CoreConsts &c, const SeedConsts &s, const uint4 *tables) {
 		if (ns == NS) {
-			cudaError_t e = cudaFuncSetAttribute(k_rotate_seeded<NS, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			// float rounding needs every register value to fit 1.5*2^23 +- 2^22 and a rounding core (D >= 2)
+			const bool rf = c.do_round && c.wsh >= 9;
+			auto *kern = rf ? k_rotate_seeded<NS, SRC, true> : k_rotate_seeded<NS, SRC, false>;
+			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (e != cudaSuccess) return e;
-			k_rotate_seeded<NS, SRC><<<grid, 1024, smem, st>>>(ph, out, nblocks, c, s, tables);
+			kern<<<grid, 1024, smem, st>>>(ph, out, nblocks, c, s, tables);
 			return cudaGetLastError();
 		}
 		return SeedTable<SRC, NS - 1>::launch(ns, grid, smem, st, ph, out, nblocks, c, s, tables);

@@ -128,3 +128,50 @@ def test_no_cpu_fallback_without_gpu():
     assert rc in (-4, -3)
     assert (out == 12345).all()
     assert L.zc_device_count() <= 0 or rc != 0
+
+
+def _gen(args, cwd):
+    import subprocess
+    exe = os.path.join(ROOT, "cordic_b200", "zcordic_gen")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "cordic_b200", "vshim"), exe])
+    return subprocess.run([exe] + args, cwd=cwd, capture_output=True, text=True)
+
+
+@pytest.mark.parametrize("name", sorted(PARAMS))
+def test_zcordic_gen_header_matches_generator(name, tmp_path):
+    """zcordic_gen takes the reference generator's flags and must write the same constant set."""
+    g = PARAMS[name]
+    a = g["args"]
+    fname = "cordic.v" if g["mode"] == "p2r" else "topolar.v"
+    args = ["-ca", "-t", g["mode"], "-f", fname]
+    for flag, key in (("-i", "iw"), ("-o", "ow"), ("-x", "xtra"), ("-p", "pw"), ("-n", "nstages")):
+        if a[key] is not None:
+            args += [flag, str(a[key])]
+    r = _gen(args, str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    got = {}
+    for line in open(os.path.join(str(tmp_path), fname[:-2] + ".h")):
+        m = re.match(r"const\s+(int|double|bool)\s+(\w+)\s*=\s*([^;]+);", line)
+        if m:
+            got[m.group(2)] = m.group(3).strip()
+    assert got == g["header"]
+
+
+@pytest.mark.parametrize("name", sorted(LUTS))
+def test_zcordic_gen_hex_matches_generator(name, tmp_path):
+    g = LUTS[name]
+    a = g["args"]
+    fname = "sintable.v" if g["mode"] == "tbl" else "quarterwav.v"
+    args = ["-t", g["mode"], "-f", fname]
+    for flag, key in (("-i", "iw"), ("-p", "pw"), ("-o", "ow")):
+        if a[key] is not None:
+            args += [flag, str(a[key])]
+    r = _gen(args, str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    hexfile = os.path.join(str(tmp_path), fname[:-2] + ".hex")
+    words = zo.hex_load(hexfile, g["nwords"] + 8)
+    assert words.size == g["nwords"]
+    assert hashlib.sha256(words.astype("<u4").tobytes()).hexdigest() == g["sha256_le_u32"]
+    if g["mode"] == "tbl" and (g["pw"], g["ow"]) == (17, 13) and os.path.exists("/root/reference/rtl/sintable.hex"):
+        assert open(hexfile, "rb").read() == open("/root/reference/rtl/sintable.hex", "rb").read()

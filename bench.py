@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--workload", default="rotate_cfg1", choices=sorted(WORKLOADS))
     ap.add_argument("--samples", type=int, default=0, help="override samples per GPU per step")
     ap.add_argument("--phase", default="sweep", choices=["sweep", "random"])
+    ap.add_argument("--seed-mode", default="table", choices=["table", "adaptive", "regs"])
+    ap.add_argument("--nco-step", type=lambda v: int(v, 0), default=NCO_STEP)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -218,6 +220,7 @@ def main():
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
 
     flags = zc.F_NO_SEED if args.workload.endswith("_noseed") else zc.F_DEFAULT
+    flags |= {"table": 0, "adaptive": zc.F_SEED_ADAPTIVE, "regs": zc.F_SEED_REGS}[args.seed_mode]
     core = zc.Cordic(**CFG1)
     # ---- synthetic inputs, resident in HBM before the timed region (4-12 GiB: far larger than L2)
     g = torch.Generator(device=devname); g.manual_seed(20261017 + rank)
@@ -252,7 +255,7 @@ def main():
         elif kind == "rotate":
             core.rotate(xy, phase, out=o_xy)
         elif kind == "nco":
-            core.nco(X0, Y0, 0, NCO_STEP, nper, n0=first, out=o_xy, flags=flags)
+            core.nco(X0, Y0, 0, args.nco_step, nper, n0=first, out=o_xy, flags=flags)
         elif kind == "topolar":
             vcore.topolar(xy, mag=o_mag, phase=o_ph)
         else:
@@ -320,7 +323,7 @@ def main():
             elif kind == "rotate":
                 core.rotate_host(a[ne:], a[:ne].view(np.uint32), o, device=local)
             elif kind == "nco":
-                core.nco_host(X0, Y0, 0, NCO_STEP, o, n0=first, device=local)
+                core.nco_host(X0, Y0, 0, args.nco_step, o, n0=first, device=local)
             elif kind == "topolar":
                 vcore.topolar_host(a, o[:ne], o[ne:].view(np.uint32), device=local)
             else:
@@ -373,7 +376,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": args.workload, "core": "p2r IW18 OW18 WW21 PW24 NSTAGES20" if kind in ("rotate_const", "rotate", "nco") else kind,
-                       "samples_per_gpu_per_step": nper, "phase": args.phase, "sharding": "independent shards, no data-path collective",
+                       "samples_per_gpu_per_step": nper, "phase": args.phase, "seed_mode": args.seed_mode, "sharding": "independent shards, no data-path collective",
                        "l2": "inputs+outputs per step are %.1f GiB per GPU, far larger than the 126 MB L2" % (bytes_per * nper / 2**30)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,

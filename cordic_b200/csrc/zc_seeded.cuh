@@ -47,6 +47,8 @@ struct SeedConsts {
 	int32_t  ush;		// u_left >> ush = 16*u, u = the reduced phase in LSBs, offset binary (30-PW)
 	int32_t  rsh;		// (T1 entry + 16*u) >> rsh = interval number (lgW+4)
 	int32_t  lgw;
+	uint32_t mul_r;		// 2^(28-PW): TD byte offset * mul_r + res_bias = residual phase, left-justified
+	int32_t  res_bias;	// rmin << (32-PW)
 	float    rscale, rbias;	// float rounding: fma(2^23*1.5 + v, 2^-D, 2^23*1.5*(1-2^-D)) rounds v/2^D to nearest even
 	uint32_t off_ts, off_t2, off_td;	// byte offsets of the tables in shared memory
 	int32_t  td_plane;	// bytes per TD plane (nres*16)
@@ -90,6 +92,7 @@ __device__ __forceinline__ int4 lds128(uint32_t addr) {
 
 template <int NS, int J = 0>
 struct Suffix {
+	// directions from the table: 2 shifts + 2 multiply-adds by +-1 + one negation per stage
 	static __device__ __forceinline__ void run(int &x, int &y, const int (&d)[SEED_MAX_NS], const SeedConsts &s) {
 		const int nd = -d[J];
 		const int sy = y >> s.sh[J], sx = x >> s.sh[J];
@@ -98,11 +101,25 @@ struct Suffix {
 		x = x1; y = y1;
 		Suffix<NS, J + 1>::run(x, y, d, s);
 	}
+	// directions from the phase recursion in registers (rtl/cordic.v:263-279), as in k_rotate
+	static __device__ __forceinline__ void run_reg(int &x, int &y, int &p, const CoreConsts &c, const SeedConsts &s) {
+		const int md = p >> 31;
+		const int d = md + md + 1, nd = -md - md - 1;
+		const int sy = y >> s.sh[J], sx = x >> s.sh[J];
+		const int x1 = imad(sy, nd, x);
+		const int y1 = imad(sx, d, y);
+		p = imad(d, c.na[s.M + J], p);
+		x = x1; y = y1;
+		Suffix<NS, J + 1>::run_reg(x, y, p, c, s);
+	}
 };
 template <int NS>
 struct Suffix<NS, NS> {
 	static __device__ __forceinline__ void run(int &, int &, const int (&)[SEED_MAX_NS], const SeedConsts &) {}
+	static __device__ __forceinline__ void run_reg(int &, int &, int &, const CoreConsts &, const SeedConsts &) {}
 };
+
+enum { TD_TABLE = 0, TD_REGS = 1, TD_ADAPTIVE = 2 };
 
 __device__ __forceinline__ uint32_t ldg_stream32(const uint32_t *p) {
 	uint32_t r;
@@ -123,7 +140,12 @@ __device__ __forceinline__ int round_out_fma(int v, const SeedConsts &s) {
 }
 
 // `nblocks` blocks of 128 consecutive samples; warp w of the grid takes blocks w, w+W, w+2W, ...
-template <int NS, int SRC, bool RF>
+// TDM: where the suffix directions come from.  TD_TABLE: always the TD table (fastest when neighbouring lanes
+// read neighbouring rows, i.e. sweeps and slow NCOs; bank-conflict bound for scattered phases).  TD_REGS: the
+// phase recursion in registers (3 more issue slots per stage, no table traffic).  TD_ADAPTIVE: per block of 128
+// samples the warp votes on whether its rows are an arithmetic progression of stride <= 1 row (conflict-free)
+// and takes the table path only then.
+template <int NS, int SRC, bool RF, int TDM>
 __global__ void __launch_bounds__(1024, 1)
 k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, size_t nblocks,
 		const __grid_constant__ CoreConsts c, const __grid_constant__ SeedConsts s,
@@ -181,6 +203,8 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 			}
 		}
 		int2 *const dst = xyout + (blk << 7) + lane;
+		int x[4], y[4];
+		uint32_t row16[4];
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			// octant fold (rtl/cordic.v:131-188): phase + 45 degrees; bits above PW fall off the top
@@ -189,22 +213,38 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 			const uint32_t u16 = tu >> s.ush;				// 16 * reduced phase
 			const uint32_t rank = (T1[tu >> s.bsh] + u16) >> s.rsh;		// carries past the step, if any
 			const int2 xy = T2[__funnelshift_l(tq, rank, 2)];		// row rank*4 + quarter turn
-			int x = xy.x, y = xy.y;
-			if (NS > 0) {
-				const unsigned char *row = TD + (int)(u16 - (uint32_t)TS[rank]);	// residual after M stages picks the row
-				int d[SEED_MAX_NS];
+			x[k] = xy.x; y[k] = xy.y;
+			row16[k] = u16 - (uint32_t)TS[rank];		// residual after M stages, as the byte offset of its TD row
+		}
+		bool use_table = (TDM == TD_TABLE);
+		if (NS > 0 && TDM == TD_ADAPTIVE) {
+			const uint32_t r0 = __shfl_sync(0xffffffffu, row16[0], 0), r1 = __shfl_sync(0xffffffffu, row16[0], 1);
+			const uint32_t stride = r1 - r0;		// 0 (broadcast), +-16 (neighbouring rows): conflict-free
+			const bool local = (stride + 16u <= 32u) && (row16[0] == r0 + lane * stride);
+			use_table = __all_sync(0xffffffffu, local);
+		}
 #pragma unroll
-				for (int j = 0; j < NS; j += 4) {
-					const int4 dv = *reinterpret_cast<const int4 *>(row + (j >> 2) * s.td_plane);
-					d[j] = dv.x;
-					if (j + 1 < SEED_MAX_NS) d[j + 1] = dv.y;
-					if (j + 2 < SEED_MAX_NS) d[j + 2] = dv.z;
-					if (j + 3 < SEED_MAX_NS) d[j + 3] = dv.w;
+		for (int k = 0; k < 4; k++) {
+			if (NS > 0) {
+				if (use_table) {
+					const unsigned char *row = TD + (int)row16[k];
+					int d[SEED_MAX_NS];
+#pragma unroll
+					for (int j = 0; j < NS; j += 4) {
+						const int4 dv = *reinterpret_cast<const int4 *>(row + (j >> 2) * s.td_plane);
+						d[j] = dv.x;
+						if (j + 1 < SEED_MAX_NS) d[j + 1] = dv.y;
+						if (j + 2 < SEED_MAX_NS) d[j + 2] = dv.z;
+						if (j + 3 < SEED_MAX_NS) d[j + 3] = dv.w;
+					}
+					Suffix<NS>::run(x[k], y[k], d, s);
+				} else {
+					int p = imad((int)row16[k], (int)s.mul_r, s.res_bias);	// residual phase, left-justified
+					Suffix<NS>::run_reg(x[k], y[k], p, c, s);
 				}
-				Suffix<NS>::run(x, y, d, s);
 			}
-			const int ox = RF ? round_out_fma(x, s) : round_out(x, c);
-			const int oy = RF ? round_out_fma(y, s) : round_out(y, c);
+			const int ox = RF ? round_out_fma(x[k], s) : round_out(x[k], c);
+			const int oy = RF ? round_out_fma(y[k], s) : round_out(y[k], c);
 			stg_stream64(dst + (k << 5), make_int2(ox, oy));
 		}
 	}
@@ -276,6 +316,9 @@ static bool seed_geometry(const zc_params *p, int neff, int M, std::vector<Inter
 	s.ush = 30 - p->pw;
 	s.rsh = lgw + 4;
 	if (LB < 1 || s.ush < 0 || ((uint64_t)R << (lgw + 4)) >= ((uint64_t)1 << 31)) return false;
+	if (p->pw > 28) return false;		// residual reconstruction needs 2^(28-PW)
+	s.mul_r = (uint32_t)1 << (28 - p->pw);
+	s.res_bias = (int32_t)((uint64_t)rmin << (32 - p->pw));
 	{
 		const int D = p->ww - p->ow;
 		s.rscale = 1.0f / (float)((uint32_t)1 << D);
@@ -392,23 +435,27 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, cu
 
 template <int SRC, int NS>
 struct SeedTable {
-	static cudaError_t launch(int ns, int grid, size_t smem, cudaStream_t st, const uint32_t *ph, int2 *out, size_t nblocks,
+	static cudaError_t launch(int ns, int tdm, int grid, size_t smem, cudaStream_t st, const uint32_t *ph, int2 *out, size_t nblocks,
 			const CoreConsts &c, const SeedConsts &s, const uint4 *tables) {
 		if (ns == NS) {
 			// float rounding needs every register value to fit 1.5*2^23 +- 2^22 and a rounding core (D >= 2)
 			const bool rf = c.do_round && c.wsh >= 9;
-			auto *kern = rf ? k_rotate_seeded<NS, SRC, true> : k_rotate_seeded<NS, SRC, false>;
+			typedef void (*kern_t)(const uint32_t *, int2 *, size_t, const CoreConsts, const SeedConsts, const uint4 *);
+			kern_t kern;
+			if (tdm == TD_TABLE) kern = rf ? k_rotate_seeded<NS, SRC, true, TD_TABLE> : k_rotate_seeded<NS, SRC, false, TD_TABLE>;
+			else if (tdm == TD_REGS) kern = rf ? k_rotate_seeded<NS, SRC, true, TD_REGS> : k_rotate_seeded<NS, SRC, false, TD_REGS>;
+			else kern = rf ? k_rotate_seeded<NS, SRC, true, TD_ADAPTIVE> : k_rotate_seeded<NS, SRC, false, TD_ADAPTIVE>;
 			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (e != cudaSuccess) return e;
 			kern<<<grid, 1024, smem, st>>>(ph, out, nblocks, c, s, tables);
 			return cudaGetLastError();
 		}
-		return SeedTable<SRC, NS - 1>::launch(ns, grid, smem, st, ph, out, nblocks, c, s, tables);
+		return SeedTable<SRC, NS - 1>::launch(ns, tdm, grid, smem, st, ph, out, nblocks, c, s, tables);
 	}
 };
 template <int SRC>
 struct SeedTable<SRC, -1> {
-	static cudaError_t launch(int, int, size_t, cudaStream_t, const uint32_t *, int2 *, size_t, const CoreConsts &,
+	static cudaError_t launch(int, int, int, size_t, cudaStream_t, const uint32_t *, int2 *, size_t, const CoreConsts &,
 			const SeedConsts &, const uint4 *) { return cudaErrorInvalidValue; }
 };
 
@@ -426,7 +473,8 @@ static int seeded_rotate_try(const zc_params *p, const CoreConsts &c, const uint
 	if (rc != ZC_OK) return rc;
 	if (!pl.usable) return ZC_OK;
 	const size_t smem = pl.s.total_bytes + 16;
-	cudaError_t e = SeedTable<SRC, SEED_MAX_NS>::launch(pl.NS, sms, smem, st, phase, (int2 *)xy_out, nblocks,
+	const int tdm = (flags & ZC_F_SEED_REGS) ? TD_REGS : (flags & ZC_F_SEED_ADAPTIVE) ? TD_ADAPTIVE : TD_TABLE;
+	cudaError_t e = SeedTable<SRC, SEED_MAX_NS>::launch(pl.NS, tdm, sms, smem, st, phase, (int2 *)xy_out, nblocks,
 		c, pl.s, (const uint4 *)pl.dev);
 	if (e != cudaSuccess)
 		return set_error(ZC_ECUDA, "launch of k_rotate_seeded failed: %s", cudaGetErrorString(e));

@@ -53,7 +53,8 @@ P2R_CONFIGS = {
 }
 
 
-@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED])
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED,
+                                   zc.F_FORCE_SEED | zc.F_SEED_ADAPTIVE, zc.F_FORCE_SEED | zc.F_SEED_REGS])
 @pytest.mark.parametrize("name", sorted(P2R_CONFIGS))
 def test_rotate_const_full_phase_sweep(name, flags):
     """The sweep of bench/cpp/cordic_tb.cpp:127-178: every one of the 2^PW phases, full-scale
@@ -67,7 +68,7 @@ def test_rotate_const_full_phase_sweep(name, flags):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_FORCE_SEED])
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_FORCE_SEED, zc.F_SEED_ADAPTIVE, zc.F_SEED_REGS])
 def test_rotate_const_other_vectors_and_random_phase(flags):
     core, op = both_p2r(**P2R_CONFIGS["cfg1"])
     rng = np.random.default_rng(SEED)
@@ -202,7 +203,7 @@ def test_lut_modes(kind, pw, ow):
         assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC])
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_SEED_ADAPTIVE, zc.F_SEED_REGS])
 def test_nco_stream(flags):
     core, op = both_p2r(**P2R_CONFIGS["cfg1"])
     n = (1 << 20) + 5

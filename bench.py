@@ -191,7 +191,7 @@ def main():
     ap.add_argument("--workload", default="rotate_cfg1", choices=sorted(WORKLOADS))
     ap.add_argument("--samples", type=int, default=0, help="override samples per GPU per step")
     ap.add_argument("--phase", default="sweep", choices=["sweep", "random"])
-    ap.add_argument("--seed-mode", default="table", choices=["table", "adaptive", "regs"])
+    ap.add_argument("--seed-mode", default="auto", choices=["auto", "words", "packed", "regs"])
     ap.add_argument("--nco-step", type=lambda v: int(v, 0), default=NCO_STEP)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
@@ -220,7 +220,7 @@ def main():
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
 
     flags = zc.F_NO_SEED if args.workload.endswith("_noseed") else zc.F_DEFAULT
-    flags |= {"table": 0, "adaptive": zc.F_SEED_ADAPTIVE, "regs": zc.F_SEED_REGS}[args.seed_mode]
+    flags |= {"auto": 0, "words": zc.F_SEED_WORDS, "packed": zc.F_SEED_PACKED, "regs": zc.F_SEED_REGS}[args.seed_mode]
     core = zc.Cordic(**CFG1)
     # ---- synthetic inputs, resident in HBM before the timed region (4-12 GiB: far larger than L2)
     g = torch.Generator(device=devname); g.manual_seed(20261017 + rank)

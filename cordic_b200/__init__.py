@@ -22,8 +22,9 @@ F_DEFAULT = 0
 F_FORCE_GENERIC = 1
 F_NO_SEED = 2
 F_FORCE_SEED = 4
-F_SEED_ADAPTIVE = 8
+F_SEED_PACKED = 8
 F_SEED_REGS = 16
+F_SEED_WORDS = 32
 
 MODE_P2R, MODE_R2P = 0, 1
 

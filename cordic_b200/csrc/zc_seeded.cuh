@@ -44,10 +44,11 @@ struct SeedConsts {
 	uint32_t mul_q;		// 2^(32-PW): phase*mul_q + 2^29 puts the quarter turn in bits 31:30
 	uint32_t mul_u;		// 2^(34-PW): phase*mul_u + 2^31 left-justifies the reduced phase u (PW-2 bits)
 	int32_t  bsh;		// u_left >> bsh = bucket number (32-LB)
-	int32_t  ush;		// u_left >> ush = 16*u, u = the reduced phase in LSBs, offset binary (30-PW)
-	int32_t  rsh;		// (T1 entry + 16*u) >> rsh = interval number (lgW+4)
+	int32_t  ush;		// u_left >> ush = u << lgrow, u = the reduced phase in LSBs, offset binary
+	int32_t  rsh;		// (T1 entry + (u << lgrow)) >> rsh = interval number (lgW+lgrow)
 	int32_t  lgw;
-	uint32_t mul_r;		// 2^(28-PW): TD byte offset * mul_r + res_bias = residual phase, left-justified
+	uint32_t mul_r;		// 2^(32-PW-lgrow): TD byte offset * mul_r + res_bias = residual phase, left-justified
+	int32_t  lgrow;		// log2(bytes per TD row slot): every T1/TS entry is scaled by it
 	int32_t  res_bias;	// rmin << (32-PW)
 	float    rscale, rbias;	// float rounding: fma(2^23*1.5 + v, 2^-D, 2^23*1.5*(1-2^-D)) rounds v/2^D to nearest even
 	uint32_t off_ts, off_t2, off_td;	// byte offsets of the tables in shared memory
@@ -119,7 +120,15 @@ struct Suffix<NS, NS> {
 	static __device__ __forceinline__ void run_reg(int &, int &, int &, const CoreConsts &, const SeedConsts &) {}
 };
 
-enum { TD_TABLE = 0, TD_REGS = 1, TD_ADAPTIVE = 2 };
+enum { TD_TABLE = 0, TD_REGS = 1, TD_PACKED = 2 };
+
+// Sign-extends byte `b` of w with one PRMT (selector nibble 8|b replicates that byte's sign bit;
+// __byte_perm() masks the replicate bit off, hence the PTX).
+__device__ __forceinline__ int sext_byte(uint32_t w, int b) {
+	int r;
+	asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "r"(0x8880 + 0x1111 * b));
+	return r;
+}
 
 __device__ __forceinline__ uint32_t ldg_stream32(const uint32_t *p) {
 	uint32_t r;
@@ -140,11 +149,11 @@ __device__ __forceinline__ int round_out_fma(int v, const SeedConsts &s) {
 }
 
 // `nblocks` blocks of 128 consecutive samples; warp w of the grid takes blocks w, w+W, w+2W, ...
-// TDM: where the suffix directions come from.  TD_TABLE: always the TD table (fastest when neighbouring lanes
-// read neighbouring rows, i.e. sweeps and slow NCOs; bank-conflict bound for scattered phases).  TD_REGS: the
-// phase recursion in registers (3 more issue slots per stage, no table traffic).  TD_ADAPTIVE: per block of 128
-// samples the warp votes on whether its rows are an arithmetic progression of stride <= 1 row (conflict-free)
-// and takes the table path only then.
+// TDM: where the suffix directions come from.  TD_TABLE: one 32-bit word per stage from the TD table (no unpacking;
+// fastest when neighbouring lanes read neighbouring rows -- sweeps, slow NCOs -- but two 16-byte reads per sample
+// make it bank-conflict bound for scattered phases).  TD_PACKED: one signed byte per stage (a quarter of the
+// shared-memory traffic, one PRMT per stage to unpack): the better trade for scattered phases.  TD_REGS: the phase
+// recursion in registers (3 more issue slots per stage, no table traffic).
 template <int NS, int SRC, bool RF, int TDM>
 __global__ void __launch_bounds__(1024, 1)
 k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, size_t nblocks,
@@ -216,17 +225,10 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 			x[k] = xy.x; y[k] = xy.y;
 			row16[k] = u16 - (uint32_t)TS[rank];		// residual after M stages, as the byte offset of its TD row
 		}
-		bool use_table = (TDM == TD_TABLE);
-		if (NS > 0 && TDM == TD_ADAPTIVE) {
-			const uint32_t r0 = __shfl_sync(0xffffffffu, row16[0], 0), r1 = __shfl_sync(0xffffffffu, row16[0], 1);
-			const uint32_t stride = r1 - r0;		// 0 (broadcast), +-16 (neighbouring rows): conflict-free
-			const bool local = (stride + 16u <= 32u) && (row16[0] == r0 + lane * stride);
-			use_table = __all_sync(0xffffffffu, local);
-		}
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			if (NS > 0) {
-				if (use_table) {
+				if (TDM == TD_TABLE) {
 					const unsigned char *row = TD + (int)row16[k];
 					int d[SEED_MAX_NS];
 #pragma unroll
@@ -237,6 +239,21 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 						if (j + 2 < SEED_MAX_NS) d[j + 2] = dv.z;
 						if (j + 3 < SEED_MAX_NS) d[j + 3] = dv.w;
 					}
+					Suffix<NS>::run(x[k], y[k], d, s);
+				} else if (TDM == TD_PACKED) {
+					const unsigned char *row = TD + (int)row16[k];	// 8-byte (NS<=8) or 16-byte rows
+					uint32_t w[4] = {0, 0, 0, 0};
+					if (NS <= 8) {
+						const int2 v = *reinterpret_cast<const int2 *>(row);
+						w[0] = (uint32_t)v.x; w[1] = (uint32_t)v.y;
+					} else {
+						const int4 v = *reinterpret_cast<const int4 *>(row);
+						w[0] = (uint32_t)v.x; w[1] = (uint32_t)v.y; w[2] = (uint32_t)v.z; w[3] = (uint32_t)v.w;
+					}
+					int d[SEED_MAX_NS];
+#pragma unroll
+					for (int j = 0; j < NS; j++)		// sign-extend byte j&3 of word j>>2
+						d[j] = sext_byte(w[j >> 2], j & 3);
 					Suffix<NS>::run(x[k], y[k], d, s);
 				} else {
 					int p = imad((int)row16[k], (int)s.mul_r, s.res_bias);	// residual phase, left-justified
@@ -256,6 +273,7 @@ struct SeedPlan {
 	int32_t x0c[4], y0c[4];		// the pre-rotated constant vector (identifies x0,y0 modulo IW)
 	int device = -1;
 	int NS = 0;
+	bool packed = false;
 	SeedConsts s;
 	void *dev = nullptr;		// tables, laid out as in shared memory
 	bool usable = false;		// false: geometry does not fit; cached so we do not retry
@@ -282,7 +300,7 @@ static void seed_intervals(const zc_params *p, int M, std::vector<Interval> &iv)
 	}
 }
 
-static bool seed_geometry(const zc_params *p, int neff, int M, std::vector<Interval> &iv, SeedConsts &s,
+static bool seed_geometry(const zc_params *p, int neff, int M, bool packed, std::vector<Interval> &iv, SeedConsts &s,
 		int &NS, int64_t &rmin, int64_t &rmax) {
 	NS = neff - M;
 	if (NS < 0 || NS > SEED_MAX_NS) return false;
@@ -303,8 +321,10 @@ static bool seed_geometry(const zc_params *p, int neff, int M, std::vector<Inter
 	const size_t R = iv.size();
 	const int nsp = (NS + 3) & ~3;
 	const size_t nres = (size_t)(rmax - rmin + 1);
+	// bytes per TD row slot: 16 (one int4 plane entry) or, packed, one signed byte per stage
+	const int lgrow = (packed && NS <= 8) ? 3 : 4;
 	const size_t b_t1 = (size_t)4 << LB, b_ts = (R * 4 + 15) & ~(size_t)15, b_t2 = R * 32,
-		     b_td = nres * (size_t)nsp * 4;
+		     b_td = packed ? ((nres << lgrow) + 15) & ~(size_t)15 : nres * (size_t)nsp * 4;
 	const size_t total = b_t1 + b_ts + b_t2 + b_td;
 	if (total + 16 > SEED_SMEM_LIMIT) return false;
 	if ((R << lgw) >= ((uint64_t)1 << 32)) return false;
@@ -313,11 +333,12 @@ static bool seed_geometry(const zc_params *p, int neff, int M, std::vector<Inter
 	s.mul_q = (uint32_t)1 << (32 - p->pw);
 	s.mul_u = (uint32_t)1 << (34 - p->pw);
 	s.bsh = 32 - LB;
-	s.ush = 30 - p->pw;
-	s.rsh = lgw + 4;
-	if (LB < 1 || s.ush < 0 || ((uint64_t)R << (lgw + 4)) >= ((uint64_t)1 << 31)) return false;
+	s.ush = 34 - p->pw - lgrow;
+	s.rsh = lgw + lgrow;
+	s.lgrow = lgrow;
+	if (LB < 1 || s.ush < 0 || ((uint64_t)R << (lgw + lgrow)) >= ((uint64_t)1 << 31)) return false;
 	if (p->pw > 28) return false;		// residual reconstruction needs 2^(28-PW)
-	s.mul_r = (uint32_t)1 << (28 - p->pw);
+	s.mul_r = (uint32_t)1 << (32 - p->pw - lgrow);
 	s.res_bias = (int32_t)((uint64_t)rmin << (32 - p->pw));
 	{
 		const int D = p->ww - p->ow;
@@ -349,11 +370,11 @@ static void seed_release(SeedPlan &pl) {
 }
 
 // Builds (or finds) the plan for (p, constant vector, device).  Called with the device current.
-static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, cudaStream_t st,
+static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, bool packed, cudaStream_t st,
 		SeedPlan &out) {
 	std::lock_guard<std::mutex> lk(g_seed_mu);
 	for (SeedPlan &pl : g_seed_cache) {
-		if (pl.device == device && std::memcmp(&pl.p, p, sizeof(*p)) == 0 &&
+		if (pl.device == device && pl.packed == packed && std::memcmp(&pl.p, p, sizeof(*p)) == 0 &&
 		    std::memcmp(pl.x0c, c.cx, sizeof(pl.x0c)) == 0 && std::memcmp(pl.y0c, c.cy, sizeof(pl.y0c)) == 0) {
 			pl.stamp = ++g_seed_clock;
 			out = pl;
@@ -361,7 +382,7 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, cu
 		}
 	}
 	SeedPlan pl;
-	pl.p = *p; pl.device = device; pl.stamp = ++g_seed_clock;
+	pl.p = *p; pl.device = device; pl.packed = packed; pl.stamp = ++g_seed_clock;
 	std::memcpy(pl.x0c, c.cx, sizeof(pl.x0c));
 	std::memcpy(pl.y0c, c.cy, sizeof(pl.y0c));
 	std::vector<Interval> iv;
@@ -369,7 +390,7 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, cu
 	bool ok = false;
 	const int neff = c.neff;
 	for (int M = (neff < 13 ? neff : 13); M >= 6 && !ok; M--)
-		ok = seed_geometry(p, neff, M, iv, pl.s, pl.NS, rmin, rmax);
+		ok = seed_geometry(p, neff, M, packed, iv, pl.s, pl.NS, rmin, rmax);
 	if (ok) {
 		const SeedConsts &s = pl.s;
 		const int pshift = c.pshift;
@@ -388,10 +409,10 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, cu
 				off = iv[r + 1].lo - b0;			// in [1, W-1]
 				if (r + 2 < R && iv[r + 2].lo < b0 + W) ok = false;	// two steps: refuse
 			}
-			t1[b] = (uint32_t)(16u * (uint32_t)(((uint64_t)r << s.lgw) + (uint64_t)(W - off) - ((uint64_t)b << s.lgw)));
+			t1[b] = (uint32_t)(((uint64_t)r << s.lgw) + (uint64_t)(W - off) - ((uint64_t)b << s.lgw)) << s.lgrow;
 		}
 		for (size_t k = 0; k < R && ok; k++) {
-			ts[k] = (uint32_t)(int32_t)(16 * (iv[k].S + half + rmin));
+			ts[k] = (uint32_t)(int32_t)((iv[k].S + half + rmin) * ((int64_t)1 << s.lgrow));
 			rep[k] = (uint32_t)((uint64_t)iv[k].lo << pshift);
 		}
 		const size_t nres = (size_t)(rmax - rmin + 1);
@@ -399,7 +420,10 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, cu
 			int64_t ph = res;
 			for (int j = 0; j < pl.NS; j++) {			// rtl/cordic.v:265-279, phase only
 				const bool neg = ph < 0;
-				td[((size_t)(j >> 2) * nres + (size_t)(res - rmin)) * 4 + (j & 3)] = (uint32_t)(neg ? -1 : 1);
+				if (packed)
+					reinterpret_cast<unsigned char *>(td)[((size_t)(res - rmin) << s.lgrow) + j] = (unsigned char)(neg ? 0xff : 0x01);
+				else
+					td[((size_t)(j >> 2) * nres + (size_t)(res - rmin)) * 4 + (j & 3)] = (uint32_t)(neg ? -1 : 1);
 				ph += neg ? (int64_t)p->angle[s.M + j] : -(int64_t)p->angle[s.M + j];
 			}
 		}
@@ -444,7 +468,7 @@ struct SeedTable {
 			kern_t kern;
 			if (tdm == TD_TABLE) kern = rf ? k_rotate_seeded<NS, SRC, true, TD_TABLE> : k_rotate_seeded<NS, SRC, false, TD_TABLE>;
 			else if (tdm == TD_REGS) kern = rf ? k_rotate_seeded<NS, SRC, true, TD_REGS> : k_rotate_seeded<NS, SRC, false, TD_REGS>;
-			else kern = rf ? k_rotate_seeded<NS, SRC, true, TD_ADAPTIVE> : k_rotate_seeded<NS, SRC, false, TD_ADAPTIVE>;
+			else kern = rf ? k_rotate_seeded<NS, SRC, true, TD_PACKED> : k_rotate_seeded<NS, SRC, false, TD_PACKED>;
 			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (e != cudaSuccess) return e;
 			kern<<<grid, 1024, smem, st>>>(ph, out, nblocks, c, s, tables);
@@ -468,12 +492,19 @@ static int seeded_rotate_try(const zc_params *p, const CoreConsts &c, const uint
 	if (nblocks == 0) return ZC_OK;
 	if (!(flags & ZC_F_FORCE_SEED) && n < ((size_t)1 << 20)) return ZC_OK;	// not worth the table load
 	if (c.neff < 6 || p->pw < 12) return ZC_OK;
+	// Which flavour: the caller's flag, else -- for the NCO, whose phase pattern the host knows -- packed rows when
+	// neighbouring lanes land more than one table row apart (|step| >= 2 phase LSBs), word rows otherwise.
+	int tdm = (flags & ZC_F_SEED_REGS) ? TD_REGS : (flags & ZC_F_SEED_PACKED) ? TD_PACKED : TD_TABLE;
+	if (SRC == SRC_NCO && !(flags & (ZC_F_SEED_REGS | ZC_F_SEED_PACKED | ZC_F_SEED_WORDS))) {
+		const int32_t sstep = (int32_t)c.nco_step;
+		const uint32_t mag = (uint32_t)(sstep < 0 ? -(int64_t)sstep : (int64_t)sstep);
+		if ((mag >> c.pshift) >= 2u) tdm = TD_PACKED;
+	}
 	SeedPlan pl;
-	int rc = seed_plan_get(p, c, device, st, pl);
+	int rc = seed_plan_get(p, c, device, tdm == TD_PACKED, st, pl);
 	if (rc != ZC_OK) return rc;
 	if (!pl.usable) return ZC_OK;
 	const size_t smem = pl.s.total_bytes + 16;
-	const int tdm = (flags & ZC_F_SEED_REGS) ? TD_REGS : (flags & ZC_F_SEED_ADAPTIVE) ? TD_ADAPTIVE : TD_TABLE;
 	cudaError_t e = SeedTable<SRC, SEED_MAX_NS>::launch(pl.NS, tdm, sms, smem, st, phase, (int2 *)xy_out, nblocks,
 		c, pl.s, (const uint4 *)pl.dev);
 	if (e != cudaSuccess)

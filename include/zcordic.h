@@ -73,9 +73,11 @@ enum {
 	ZC_F_FORCE_GENERIC = 1,	/* runtime-parameter kernel that models the WW-bit wrap       */
 	ZC_F_NO_SEED       = 2,	/* rotate_const/nco: run every stage in registers (no table-seeded prefix) */
 	ZC_F_FORCE_SEED    = 4,	/* rotate_const/nco: use the table-seeded prefix even for small n */
-	ZC_F_SEED_ADAPTIVE = 8,	/* seeded kernel: each warp picks table or registers for the suffix directions per 128-sample block
-				   (default: always the table -- fastest for sweeps / slow NCOs, bank-conflict bound for scattered phases) */
-	ZC_F_SEED_REGS     = 16	/* seeded kernel: always run the suffix phase recursion in registers */
+	ZC_F_SEED_PACKED   = 8,	/* seeded kernel: suffix directions as one byte per stage (less shared-memory traffic: the better
+				   choice when neighbouring samples have scattered phases; default for NCO steps >= 2 LSBs) */
+	ZC_F_SEED_REGS     = 16,	/* seeded kernel: run the suffix phase recursion in registers (no direction table) */
+	ZC_F_SEED_WORDS    = 32	/* seeded kernel: suffix directions as one word per stage (default except for fast NCOs:
+				   fastest for phase sweeps and slow NCOs) */
 };
 
 int         zc_version(void);				/* major*1000 + minor */

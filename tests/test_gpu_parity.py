@@ -54,7 +54,7 @@ P2R_CONFIGS = {
 
 
 @pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED,
-                                   zc.F_FORCE_SEED | zc.F_SEED_ADAPTIVE, zc.F_FORCE_SEED | zc.F_SEED_REGS])
+                                   zc.F_FORCE_SEED | zc.F_SEED_PACKED, zc.F_FORCE_SEED | zc.F_SEED_REGS])
 @pytest.mark.parametrize("name", sorted(P2R_CONFIGS))
 def test_rotate_const_full_phase_sweep(name, flags):
     """The sweep of bench/cpp/cordic_tb.cpp:127-178: every one of the 2^PW phases, full-scale
@@ -68,7 +68,7 @@ def test_rotate_const_full_phase_sweep(name, flags):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_FORCE_SEED, zc.F_SEED_ADAPTIVE, zc.F_SEED_REGS])
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_FORCE_SEED, zc.F_SEED_PACKED, zc.F_SEED_REGS])
 def test_rotate_const_other_vectors_and_random_phase(flags):
     core, op = both_p2r(**P2R_CONFIGS["cfg1"])
     rng = np.random.default_rng(SEED)
@@ -203,7 +203,7 @@ def test_lut_modes(kind, pw, ow):
         assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_SEED_ADAPTIVE, zc.F_SEED_REGS])
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_SEED_PACKED, zc.F_SEED_REGS, zc.F_SEED_WORDS])
 def test_nco_stream(flags):
     core, op = both_p2r(**P2R_CONFIGS["cfg1"])
     n = (1 << 20) + 5

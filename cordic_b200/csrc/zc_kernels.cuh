@@ -46,6 +46,13 @@ __device__ __forceinline__ int imad(int a, int b, int c) {
 	asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
 	return r;
 }
+// Negation kept opaque to the optimiser: left to itself it rewrites -(2m+1) as a second LOP3 on the already
+// saturated ALU pipe; as a lone `neg` ptxas emits IMAD.MOV, which runs on the light FMA pipe.
+__device__ __forceinline__ int ineg(int a) {
+	int r;
+	asm("neg.s32 %0, %1;" : "=r"(r) : "r"(a));
+	return r;
+}
 
 // ---- one micro-rotation, rotation mode (rtl/cordic.v:263-279) ---------------------------
 // d = +1 when the residual phase is >= 0, else -1.  x' = x - d*(y>>>k); y' = y + d*(x>>>k);
@@ -54,15 +61,12 @@ __device__ __forceinline__ int imad(int a, int b, int c) {
 template <int K, int FORM>
 __device__ __forceinline__ void rot_step(int &x, int &y, int &p, const int na) {
 	constexpr int S = (K + 1 > 31) ? 31 : (K + 1);
+	// Pipe budget per stage (profiles/ubench_r1.txt): the ALU pipe (shifts, LEA/IADD3) and the heavy FMA pipe
+	// (IMAD) each retire one warp-instruction per 2 clocks.  3 shifts + (2*md+1) on the ALU pipe, three IMADs
+	// on the heavy pipe, and the negation as an IMAD.MOV that ptxas places on the light FMA pipe.
 	const int md = p >> 31;
-	int d, nd;
-	if (FORM == 0) {
-		d = md | 1;
-		nd = ~md | 1;
-	} else {
-		d = imad(md, 2, 1);
-		nd = imad(md, -2, -1);
-	}
+	const int d = md + md + 1;
+	const int nd = ineg(d);
 	const int sy = y >> S, sx = x >> S;
 	const int x1 = imad(sy, nd, x);
 	const int y1 = imad(sx, d, y);
@@ -78,14 +82,8 @@ template <int K, int FORM>
 __device__ __forceinline__ void vec_step(int &x, int &y, uint32_t &ph, const int pa) {
 	constexpr int S = (K + 1 > 31) ? 31 : (K + 1);
 	const int md = y >> 31;
-	int s, ns;
-	if (FORM == 0) {
-		s = md | 1;
-		ns = ~md | 1;
-	} else {
-		s = imad(md, 2, 1);
-		ns = imad(md, -2, -1);
-	}
+	const int s = md + md + 1;
+	const int ns = ineg(s);
 	const int sy = y >> S, sx = x >> S;
 	const int x1 = imad(sy, s, x);
 	const int y1 = imad(sx, ns, y);

@@ -105,7 +105,7 @@ struct Suffix {
 	// directions from the phase recursion in registers (rtl/cordic.v:263-279), as in k_rotate
 	static __device__ __forceinline__ void run_reg(int &x, int &y, int &p, const CoreConsts &c, const SeedConsts &s) {
 		const int md = p >> 31;
-		const int d = md + md + 1, nd = -md - md - 1;
+		const int d = md + md + 1, nd = ineg(d);
 		const int sy = y >> s.sh[J], sx = x >> s.sh[J];
 		const int x1 = imad(sy, nd, x);
 		const int y1 = imad(sx, d, y);

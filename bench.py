@@ -35,6 +35,7 @@ WORKLOADS = {
     "sintable_p17": ("lut_sin", 1 << 30, 8),           # configs[3]
     "quarterwav_p18": ("lut_qwav", 1 << 30, 8),        # configs[3]
     "nco_cfg1": ("nco", 1 << 30, 8),                   # configs[4]  8 B out, no input stream
+    "quadtbl_p18": ("lut_quad", 1 << 30, 8),           # rtl/quadtbl.v, PW18/OW13
 }
 CFG1 = dict(iw=18, ow=18, xtra=2, phase_bits=24, nstages=20)
 X0, Y0 = (1 << 17) - 1, 0          # full-scale input of bench/cpp/cordic_tb.cpp:68-69
@@ -129,6 +130,11 @@ def cpu_run(kind, n, threads):
         xy = rng.integers(-32768, 32768, size=(n, 2), dtype=np.int64).astype(np.int32)
         t0 = time.perf_counter()
         zo.topolar(p, xy)
+    elif kind == "lut_quad":
+        rc, q = zo.derive_qtbl(0, 13, 2, 18)
+        phase = (np.arange(n, dtype=np.uint32) & 0x3FFFF)
+        t0 = time.perf_counter()
+        zo.quadtbl(q, phase)
     else:
         pw, ow = (17, 13) if kind == "lut_sin" else (18, 24)
         tbl = zo.sintable(pw, ow) if kind == "lut_sin" else zo.quarterwav(pw, ow)
@@ -234,17 +240,18 @@ def main():
     if kind in ("rotate", "topolar"):
         lim = 1 << 17 if kind == "rotate" else 1 << 15
         xy = torch.randint(-lim, lim, (nper, 2), dtype=torch.int32, device=devname, generator=g)
-    if kind in ("lut_sin", "lut_qwav"):
+    if kind in ("lut_sin", "lut_qwav", "lut_quad"):
         if args.phase == "sweep":
             phase = ((torch.arange(nper, dtype=torch.int64, device=devname) + first) * 4).bitwise_and_(0xFFFFFFFF).to(torch.int32)
         else:
             phase = torch.randint(-(1 << 31), 1 << 31, (nper,), dtype=torch.int64, device=devname, generator=g).to(torch.int32)
-        lut = zc.SinTable(phase_bits=17, ow=13) if kind == "lut_sin" else zc.QuarterWav(phase_bits=18, ow=24)
+        lut = (zc.SinTable(phase_bits=17, ow=13) if kind == "lut_sin" else zc.QuarterWav(phase_bits=18, ow=24)
+               if kind == "lut_qwav" else zc.QuadTbl(ow=13, phase_bits=18))
     if kind == "topolar":
         vcore = zc.Topolar(iw=16, ow=16, xtra=2)
         o_mag = torch.empty(nper, dtype=torch.int32, device=devname)
         o_ph = torch.empty(nper, dtype=torch.int32, device=devname)
-    elif kind in ("lut_sin", "lut_qwav"):
+    elif kind in ("lut_sin", "lut_qwav", "lut_quad"):
         o_val = torch.empty(nper, dtype=torch.int32, device=devname)
     else:
         o_xy = torch.empty((nper, 2), dtype=torch.int32, device=devname)
@@ -305,11 +312,11 @@ def main():
     e2e = None
     if not args.no_e2e:
         ne = nper if world == 1 else min(nper, 1 << 28)
-        in_words = {"rotate_const": ne, "rotate": 3 * ne, "nco": 0, "topolar": 2 * ne, "lut_sin": ne, "lut_qwav": ne}[kind]
-        out_words = {"rotate_const": 2 * ne, "rotate": 2 * ne, "nco": 2 * ne, "topolar": 2 * ne, "lut_sin": ne, "lut_qwav": ne}[kind]
+        in_words = {"rotate_const": ne, "rotate": 3 * ne, "nco": 0, "topolar": 2 * ne, "lut_sin": ne, "lut_qwav": ne, "lut_quad": ne}[kind]
+        out_words = {"rotate_const": 2 * ne, "rotate": 2 * ne, "nco": 2 * ne, "topolar": 2 * ne, "lut_sin": ne, "lut_qwav": ne, "lut_quad": ne}[kind]
         hin = zc.PinnedBuffer(max(in_words, 1), np.int32)
         hout = zc.PinnedBuffer(out_words, np.int32)
-        if kind in ("rotate_const", "lut_sin", "lut_qwav"):
+        if kind in ("rotate_const", "lut_sin", "lut_qwav", "lut_quad"):
             hin.array[:ne] = phase[:ne].cpu().numpy()
         elif kind == "rotate":
             hin.array[:ne] = phase[:ne].cpu().numpy(); hin.array[ne:] = xy[:ne].cpu().numpy().reshape(-1)

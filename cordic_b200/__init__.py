@@ -59,6 +59,22 @@ class Params(ctypes.Structure):
         return h
 
 
+class QuadTblParams(ctypes.Structure):
+    """zc_quadtbl (include/zcordic.h)."""
+    _fields_ = [
+        ("ow", ctypes.c_int32), ("nextra", ctypes.c_int32), ("pw", ctypes.c_int32), ("ww", ctypes.c_int32),
+        ("lgtbl", ctypes.c_int32), ("dxbits", ctypes.c_int32), ("cbits", ctypes.c_int32), ("lbits", ctypes.c_int32),
+        ("qbits", ctypes.c_int32), ("reserved", ctypes.c_int32), ("scale", ctypes.c_int64),
+        ("itbl_err", ctypes.c_double), ("tbl_err", ctypes.c_double), ("spurdb", ctypes.c_double),
+        ("ctbl", ctypes.c_uint32 * 4096), ("ltbl", ctypes.c_uint32 * 4096), ("qtbl", ctypes.c_uint32 * 4096),
+    ]
+
+    def header(self):
+        """The constant set of the generated rtl/quadtbl.h, by the reference's names."""
+        return dict(OW=self.ow, NEXTRA=self.nextra, PW=self.pw, TBL_LGSZ=self.lgtbl, TBL_SZ=1 << self.lgtbl,
+                    SCALE=self.scale, ITBL_ERR=self.itbl_err, TBL_ERR=self.tbl_err, SPURDB=self.spurdb)
+
+
 _lib = None
 
 _SIGNATURES = {
@@ -98,6 +114,11 @@ _SIGNATURES = {
                                   ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
     "zc_lut_qwav": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                    ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "zc_derive_qtbl": (ctypes.c_int, [ctypes.c_int] * 4 + [ctypes.POINTER(QuadTblParams)]),
+    "zc_quadtbl_sin": (ctypes.c_int, [ctypes.POINTER(QuadTblParams), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                      ctypes.c_int, ctypes.c_void_p]),
+    "zc_quadtbl_sin_host": (ctypes.c_int, [ctypes.POINTER(QuadTblParams), ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_size_t, ctypes.c_int]),
     "zc_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "zc_host_free": (None, [ctypes.c_void_p]),
     "zc_rotate_const_host": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32,
@@ -169,6 +190,13 @@ def derive_qtr(iw=0, pw=0, ow=0):
     a, b = ctypes.c_int(), ctypes.c_int()
     _check(lib().zc_derive_qtr(iw or 0, pw or 0, ow or 0, ctypes.byref(a), ctypes.byref(b)))
     return a.value, b.value
+
+
+def derive_qtbl(iw=0, ow=0, xtra=2, pw=0):
+    """``gencordic -t qtbl [-i iw] [-o ow] [-x xtra] [-p pw]`` (sw/main.cpp:444-484, sw/quadtbl.cpp)."""
+    q = QuadTblParams()
+    _check(lib().zc_derive_qtbl(iw or 0, ow or 0, xtra, pw or 0, ctypes.byref(q)))
+    return q
 
 
 def build_sintable(pw, ow):
@@ -388,3 +416,33 @@ class SinTable(_Lut):
 class QuarterWav(_Lut):
     """rtl/quarterwav.v: quarter-wave table with index fold and negate (``gencordic -t qtr``)."""
     QUARTER = True
+
+
+class QuadTbl:
+    """rtl/quadtbl.v: table lookup with quadratic interpolation (``gencordic -t qtbl``)."""
+
+    def __init__(self, iw=0, ow=0, xtra=2, phase_bits=0):
+        self.params = derive_qtbl(iw, ow, xtra, phase_bits)
+        for k, v in self.params.header().items():
+            setattr(self, k, v)
+
+    def tables(self):
+        n = 1 << self.params.lgtbl
+        return (np.array(self.params.ctbl[:n], dtype=np.uint32), np.array(self.params.ltbl[:n], dtype=np.uint32),
+                np.array(self.params.qtbl[:n], dtype=np.uint32))
+
+    def lookup(self, phase32, out=None, stream=None):
+        """phase32: CUDA tensor of 32-bit NCO phase words; i_phase = phase32 >> (32-PW).  Returns o_sin."""
+        torch = _torch()
+        n = phase32.numel()
+        dev = phase32.device.index or 0
+        if out is None:
+            out = torch.empty(n, dtype=torch.int32, device=phase32.device)
+        _check(lib().zc_quadtbl_sin(ctypes.byref(self.params), _dev_ptr(phase32), _dev_ptr(out, n), n, dev,
+                                    _stream_ptr(dev, stream)))
+        return out
+
+    def lookup_host(self, phase32, out, device=0):
+        n = phase32.size if isinstance(phase32, np.ndarray) else phase32.numel()
+        _check(lib().zc_quadtbl_sin_host(ctypes.byref(self.params), _host_ptr(phase32), _host_ptr(out, n), n, device))
+        return out

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libzcordic.so")
 SOURCES = ["zc_api.cu", "zc_params.cpp"]
-HEADERS = ["zc_internal.h", "zc_kernels.cuh", "zc_seeded.cuh", os.path.join(ROOT, "include", "zcordic.h")]
+HEADERS = ["zc_internal.h", "zc_kernels.cuh", "zc_seeded.cuh", "zc_quadtbl.cuh", os.path.join(ROOT, "include", "zcordic.h")]
 
 
 def _stale():

@@ -3,12 +3,14 @@
 #include "zc_internal.h"
 #include "zc_kernels.cuh"
 #include "zc_seeded.cuh"
+#include "zc_quadtbl.cuh"
 
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace zc {
 
@@ -312,6 +314,93 @@ static int launch_lut(int pw, int ow, const uint32_t *tbl, const uint32_t *phase
 	return ZC_OK;
 }
 
+// ---- quadtbl ------------------------------------------------------------------------------------
+// Device copies of coefficient tables, keyed by content (the zc_quadtbl is caller memory).
+struct QtDevTable { int device; uint64_t hash; int ntbl; int32_t *dev; bool nowrap; uint64_t stamp; };
+static std::mutex g_qt_mu;
+static std::vector<QtDevTable> g_qt_cache;
+static uint64_t g_qt_clock = 0;
+
+static uint64_t qt_hash(const zc_quadtbl *q) {
+	uint64_t h = 1469598103934665603ull;
+	auto mix = [&](uint32_t w) { h = (h ^ w) * 1099511628211ull; };
+	const int n = 1 << q->lgtbl;
+	mix((uint32_t)q->lgtbl);
+	for (int k = 0; k < n; k++) { mix(q->ctbl[k]); mix(q->ltbl[k]); mix(q->qtbl[k]); }
+	return h;
+}
+
+static inline int32_t sext32(uint32_t w, int bits) { return (int32_t)(w << (32 - bits)) >> (32 - bits); }
+
+// Uploads (once) the coefficient tables sign-extended, and decides whether the register wraps can be skipped:
+// |lsum| <= |l| + |q| (dx < 2^(DXBITS-1), so the renormalised product is at most |q|) must fit LBITS, and
+// |r| <= |c| + |l| + |q| must fit CBITS, entry by entry.
+static int qt_device_tables(const zc_quadtbl *q, int device, cudaStream_t st, const int32_t **out, bool *nowrap) {
+	const uint64_t h = qt_hash(q);
+	const int n = 1 << q->lgtbl;
+	std::lock_guard<std::mutex> lk(g_qt_mu);
+	for (QtDevTable &e : g_qt_cache)
+		if (e.device == device && e.hash == h && e.ntbl == n) {
+			e.stamp = ++g_qt_clock; *out = e.dev; *nowrap = e.nowrap;
+			return ZC_OK;
+		}
+	std::vector<int32_t> host(3 * (size_t)n);
+	bool safe = true;
+	for (int k = 0; k < n; k++) {
+		const int64_t cv = sext32(q->ctbl[k], q->cbits), lv = sext32(q->ltbl[k], q->lbits), qv = sext32(q->qtbl[k], q->qbits);
+		host[k] = (int32_t)cv; host[n + k] = (int32_t)lv; host[2 * n + k] = (int32_t)qv;
+		const int64_t al = (lv < 0 ? -lv : lv) + (qv < 0 ? -qv : qv) + 1, ac = (cv < 0 ? -cv : cv) + al + 1;
+		if (al >= ((int64_t)1 << (q->lbits - 1)) || ac >= ((int64_t)1 << (q->cbits - 1))) safe = false;
+	}
+	int32_t *dev = nullptr;
+	ZC_CUDA(cudaMalloc((void **)&dev, host.size() * 4));
+	cudaError_t e = cudaMemcpyAsync(dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	if (e != cudaSuccess) { cudaFree(dev); return set_error(ZC_ECUDA, "quadtbl table upload failed: %s", cudaGetErrorString(e)); }
+	if (g_qt_cache.size() >= 16) {
+		size_t victim = 0;
+		for (size_t k = 1; k < g_qt_cache.size(); k++) if (g_qt_cache[k].stamp < g_qt_cache[victim].stamp) victim = k;
+		cudaFree(g_qt_cache[victim].dev);
+		g_qt_cache.erase(g_qt_cache.begin() + victim);
+	}
+	g_qt_cache.push_back(QtDevTable{device, h, n, dev, safe, ++g_qt_clock});
+	*out = dev; *nowrap = safe;
+	return ZC_OK;
+}
+
+static int launch_quadtbl(const zc_quadtbl *q, const uint32_t *phase32, int32_t *out, size_t n, int device, void *stream) {
+	int rc = check_qtbl(q);
+	if (rc != ZC_OK) return rc;
+	if (n && (!phase32 || !out)) return set_error(ZC_EINVAL, "NULL buffer");
+	DeviceInfo di;
+	if ((rc = device_info(device, di)) != ZC_OK) return rc;
+	if (n == 0) return ZC_OK;
+	DeviceScope scope;
+	if ((rc = scope.enter(device)) != ZC_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	const int32_t *tables = nullptr;
+	bool nowrap = false;
+	if ((rc = qt_device_tables(q, device, st, &tables, &nowrap)) != ZC_OK) return rc;
+	QtConsts c;
+	c.pshift = 32 - q->pw; c.dxs = q->dxbits - 1; c.dxmask = (1u << (q->dxbits - 1)) - 1u;
+	c.qsh = 32 - q->qbits; c.lsh = 32 - q->lbits; c.csh = 32 - q->cbits;
+	c.xtra = q->nextra; c.rc = (1 << (q->nextra - 1)) - 1;
+	c.keep_hi = (1 << (q->ow - 1)) - 1; c.keep_lo = -(1 << (q->ow - 2));
+	c.osh = 32 - q->ow; c.ntbl = 1 << q->lgtbl;
+	const bool vec = aligned16(phase32) && aligned16(out);
+	const size_t groups = vec ? n / 4 : 0, tail = n - groups * 4;
+	const bool wide = (q->qbits + q->dxbits > 31) || (q->lbits + q->dxbits > 31);
+	const int grid = grid_for(groups ? groups : tail, di, 8);
+	const size_t smem = 3 * (size_t)c.ntbl * 4;
+#define ZC_QT_LAUNCH(W, NW)                                                                           \
+	k_quadtbl<W, NW><<<grid, 256, smem, st>>>((const int4 *)phase32, (int4 *)out, tables, groups,        \
+		phase32 + groups * 4, out + groups * 4, (int)tail, c)
+	if (wide) { if (nowrap) ZC_QT_LAUNCH(true, true); else ZC_QT_LAUNCH(true, false); }
+	else      { if (nowrap) ZC_QT_LAUNCH(false, true); else ZC_QT_LAUNCH(false, false); }
+#undef ZC_QT_LAUNCH
+	return post_launch("k_quadtbl");
+}
+
 // ---- host-buffer pipeline ---------------------------------------------------------------------
 // Streams chunks H2D -> kernel -> D2H through NBUF device buffers on three streams so copies in
 // both directions overlap compute.  `launch(chunk_index_offset, count, din0, din1, dout0, dout1,
@@ -455,6 +544,9 @@ int zc_derive_tbl(int iw, int pw, int ow, int *pw_out, int *ow_out) {
 int zc_derive_qtr(int iw, int pw, int ow, int *pw_out, int *ow_out) {
 	return derive_lut(true, iw, pw, ow, pw_out, ow_out);
 }
+int zc_derive_qtbl(int iw, int ow, int xtra_user, int pw, zc_quadtbl *out) {
+	return derive_qtbl(iw, ow, xtra_user, pw, out);
+}
 int zc_lut_build_sintable(int pw, int ow, uint32_t *tbl) { return build_sintable(pw, ow, tbl); }
 int zc_lut_build_quarterwav(int pw, int ow, uint32_t *tbl) { return build_quarterwav(pw, ow, tbl); }
 
@@ -519,6 +611,10 @@ int zc_lut_sin(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32,
 int zc_lut_qwav(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int32_t *out, size_t n,
 		int device, void *stream) {
 	return launch_lut<true>(pw, ow, tbl_dev, phase32, out, n, device, stream);
+}
+
+int zc_quadtbl_sin(const zc_quadtbl *q, const uint32_t *phase32, int32_t *out, size_t n, int device, void *stream) {
+	return launch_quadtbl(q, phase32, out, n, device, stream);
 }
 
 // ---- host buffers --------------------------------------------------------------------------
@@ -620,6 +716,18 @@ static int lut_host(bool quarter, int pw, int ow, const uint32_t *tbl_host, cons
 		if (scope.enter(device) == ZC_OK) cudaFree(tbl_dev);
 	}
 	return rc;
+}
+
+int zc_quadtbl_sin_host(const zc_quadtbl *q, const uint32_t *phase32, int32_t *out, size_t n, int device) {
+	int rc = check_qtbl(q);
+	if (rc != ZC_OK) return rc;
+	if (n && (!phase32 || !out)) return set_error(ZC_EINVAL, "NULL buffer");
+	const Lane in[2] = {{4, (const char *)phase32, nullptr}, {0, nullptr, nullptr}};
+	const Lane outl[2] = {{4, nullptr, (char *)out}, {0, nullptr, nullptr}};
+	return host_pipeline(device, n, in, outl,
+		[&](size_t, size_t cnt, char *i0, char *, char *o0, char *, cudaStream_t st) {
+			return zc_quadtbl_sin(q, (const uint32_t *)i0, (int32_t *)o0, cnt, device, st);
+		});
 }
 
 int zc_lut_sin_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int32_t *out,

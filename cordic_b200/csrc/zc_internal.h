@@ -16,6 +16,8 @@ int derive_lut(bool quarter, int iw, int pw, int ow, int *pw_out, int *ow_out);
 int check_lut(bool quarter, int pw, int ow);
 int build_sintable(int pw, int ow, uint32_t *tbl);
 int build_quarterwav(int pw, int ow, uint32_t *tbl);
+int derive_qtbl(int iw, int ow, int xtra_user, int pw, zc_quadtbl *o);
+int check_qtbl(const zc_quadtbl *q);
 
 // Validates a zc_params handed back to us across the ABI (it is caller memory).
 int check_params(const zc_params *p, int want_mode);

@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 namespace zc {
 
@@ -197,6 +198,139 @@ int build_quarterwav(int pw, int ow, uint32_t *tbl) {
 		long w = (long)(maxv * std::sin(ph));
 		tbl[k] = (uint32_t)(w & mask);
 	}
+	return ZC_OK;
+}
+
+// ---- quadratically interpolated table: gencordic -t qtbl ------------------------------------------
+namespace {
+
+struct QuadFit {			// one pass of sw/quadtbl.cpp:136-266 for a table of 2^lg entries
+	std::vector<double> c, l, q;	// constant, linear, quadratic coefficient per entry, scaled to |c| <= 1
+	double worst;			// largest signed fit error over the table (sw/quadtbl.cpp:72-114)
+};
+
+double sinc_pi(double v) { const double x = v * M_PI; return std::sin(x) / x; }	// sw/quadtbl.cpp:54-57
+
+// Largest-magnitude error of c + (l + q t) t against the sine over one table step, sampled as the
+// generator samples it: both ends and 64 interior points (sw/quadtbl.cpp:72-114).
+double fit_error(double c, double l, double q, double idx, int n) {
+	double ang = 2.0 * M_PI * idx / (double)n;
+	const double at_left = c - std::sin(ang);
+	ang = 2.0 * M_PI * (idx + 1) / (double)n;
+	const double at_right = c + l + q - std::sin(ang);
+	double inside = 0;
+	for (int k = 0; k < 64; k++) {
+		const double t = k / 64.0;
+		const double e = c + (l + q * t) * t - std::sin(2.0 * M_PI * (idx + t) / n);
+		if (std::fabs(e) > std::fabs(inside)) inside = e;
+	}
+	double worst = at_left;
+	if (std::fabs(worst) < std::fabs(at_right)) worst = at_right;
+	if (std::fabs(worst) < std::fabs(inside)) worst = inside;
+	return worst;
+}
+
+QuadFit quad_fit(int lg) {
+	const int n = 1 << lg;
+	const double half_step = M_PI / (double)n, step = half_step * 2.;
+	QuadFit f;
+	f.c.resize(n); f.l.resize(n); f.q.resize(n);
+	std::vector<double> &c = f.c, &l = f.l, &q = f.q;
+	for (int i = 0; i < n; i++) c[i] = std::sin(step * i + half_step);		// mid-interval samples
+	for (int i = 1; i < n - 1; i++) l[i] = (c[i + 1] - c[i - 1]) / 2.0;		// central difference
+	l[0] = (c[1] - c[n - 1]) / 2.0;
+	l[n - 1] = (c[0] - c[n - 2]) / 2.0;
+	for (int i = 1; i < n - 1; i++) q[i] = -(c[i] - 0.5 * (c[i + 1] + c[i - 1]));	// second difference
+	q[0] = -(c[0] - 0.5 * (c[1] + c[n - 1]));
+	q[n - 1] = -(c[n - 1] - 0.5 * (c[0] + c[n - 2]));
+	for (int i = 0; i < n; i++)							// the quadratic's own smoothing
+		c[i] = 0.75 * std::sin(step * i + half_step)
+			+ (std::sin(step * (i - 1) + half_step) + std::sin(step * (i + 1) + half_step)) / 8.0;
+	const double del = 1.0, hdel = del / 2.0;					// re-centre on the interval's left edge
+	for (int i = 0; i < n; i++) c[i] = q[i] * hdel * hdel - l[i] * hdel + c[i];
+	for (int i = 0; i < n; i++) l[i] = l[i] - del * q[i];
+	const double gain = std::pow(1. / sinc_pi(half_step), 3);			// undo the interpolator's droop
+	for (int i = 0; i < n; i++) c[i] *= gain;
+	for (int i = 0; i < n; i++) l[i] *= gain;
+	for (int i = 0; i < n; i++) q[i] *= gain;
+	double peak = 0.0;
+	for (int i = 0; i < n; i++) peak = (peak > std::fabs(c[i])) ? peak : std::fabs(c[i]);
+	for (int i = 0; i < n; i++) c[i] *= 1. / peak;
+	for (int i = 0; i < n; i++) l[i] *= 1. / peak;
+	for (int i = 0; i < n; i++) q[i] *= 1. / peak;
+	f.worst = 0.0;
+	for (int i = 0; i < n; i++) {
+		const double e = fit_error(c[i], l[i], q[i], i, n);
+		if (std::fabs(e) > std::fabs(f.worst)) f.worst = e;
+	}
+	return f;
+}
+
+double peak_of(const std::vector<double> &v) {
+	double m = 0.0;
+	for (double x : v) m = (m > std::fabs(x)) ? m : std::fabs(x);
+	return m;
+}
+
+} // namespace
+
+int derive_qtbl(int iw, int ow, int xtra_user, int pw, zc_quadtbl *o) {
+	if (!o) return set_error(ZC_EINVAL, "NULL zc_quadtbl");
+	resolve_widths(iw, ow);						// sw/main.cpp:446-454
+	const int wide = (ow > iw) ? ow : iw;
+	int nxtra = xtra_user + 1;					// :456
+	if (pw <= 0) {
+		const int ww_cli = wide + nxtra;
+		if (ww_cli < 1 || ww_cli > 62) return set_error(ZC_ERANGE, "working width %d out of range", ww_cli);
+		pw = calc_phase_bits(ww_cli);				// :458-459
+	}
+	const int wid = ow + nxtra;					// the width the tables are built for
+	if (nxtra < 0 || pw <= 4 || pw > 32 || wid <= 6 || wid > 30)
+		return set_error(ZC_ERANGE, "quadtbl needs XTRA>=0, 4<PW<=32, 6<OW+XTRA<=30 (got OW=%d XTRA=%d PW=%d)", ow, nxtra, pw);
+	const long fullscale = (1l << (wid - 1)) - 2l;			// max_integer(), sw/quadtbl.cpp:59-61
+	// sw/quadtbl.cpp:295-301: double the table until the fit error is under one output unit
+	int lg = 3;
+	QuadFit fit;
+	double tblerr;
+	do {
+		lg++;
+		if (lg > ZC_QT_MAXLG) return set_error(ZC_ERANGE, "quadtbl would need more than 2^%d entries", ZC_QT_MAXLG);
+		fit = quad_fit(lg);
+		tblerr = fit.worst * fullscale;
+	} while (std::fabs(tblerr) > 1.0 && lg < 20);
+	if (pw <= lg) return set_error(ZC_ERANGE, "PW=%d too small for a 2^%d-entry table", pw, lg);
+	std::memset(o, 0, sizeof(*o));
+	// coefficient widths: sw/quadtbl.cpp:236-238
+	o->cbits = wid + (int)std::ceil(std::log(peak_of(fit.c)) / std::log(2.0));
+	o->lbits = wid + (int)std::ceil(-std::log(1. / peak_of(fit.l)) / std::log(2.0));
+	o->qbits = wid + (int)std::ceil(-std::log(1. / peak_of(fit.q)) / std::log(2.0));
+	if (nxtra < 2) nxtra = 2;					// sw/quadtbl.cpp:315-316 (after the tables!)
+	o->ow = ow; o->nextra = nxtra; o->pw = pw; o->ww = ow + nxtra;
+	o->lgtbl = lg; o->dxbits = pw - lg + 1;
+	o->scale = (1l << (ow - 1)) - 2l;				// :789-790
+	o->itbl_err = tblerr;
+	o->tbl_err = tblerr * std::pow(0.5, wid);			// :793-795
+	o->spurdb = 20. * std::log(std::pow(sinc_pi(1.0 - (1. / (1 << lg))), 3.)) / std::log(10.0);	// :797-799
+	if (o->cbits < 2 || o->cbits > 30 || o->lbits < 2 || o->qbits < 2)
+		return set_error(ZC_ERANGE, "quadtbl coefficient widths out of range");
+	const long cm = (1l << o->cbits) - 1l, lm = (1l << o->lbits) - 1l, qm = (1l << o->qbits) - 1l;
+	for (int k = 0; k < (1 << lg); k++) {				// :250-266 + sw/hexfile.cpp:78-89
+		o->ctbl[k] = (uint32_t)((long)(fullscale * fit.c[k]) & cm);
+		o->ltbl[k] = (uint32_t)((long)(fullscale * fit.l[k]) & lm);
+		o->qtbl[k] = (uint32_t)((long)(fullscale * fit.q[k]) & qm);
+	}
+	return check_qtbl(o);
+}
+
+// What the kernel implements: CBITS == WW (true whenever -x >= 1), nested coefficient widths, and
+// products that fit 62 bits.
+int check_qtbl(const zc_quadtbl *q) {
+	if (!q) return set_error(ZC_EINVAL, "NULL zc_quadtbl");
+	if (q->lgtbl < 1 || q->lgtbl > ZC_QT_MAXLG || q->pw <= q->lgtbl || q->pw > 32 || q->dxbits != q->pw - q->lgtbl + 1 ||
+	    q->dxbits < 2 || q->ow < 2 || q->nextra < 2 || q->ww != q->ow + q->nextra || q->cbits != q->ww || q->cbits > 30 ||
+	    q->lbits < q->qbits + 1 || q->cbits < q->lbits + 1 || q->qbits < 2 || q->lbits + q->dxbits > 62)
+		return set_error(ZC_ERANGE, "unsupported quadtbl geometry OW=%d XTRA=%d PW=%d LGTBL=%d CBITS=%d LBITS=%d QBITS=%d",
+			q->ow, q->nextra, q->pw, q->lgtbl, q->cbits, q->lbits, q->qbits);
 	return ZC_OK;
 }
 

@@ -67,6 +67,22 @@ typedef struct zc_params {
 	double	 best_cnr;		/* BEST_POSSIBLE_CNR (p2r only, else 0)             */
 } zc_params;
 
+/* The quadratically interpolated sine table of `gencordic -t qtbl` (rtl/quadtbl.v, rtl/quadtbl.h):
+ * its localparams (rtl/quadtbl.v:49-51,65-71), the header constants (rtl/quadtbl.h) and the three
+ * $readmemh coefficient tables (rtl/quadtbl_{c,l,q}tbl.hex), words masked to CBITS/LBITS/QBITS. */
+#define ZC_QT_MAXLG 12
+typedef struct zc_quadtbl {
+	int32_t	 ow, nextra;		/* OW, NEXTRA (= XTRA)                               */
+	int32_t	 pw, ww;		/* PW, WW = OW+XTRA                                  */
+	int32_t	 lgtbl, dxbits;		/* LGTBL, DXBITS = PW-LGTBL+1                        */
+	int32_t	 cbits, lbits, qbits;	/* CBITS, LBITS, QBITS                               */
+	int32_t	 reserved;
+	int64_t	 scale;			/* SCALE                                             */
+	double	 itbl_err, tbl_err;	/* ITBL_ERR, TBL_ERR                                 */
+	double	 spurdb;		/* SPURDB                                            */
+	uint32_t ctbl[1 << ZC_QT_MAXLG], ltbl[1 << ZC_QT_MAXLG], qtbl[1 << ZC_QT_MAXLG];
+} zc_quadtbl;
+
 /* flags for the *_ex entry points */
 enum {
 	ZC_F_DEFAULT       = 0,
@@ -98,6 +114,10 @@ int zc_derive_r2p(int iw, int ow, int xtra_user, int pw, int nstages, zc_params 
 int zc_derive_tbl(int iw, int pw, int ow, int *pw_out, int *ow_out);
 /* gencordic -t qtr ...                       sw/main.cpp:401-422 ; limit sw/sintable.cpp:190 */
 int zc_derive_qtr(int iw, int pw, int ow, int *pw_out, int *ow_out);
+
+/* gencordic -t qtbl [-i iw] [-o ow] [-p pw] [-x xtra]   sw/main.cpp:444-484, sw/quadtbl.cpp:136-304
+ * (table growth until the table error is below one unit, coefficient widths, the three tables). */
+int zc_derive_qtbl(int iw, int ow, int xtra_user, int pw, zc_quadtbl *out);
 
 /* The $readmemh table contents (host side; same libm as the generator so the words equal
  * rtl/sintable.hex / rtl/quarterwav.hex).  Words are masked to OW bits as hextable() writes
@@ -140,6 +160,10 @@ int zc_lut_sin(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32,
 int zc_lut_qwav(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int32_t *out,
 		size_t n, int device, void *stream);
 
+/* rtl/quadtbl.v:143-291: table lookup + quadratic interpolation + overflow-safe convergent rounding.
+ * phase32 is a 32-bit NCO word; the core sees i_phase = phase32 >> (32-PW).  out[i] = o_sin. */
+int zc_quadtbl_sin(const zc_quadtbl *q, const uint32_t *phase32, int32_t *out, size_t n, int device, void *stream);
+
 /* ---- the data path, host buffers (end-to-end) ---------------------------------------- */
 
 void *zc_host_alloc(size_t bytes);		/* pinned; NULL on failure */
@@ -157,6 +181,7 @@ int zc_lut_sin_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *ph
 		int32_t *out, size_t n, int device);
 int zc_lut_qwav_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32,
 		int32_t *out, size_t n, int device);
+int zc_quadtbl_sin_host(const zc_quadtbl *q, const uint32_t *phase32, int32_t *out, size_t n, int device);
 
 /* Number of kernel launches this library has enqueued from the calling process so far
  * (all devices); lets a benchmark report how many of OUR kernels ran in a timed region. */

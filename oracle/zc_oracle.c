@@ -426,6 +426,187 @@ int32_t zo_quarterwav_lookup1(int pw, int ow, const uint32_t *tbl, uint32_t phas
 	return (int32_t)sx((int64_t)v, ow);
 }
 
+/* ---- quadratic-interpolation core: sw/quadtbl.cpp + rtl/quadtbl.v -------- */
+
+/* sw/quadtbl.cpp:54-57 */
+static double qt_sinc(double v) {
+	double x = v * M_PI;
+	return sin(x) / x;
+}
+
+/* sw/quadtbl.cpp:72-114 */
+static double qt_est_max_err(double c, double l, double q, double idx, int N) {
+	double lft, rht, mid, ph;
+	ph = 2.0 * M_PI * idx / (double)N;
+	lft = c - sin(ph);
+	ph = 2.0 * M_PI * (idx + 1) / (double)N;
+	rht = c + l + q - sin(ph);
+	mid = 0;
+	for (int k = 0; k < 64; k++) {
+		double mer, mph, mdx;
+		mdx = k / 64.0;
+		mph = 2.0 * M_PI * (idx + mdx) / N;
+		mer = c + (l + q * mdx) * mdx - sin(mph);
+		if (fabs(mer) > fabs(mid))
+			mid = mer;
+	}
+	double er = lft;
+	if (fabs(er) < fabs(rht))
+		er = rht;
+	if (fabs(er) < fabs(mid))
+		er = mid;
+	return er;
+}
+
+/* sw/quadtbl.cpp:136-266: coefficient tables, their widths and the table error */
+static void qt_build(int lgsz, int wid, int *cbits, int *lbits, int *qbits, double *tblerr,
+		long *ct, long *lt, long *qt) {
+	int ln = (1 << lgsz);
+	long maxv = (1l << (wid - 1)) - 2l;		/* max_integer(): :59-61 */
+	double dl = M_PI / (double)ln, dph = dl * 2.;
+	double *table = (double *)malloc(sizeof(double) * ln);
+	double *slope = (double *)malloc(sizeof(double) * ln);
+	double *dslope = (double *)malloc(sizeof(double) * ln);
+	int i;
+	for (i = 0; i < ln; i++)
+		table[i] = sin(dph * i + dl);
+	for (i = 1; i < ln - 1; i++)
+		slope[i] = (table[i + 1] - table[i - 1]) / 2.0;
+	slope[0] = (table[1] - table[ln - 1]) / 2.0;
+	slope[ln - 1] = (table[0] - table[ln - 2]) / 2.0;
+	for (i = 1; i < ln - 1; i++)
+		dslope[i] = -(table[i] - 0.5 * (table[i + 1] + table[i - 1]));
+	dslope[0] = -(table[0] - 0.5 * (table[1] + table[ln - 1]));
+	dslope[ln - 1] = -(table[ln - 1] - 0.5 * (table[0] + table[ln - 2]));
+	for (i = 0; i < ln; i++)
+		table[i] = 0.75 * sin(dph * i + dl)
+			+ (sin(dph * (i - 1) + dl) + sin(dph * (i + 1) + dl)) / 8.0;
+	const double del = 1.0, hlfdel = del / 2.0;
+	for (i = 0; i < ln; i++)
+		table[i] = dslope[i] * hlfdel * hlfdel - slope[i] * hlfdel + table[i];
+	for (i = 0; i < ln; i++)
+		slope[i] = slope[i] - del * dslope[i];
+	double fctr = pow(1. / qt_sinc(dl), 3);
+	for (i = 0; i < ln; i++) table[i] *= fctr;
+	for (i = 0; i < ln; i++) slope[i] *= fctr;
+	for (i = 0; i < ln; i++) dslope[i] *= fctr;
+	double mxtbl = 0.0, mxslope = 0.0, mxdslope = 0.0;
+	for (i = 0; i < ln; i++)
+		mxtbl = (mxtbl > fabs(table[i])) ? mxtbl : fabs(table[i]);
+	for (i = 0; i < ln; i++) table[i] *= 1. / mxtbl;
+	for (i = 0; i < ln; i++) slope[i] *= 1. / mxtbl;
+	for (i = 0; i < ln; i++) dslope[i] *= 1. / mxtbl;
+	double mxerr = 0.0, err;
+	for (i = 0; i < ln; i++) {
+		err = qt_est_max_err(table[i], slope[i], dslope[i], i, ln);
+		if (fabs(err) > fabs(mxerr))
+			mxerr = err;
+	}
+	mxerr *= maxv;
+	*tblerr = mxerr;
+	mxtbl = 0.0;
+	for (i = 0; i < ln; i++)
+		mxtbl = (mxtbl > fabs(table[i])) ? mxtbl : fabs(table[i]);
+	for (i = 0; i < ln; i++) {
+		mxslope = (mxslope > fabs(slope[i])) ? mxslope : fabs(slope[i]);
+		mxdslope = (mxdslope > fabs(dslope[i])) ? mxdslope : fabs(dslope[i]);
+	}
+	*cbits = wid + (int)ceil(log(mxtbl) / log(2.0));
+	*lbits = wid + (int)ceil(-log(1. / mxslope) / log(2.0));
+	*qbits = wid + (int)ceil(-log(1. / mxdslope) / log(2.0));
+	for (i = 0; i < ln; i++) {
+		ct[i] = (long)(maxv * table[i]);
+		lt[i] = (long)(maxv * slope[i]);
+		qt[i] = (long)(maxv * dslope[i]);
+	}
+	free(table); free(slope); free(dslope);
+}
+
+int zo_derive_qtbl(int iw, int ow, int xtra_user, int pw, zo_quadtbl *q) {
+	memset(q, 0, sizeof(*q));
+	default_widths(&iw, &ow);			/* sw/main.cpp:446-454 */
+	int mx = (ow > iw) ? ow : iw;
+	int nxtra = xtra_user + 1;			/* :456 */
+	int ww_main = mx + nxtra;
+	if (pw <= 0)
+		pw = zo_calc_phase_bits(ww_main);	/* :458-459 */
+	if (nxtra < 0 || pw <= 4 || pw > 32)
+		return -1;
+	/* sw/quadtbl.cpp:295-301: grow the table until the table error is below one unit */
+	int lgtbl = 3, cbits = 0, lbits = 0, qbits = 0;
+	double tblerr = 0;
+	static long ct[1 << ZO_QT_MAXLG], lt[1 << ZO_QT_MAXLG], qt[1 << ZO_QT_MAXLG];
+	if (ow + nxtra <= 6 || ow + nxtra > 30)
+		return -1;
+	do {
+		lgtbl++;
+		if (lgtbl > ZO_QT_MAXLG)
+			return -1;
+		qt_build(lgtbl, ow + nxtra, &cbits, &lbits, &qbits, &tblerr, ct, lt, qt);
+	} while ((fabs(tblerr) > 1.0) && (lgtbl < 20));
+	if (pw <= lgtbl)
+		return -1;
+	int wid = ow + nxtra;
+	if (nxtra < 2)					/* :315-316 */
+		nxtra = 2;
+	q->ow = ow; q->nextra = nxtra; q->pw = pw; q->ww = ow + nxtra;
+	q->lgtbl = lgtbl; q->dxbits = pw - lgtbl + 1;
+	q->cbits = cbits; q->lbits = lbits; q->qbits = qbits;
+	q->scale = (1l << (ow - 1)) - 2l;		/* :789-790 */
+	q->itbl_err = tblerr;
+	q->tbl_err = tblerr * pow(0.5, wid);		/* :793-795 (ow + nxtra before the clamp) */
+	{
+		double spur = pow(qt_sinc(1.0 - (1. / (1 << lgtbl))), 3.);
+		q->spurdb = 20. * log(spur) / log(10.0);	/* :797-799 */
+	}
+	long cm = (1l << cbits) - 1l, lm = (1l << lbits) - 1l, qm = (1l << qbits) - 1l;
+	for (int k = 0; k < (1 << lgtbl); k++) {
+		q->ctbl[k] = (uint32_t)(ct[k] & cm);
+		q->ltbl[k] = (uint32_t)(lt[k] & lm);
+		q->qtbl[k] = (uint32_t)(qt[k] & qm);
+	}
+	/* widths this restatement (and the engine) accept: what every sane command line produces */
+	if (q->cbits != q->ww || q->lbits < q->qbits + 1 || q->cbits < q->lbits + 1 || q->dxbits < 2
+			|| q->qbits < 2 || q->cbits > 30 || q->lbits + q->dxbits > 62)
+		return -2;
+	return 0;
+}
+
+/* rtl/quadtbl.v:143-291 */
+int32_t zo_quadtbl1(const zo_quadtbl *q, uint32_t phase) {
+	const int PW = q->pw, DX = q->dxbits, QB = q->qbits, LB = q->lbits, CB = q->cbits;
+	const int WW = q->ww, OW = q->ow, XTRA = q->nextra;
+	uint64_t ip = ux(phase, PW);
+	uint32_t idx = (uint32_t)(ip >> (DX - 1));			/* i_phase[(PW-1):(DXBITS-1)] */
+	int64_t qv = sx(q->qtbl[idx], QB), lv = sx(q->ltbl[idx], LB), cv = sx(q->ctbl[idx], CB);
+	int64_t dx = (int64_t)(ip & ((1ull << (DX - 1)) - 1ull));	/* { 1'b0, i_phase[(DXBITS-2):0] } */
+	int64_t qprod = sx(qv * dx, QB + DX);				/* :173 */
+	/* :196-199: w_qprod = { sign..., qprod[(QBITS+DXBITS-1):(DXBITS-1)] } -- an arithmetic shift */
+	int64_t w_qprod = sx(qprod >> (DX - 1), LB);
+	int64_t lsum = sx(w_qprod + lv, LB);				/* :205 */
+	int64_t lprod = sx(lsum * dx, LB + DX);				/* :231 */
+	int64_t w_lprod = sx(lprod >> (DX - 1), CB);			/* :247-248 */
+	int64_t r = sx(w_lprod + cv, CB);				/* :254 */
+	uint64_t rb = ux((uint64_t)r, CB);
+	uint64_t w;
+	/* :262-271: do not round when that would overflow the WW-bit word */
+	uint64_t mid_hi = (rb >> XTRA) & ((1ull << (WW - 1 - XTRA)) - 1ull);	/* r[(WW-2):XTRA] */
+	uint64_t mid_lo = (WW - 2 - XTRA > 0) ? ((rb >> XTRA) & ((1ull << (WW - 2 - XTRA)) - 1ull)) : 0;	/* r[(WW-3):XTRA] */
+	int top = (int)((rb >> (WW - 1)) & 1), top2 = (int)((rb >> (WW - 2)) & 3);
+	if (!top && mid_hi == ((1ull << (WW - 1 - XTRA)) - 1ull))
+		w = rb;
+	else if (top2 == 3 && mid_lo == 0)
+		w = rb;
+	else {
+		int D = WW - OW;
+		int b = (int)((rb >> D) & 1);
+		uint64_t add = b ? (1ull << (D - 1)) : ((1ull << (D - 1)) - 1ull);
+		w = rb + add;
+	}
+	w = ux(w, WW);
+	return (int32_t)sx((int64_t)(w >> XTRA), OW);			/* o_sin <= w_value[(WW-1):XTRA] */
+}
+
 /* ---- batched forms ----------------------------------------------------- */
 
 typedef struct job {
@@ -440,10 +621,11 @@ typedef struct job {
 	uint64_t n0;
 	int pw, ow;
 	const uint32_t *tbl;
+	const zo_quadtbl *qt;
 	size_t lo, hi;
 } job;
 
-enum { K_ROTC, K_ROT, K_TOPOLAR, K_NCO, K_SIN, K_QWAV };
+enum { K_ROTC, K_ROT, K_TOPOLAR, K_NCO, K_SIN, K_QWAV, K_QTBL };
 
 static void run_range(const job *j) {
 	size_t i;
@@ -477,6 +659,10 @@ static void run_range(const job *j) {
 	case K_QWAV:
 		for (i = j->lo; i < j->hi; i++)
 			j->out0[i] = zo_quarterwav_lookup1(j->pw, j->ow, j->tbl, j->phase_in[i]);
+		break;
+	case K_QTBL:
+		for (i = j->lo; i < j->hi; i++)
+			j->out0[i] = zo_quadtbl1(j->qt, j->phase_in[i]);
 		break;
 	}
 }
@@ -555,6 +741,12 @@ void zo_lut_qwav(int pw, int ow, const uint32_t *tbl, const uint32_t *phase32,
 		int32_t *out, size_t n, int nthreads) {
 	job j; memset(&j, 0, sizeof(j));
 	j.kind = K_QWAV; j.pw = pw; j.ow = ow; j.tbl = tbl; j.phase_in = phase32; j.out0 = out;
+	run_parallel(&j, n, nthreads);
+}
+
+void zo_quadtbl_batch(const zo_quadtbl *q, const uint32_t *phase, int32_t *out, size_t n, int nthreads) {
+	job j; memset(&j, 0, sizeof(j));
+	j.kind = K_QTBL; j.qt = q; j.phase_in = phase; j.out0 = out;
 	run_parallel(&j, n, nthreads);
 }
 

@@ -105,6 +105,24 @@ void	zo_lut_sin(int pw, int ow, const uint32_t *tbl, const uint32_t *phase32,
 void	zo_lut_qwav(int pw, int ow, const uint32_t *tbl, const uint32_t *phase32,
 		int32_t *out, size_t n, int nthreads);
 
+/* ---- quadratically interpolated sine table: sw/quadtbl.cpp, rtl/quadtbl.v ------------------ */
+#define ZO_QT_MAXLG 12
+typedef struct zo_quadtbl {
+	int	ow, nextra;	/* OW, NEXTRA (XTRA) as printed in rtl/quadtbl.h		*/
+	int	pw, ww;		/* PW ; WW = OW+XTRA						*/
+	int	lgtbl, dxbits, cbits, lbits, qbits;	/* localparams of rtl/quadtbl.v:65-71		*/
+	long	scale;		/* SCALE  = max_integer(ow)					*/
+	double	itbl_err;	/* ITBL_ERR (the loop's tblerr)					*/
+	double	tbl_err;	/* TBL_ERR							*/
+	double	spurdb;		/* SPURDB							*/
+	uint32_t ctbl[1 << ZO_QT_MAXLG], ltbl[1 << ZO_QT_MAXLG], qtbl[1 << ZO_QT_MAXLG];	/* $readmemh words */
+} zo_quadtbl;
+/* gencordic -t qtbl [-i iw] [-o ow] [-p pw] [-x xtra]: sw/main.cpp:444-484 + sw/quadtbl.cpp:270-304 */
+int	zo_derive_qtbl(int iw, int ow, int xtra_user, int pw, zo_quadtbl *q);
+/* rtl/quadtbl.v:143-291, one sample; phase is the PW-bit port word */
+int32_t	zo_quadtbl1(const zo_quadtbl *q, uint32_t phase);
+void	zo_quadtbl_batch(const zo_quadtbl *q, const uint32_t *phase, int32_t *out, size_t n, int nthreads);
+
 /* sw/hexfile.cpp:78-89 -- parse a $readmemh file written by hextable(). Returns #words. */
 long	zo_hex_load(const char *fname, uint32_t *words, long maxwords);
 

@@ -67,6 +67,18 @@ LUT_MATRIX = [
 ]
 
 
+# (name, iw, ow, xtra, pw) for -t qtbl
+QTBL_MATRIX = [
+    ("qtbl_shipped", None, 13, None, 18),          # sw/Makefile:173-178 (NB=13, PB=18)
+    ("qtbl_o13_pauto", None, 13, None, None),
+    ("qtbl_o16_p20", None, 16, None, 20),
+    ("qtbl_o10_p14_x1", None, 10, 1, 14),
+    ("qtbl_o20_p24", None, 20, None, 24),
+    ("qtbl_i12_o14_x3", 12, 14, 3, 22),
+    ("qtbl_o8_p12", None, 8, None, 12),
+]
+
+
 def run_gen(args, cwd):
     r = subprocess.run([GEN] + args, cwd=cwd, capture_output=True, text=True)
     return r.returncode, r.stdout + r.stderr
@@ -158,11 +170,39 @@ def main():
                 "head": [int(v) for v in arr[:16]],
                 "tail": [int(v) for v in arr[-16:]],
             }
+        qtbls = {}
+        for name, iw, ow, x, pw in QTBL_MATRIX:
+            d = os.path.join(td, name)
+            os.makedirs(d)
+            args = ["-vca", "-t", "qtbl", "-f", "quadtbl.v", "-c"]
+            if iw is not None: args += ["-i", str(iw)]
+            if ow is not None: args += ["-o", str(ow)]
+            if x is not None: args += ["-x", str(x)]
+            if pw is not None: args += ["-p", str(pw)]
+            rc, log = run_gen(args, d)
+            assert rc == 0, (name, log)
+            hdr = {}
+            for line in open(os.path.join(d, "quadtbl.h")):
+                m = re.match(r"const\s+(int|long|double|bool)\s+(\w+)\s*=\s*([^;]+);", line)
+                if m:
+                    hdr[m.group(2)] = m.group(3).strip()
+            txt = open(os.path.join(d, "quadtbl.v")).read()
+            lp = {k: int(re.search(k + r"\s*=\s*(\d+)", txt).group(1)) for k in ("LGTBL", "QBITS", "LBITS", "CBITS")}
+            lp["XTRA"] = int(re.search(r"XTRA=\s*(\d+)", txt).group(1))
+            qtbls[name] = {
+                "args": {"iw": iw, "ow": ow, "xtra": x, "pw": pw}, "cmdline": " ".join(args),
+                "header": hdr, "localparams": lp,
+                "ctbl": load_hex(os.path.join(d, "quadtbl_ctbl.hex")),
+                "ltbl": load_hex(os.path.join(d, "quadtbl_ltbl.hex")),
+                "qtbl": load_hex(os.path.join(d, "quadtbl_qtbl.hex")),
+            }
+    with open(os.path.join(HERE, "gen_quadtbl.json"), "w") as f:
+        json.dump(qtbls, f, indent=1, sort_keys=True)
     with open(os.path.join(HERE, "gen_params.json"), "w") as f:
         json.dump(params, f, indent=1, sort_keys=True)
     with open(os.path.join(HERE, "gen_luts.json"), "w") as f:
         json.dump(luts, f, indent=1, sort_keys=True)
-    print("wrote", len(params), "cordic configs and", len(luts), "LUT configs")
+    print("wrote", len(params), "cordic configs,", len(luts), "LUT configs and", len(qtbls), "quadtbl configs")
 
 
 if __name__ == "__main__":

@@ -203,6 +203,42 @@ def test_lut_modes(kind, pw, ow):
         assert np.array_equal(got, want)
 
 
+QTBL_CONFIGS = {
+    "shipped": dict(ow=13, pw=18),                     # rtl/quadtbl.h
+    "o13_pauto": dict(ow=13),
+    "o16_p20": dict(ow=16, pw=20),
+    "o10_p14_x1": dict(ow=10, xtra=1, pw=14),
+    "o20_p24": dict(ow=20, pw=24),
+    "o8_p12": dict(ow=8, pw=12),
+    "o16_p32": dict(ow=16, pw=32),                     # 25-bit dx: the 64-bit product path
+}
+
+
+@pytest.mark.parametrize("name", sorted(QTBL_CONFIGS))
+def test_quadtbl_every_phase(name):
+    """rtl/quadtbl.v over every phase (bench/cpp/quadtbl_tb.cpp:96-121 sweeps the same), ragged and random too."""
+    cfg = QTBL_CONFIGS[name]
+    core = zc.QuadTbl(ow=cfg["ow"], xtra=cfg.get("xtra", 2), phase_bits=cfg.get("pw", 0))
+    rc, q = zo.derive_qtbl(0, cfg["ow"], cfg.get("xtra", 2), cfg.get("pw", 0))
+    assert rc == 0 and core.PW == q.pw
+    pw = q.pw
+    rng = np.random.default_rng(SEED + 9)
+    if pw <= 24:
+        port = np.arange(1 << pw, dtype=np.uint32)
+    else:
+        port = rng.integers(0, 1 << pw, size=1 << 22, dtype=np.uint64).astype(np.uint32)
+        port[:4] = [0, 1, (1 << pw) - 1, 1 << (pw - 1)]
+    words = (port.astype(np.uint64) << (32 - pw)).astype(np.uint32) | rng.integers(0, 1 << (32 - pw), size=port.size, dtype=np.uint64).astype(np.uint32)
+    got = host(core.lookup(dev(words)))
+    assert np.array_equal(got, zo.quadtbl(q, port))
+    for m in (1, 3, 5, 1023):            # ragged sizes, misaligned start
+        got = host(core.lookup(dev(words)[1:1 + m]))
+        assert np.array_equal(got, zo.quadtbl(q, port[1:1 + m]))
+    out = np.empty(port.size, dtype=np.int32)
+    core.lookup_host(words, out)
+    assert np.array_equal(out, zo.quadtbl(q, port))
+
+
 @pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_SEED_PACKED, zc.F_SEED_REGS, zc.F_SEED_WORDS])
 def test_nco_stream(flags):
     core, op = both_p2r(**P2R_CONFIGS["cfg1"])

@@ -41,6 +41,12 @@ def test_reference_topolar_tb_over_gpu():
     assert "Max phase     error: 6.40" in r.stdout and "Max magnitude error:  0.870814" in r.stdout
 
 
+def test_reference_quadtbl_tb_over_gpu():
+    r = run("quadtbl_tb_gpu_shipped")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "SUCCESS!!" in r.stdout and "MXERR: 1.565887" in r.stdout and "SFDR =   89.37 dBc" in r.stdout
+
+
 @pytest.mark.skipif(not os.environ.get("ZC_SLOW"), reason="2^24 clocked ticks through 22-sample batches: ~1 min; set ZC_SLOW=1")
 def test_reference_cordic_tb_cfg1_over_gpu():
     r = run("cordic_tb_gpu_cfg1", timeout=900)

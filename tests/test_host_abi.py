@@ -13,7 +13,7 @@ import pytest
 import cordic_b200 as zc
 from . import zo
 from .conftest import ROOT
-from .test_oracle_golden import LUTS, PARAMS, check_against_generator
+from .test_oracle_golden import LUTS, PARAMS, QTBLS, check_against_generator, check_quadtbl_against_generator
 
 
 @pytest.mark.parametrize("name", sorted(PARAMS))
@@ -53,6 +53,16 @@ def test_lut_build_matches_generator(name):
     assert tbl.size == g["nwords"]
     assert hashlib.sha256(tbl.astype("<u4").tobytes()).hexdigest() == g["sha256_le_u32"]
     assert [int(v) for v in tbl[::g["stride"]]] == g["samples"]
+
+
+@pytest.mark.parametrize("name", sorted(QTBLS))
+def test_quadtbl_derive_matches_generator_and_oracle(name):
+    a = QTBLS[name]["args"]
+    x = 2 if a["xtra"] is None else a["xtra"]
+    q = zc.derive_qtbl(a["iw"], a["ow"], x, a["pw"])
+    check_quadtbl_against_generator(name, q)
+    rc, o = zo.derive_qtbl(a["iw"], a["ow"], x, a["pw"])
+    assert rc == 0 and (q.itbl_err, q.tbl_err, q.spurdb) == (o.itbl_err, o.tbl_err, o.spurdb)
 
 
 def test_generator_limits_are_enforced():
@@ -175,3 +185,24 @@ def test_zcordic_gen_hex_matches_generator(name, tmp_path):
     assert hashlib.sha256(words.astype("<u4").tobytes()).hexdigest() == g["sha256_le_u32"]
     if g["mode"] == "tbl" and (g["pw"], g["ow"]) == (17, 13) and os.path.exists("/root/reference/rtl/sintable.hex"):
         assert open(hexfile, "rb").read() == open("/root/reference/rtl/sintable.hex", "rb").read()
+
+
+@pytest.mark.parametrize("name", sorted(QTBLS))
+def test_zcordic_gen_quadtbl_matches_generator(name, tmp_path):
+    g = QTBLS[name]
+    a = g["args"]
+    args = ["-ca", "-t", "qtbl", "-f", "quadtbl.v"]
+    for flag, key in (("-i", "iw"), ("-o", "ow"), ("-x", "xtra"), ("-p", "pw")):
+        if a[key] is not None:
+            args += [flag, str(a[key])]
+    r = _gen(args, str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    got = {}
+    for line in open(os.path.join(str(tmp_path), "quadtbl.h")):
+        m = re.match(r"const\s+(int|long|double|bool)\s+(\w+)\s*=\s*([^;]+);", line)
+        if m:
+            got[m.group(2)] = m.group(3).strip()
+    assert got == g["header"]
+    for nm in "clq":
+        words = zo.hex_load(os.path.join(str(tmp_path), "quadtbl_%stbl.hex" % nm), 4096)
+        assert words.tolist() == g[nm + "tbl"]

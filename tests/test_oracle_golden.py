@@ -19,6 +19,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 PARAMS = json.load(open(os.path.join(GOLD, "gen_params.json")))
 LUTS = json.load(open(os.path.join(GOLD, "gen_luts.json")))
 KATS = json.load(open(os.path.join(GOLD, "survey_kats.json")))
+QTBLS = json.load(open(os.path.join(GOLD, "gen_quadtbl.json")))
 
 
 def header_strings(p, mode):
@@ -109,6 +110,53 @@ def test_oracle_matches_survey_known_answers(name):
             assert xy[:8, 1].tolist() == s["first8_y"]
 
 
+def quadtbl_header_strings(q):
+    """rtl/quadtbl.h as sw/quadtbl.cpp:783-799 prints it."""
+    return {"OW": "%d" % q.ow, "NEXTRA": "%d" % q.nextra, "PW": "%d" % q.pw, "TBL_LGSZ": "%d" % q.lgtbl,
+            "TBL_SZ": "%d" % (1 << q.lgtbl), "SCALE": "%d" % q.scale, "ITBL_ERR": "%.2f" % q.itbl_err,
+            "TBL_ERR": "%.16f" % q.tbl_err, "SPURDB": "%6.2f" % q.spurdb}
+
+
+def check_quadtbl_against_generator(name, q):
+    g = QTBLS[name]
+    want = {k: v for k, v in g["header"].items() if k not in ("HAS_RESET", "HAS_AUX")}
+    got = quadtbl_header_strings(q)
+    got["SPURDB"] = got["SPURDB"].strip()
+    assert got == want, name
+    lp = g["localparams"]
+    assert (q.lgtbl, q.qbits, q.lbits, q.cbits, q.nextra) == (lp["LGTBL"], lp["QBITS"], lp["LBITS"], lp["CBITS"], lp["XTRA"])
+    n = 1 << q.lgtbl
+    assert list(q.ctbl[:n]) == g["ctbl"] and list(q.ltbl[:n]) == g["ltbl"] and list(q.qtbl[:n]) == g["qtbl"], name
+
+
+@pytest.mark.parametrize("name", sorted(QTBLS))
+def test_oracle_quadtbl_matches_generator(name):
+    a = QTBLS[name]["args"]
+    rc, q = zo.derive_qtbl(a["iw"], a["ow"], 2 if a["xtra"] is None else a["xtra"], a["pw"])
+    assert rc == 0
+    check_quadtbl_against_generator(name, q)
+
+
+@pytest.mark.skipif(not has_reference(), reason="reference tree not mounted")
+def test_oracle_quadtbl_matches_checked_in_hex():
+    rc, q = zo.derive_qtbl(0, 13, 2, 18)
+    for nm, arr in (("c", q.ctbl), ("l", q.ltbl), ("q", q.qtbl)):
+        want = zo.hex_load("/root/reference/rtl/quadtbl_%stbl.hex" % nm, 64)
+        assert np.array_equal(np.array(arr[:64], dtype=np.uint32), want)
+
+
+def test_oracle_quadtbl_passes_the_testbench_criterion():
+    """bench/cpp/quadtbl_tb.cpp:146-177: max |sin(ph)*(2^(OW-1)-1) - o_sin| over all 2^PW phases must stay
+    below |TBL_ERR| + 2; extremes are the values the survey of the shipped core gives."""
+    rc, q = zo.derive_qtbl(0, 13, 2, 18)
+    n = 1 << q.pw
+    ph = np.arange(n, dtype=np.uint32)
+    out = zo.quadtbl(q, ph)
+    ideal = np.sin(ph * (2.0 * np.pi / n)) * ((1 << (q.ow - 1)) - 1)
+    assert np.abs(ideal - out).max() <= abs(q.tbl_err) + 2.0
+    assert out.max() == 4095 and out.min() == -4096
+
+
 def test_oracle_wraps_at_working_width():
     """The oracle models the WW-bit registers: a configuration too narrow for its own gain
     overflows in the RTL, and the restatement must overflow identically (not saturate)."""
@@ -147,6 +195,14 @@ def test_reference_topolar_tb_passes_over_oracle():
     assert r.returncode == 0, r.stdout
     assert "SUCCESS" in r.stdout and "Max phase     error: 6.40" in r.stdout
     assert "Max magnitude error:  0.870814" in r.stdout
+
+
+def test_reference_quadtbl_tb_passes_over_oracle():
+    """bench/cpp/quadtbl_tb.cpp, unmodified, shipped core: its threshold (:175-177) passes."""
+    r = _run_tb("quadtbl_tb_shipped")
+    assert r.returncode == 0, r.stdout
+    assert "SUCCESS!!" in r.stdout and "MXERR: 1.565887" in r.stdout
+    assert "MXVAL: 0x00000fff" in r.stdout and "MNVAL: 0xfffff000" in r.stdout
 
 
 def test_reference_topolar_tb_cfg2_is_out_of_its_tuned_range():

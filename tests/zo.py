@@ -15,6 +15,14 @@ class ZoParams(ctypes.Structure):
                 ("qvar", ctypes.c_double), ("pvar_rad", ctypes.c_double), ("best_cnr", ctypes.c_double)]
 
 
+class ZoQuadTbl(ctypes.Structure):
+    _fields_ = [("ow", ctypes.c_int), ("nextra", ctypes.c_int), ("pw", ctypes.c_int), ("ww", ctypes.c_int),
+                ("lgtbl", ctypes.c_int), ("dxbits", ctypes.c_int), ("cbits", ctypes.c_int), ("lbits", ctypes.c_int),
+                ("qbits", ctypes.c_int), ("scale", ctypes.c_long), ("itbl_err", ctypes.c_double),
+                ("tbl_err", ctypes.c_double), ("spurdb", ctypes.c_double),
+                ("ctbl", ctypes.c_uint32 * 4096), ("ltbl", ctypes.c_uint32 * 4096), ("qtbl", ctypes.c_uint32 * 4096)]
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -34,6 +42,10 @@ def lib():
         L.zo_quarterwav_build.argtypes = [ci, ci, vp]
         L.zo_lut_sin.argtypes = [ci, ci, vp, vp, vp, sz, ci]
         L.zo_lut_qwav.argtypes = [ci, ci, vp, vp, vp, sz, ci]
+        L.zo_derive_qtbl.argtypes = [ci] * 4 + [ctypes.POINTER(ZoQuadTbl)]
+        L.zo_quadtbl1.argtypes = [ctypes.POINTER(ZoQuadTbl), u32]
+        L.zo_quadtbl1.restype = i32
+        L.zo_quadtbl_batch.argtypes = [ctypes.POINTER(ZoQuadTbl), vp, vp, sz, ci]
         L.zo_hex_load.argtypes = [ctypes.c_char_p, vp, ctypes.c_long]
         L.zo_hex_load.restype = ctypes.c_long
         _lib = L
@@ -140,3 +152,17 @@ def hex_load(path, maxwords):
     n = lib().zo_hex_load(path.encode(), w.ctypes.data, maxwords)
     assert n >= 0, n
     return w[:n]
+
+
+def derive_qtbl(iw=0, ow=0, xtra=2, pw=0):
+    q = ZoQuadTbl()
+    rc = lib().zo_derive_qtbl(iw or 0, ow or 0, xtra, pw or 0, ctypes.byref(q))
+    return rc, q
+
+
+def quadtbl(q, phase_port):
+    """phase_port: the PW-bit i_phase words (not 32-bit NCO words)."""
+    phase_port = _c(phase_port, np.uint32)
+    out = np.empty(phase_port.size, dtype=np.int32)
+    lib().zo_quadtbl_batch(ctypes.byref(q), phase_port.ctypes.data, out.ctypes.data, phase_port.size, NTHREADS)
+    return out

@@ -119,6 +119,12 @@ _SIGNATURES = {
                                       ctypes.c_int, ctypes.c_void_p]),
     "zc_quadtbl_sin_host": (ctypes.c_int, [ctypes.POINTER(QuadTblParams), ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.c_size_t, ctypes.c_int]),
+    "zc_nco_mix": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64,
+                                  ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "zc_nco_mix_host": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                       ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
+    "zc_hex_write": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
+    "zc_hex_read": (ctypes.c_long, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]),
     "zc_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "zc_host_free": (None, [ctypes.c_void_p]),
     "zc_rotate_const_host": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32,
@@ -197,6 +203,20 @@ def derive_qtbl(iw=0, ow=0, xtra=2, pw=0):
     q = QuadTblParams()
     _check(lib().zc_derive_qtbl(iw or 0, ow or 0, xtra, pw or 0, ctypes.byref(q)))
     return q
+
+
+def hex_write(path, words, bits):
+    """Write a $readmemh file in the reference's layout (sw/hexfile.cpp:78-89)."""
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    _check(lib().zc_hex_write(path.encode(), w.ctypes.data, w.size, bits))
+
+
+def hex_read(path, max_words=1 << 26):
+    w = np.zeros(max_words, dtype=np.uint32)
+    n = lib().zc_hex_read(path.encode(), w.ctypes.data, max_words)
+    if n < 0:
+        _check(int(n))
+    return w[:n].copy()
 
 
 def build_sintable(pw, ow):
@@ -323,6 +343,17 @@ class Cordic:
         _check(lib().zc_nco_rotate_ex(ctypes.byref(self.params), int(x0), int(y0), int(phase0) & 0xFFFFFFFF,
                                       int(step) & 0xFFFFFFFF, int(n0), _dev_ptr(out, 2 * n), n, dev,
                                       _stream_ptr(dev, stream), flags))
+        return out
+
+    def mix(self, xy, phase0, step, n0=0, out=None, stream=None):
+        """NCO mixer: rotate each (x, y) of ``xy`` by phase0 + (n0+i)*step (32-bit accumulator)."""
+        torch = _torch()
+        n = xy.numel() // 2
+        dev = xy.device.index or 0
+        if out is None:
+            out = torch.empty((n, 2), dtype=torch.int32, device=xy.device)
+        _check(lib().zc_nco_mix(ctypes.byref(self.params), _dev_ptr(xy, 2 * n), int(phase0) & 0xFFFFFFFF,
+                                int(step) & 0xFFFFFFFF, int(n0), _dev_ptr(out, 2 * n), n, dev, _stream_ptr(dev, stream)))
         return out
 
     # host buffers (end to end) -----------------------------------------------------------

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -215,13 +216,13 @@ static int launch_rotate(const zc_params *p, CoreConsts &c, const uint32_t *phas
 	if ((rc = scope.enter(device)) != ZC_OK) return rc;
 	cudaStream_t st = (cudaStream_t)stream;
 
-	const bool vec_ok = aligned16(xy_out) && (SRC == SRC_NCO || aligned16(phase)) &&
-		(SRC != SRC_XY || aligned16(xy_in));
+	constexpr bool has_phase = (SRC == SRC_CONST || SRC == SRC_XY), has_xy = (SRC == SRC_XY || SRC == SRC_MIX);
+	const bool vec_ok = aligned16(xy_out) && (!has_phase || aligned16(phase)) && (!has_xy || aligned16(xy_in));
 	const bool fast = !(flags & ZC_F_FORCE_GENERIC) && fast_path_is_exact(p) && vec_ok &&
 		c.neff >= 1 && c.neff <= 32;
 	size_t done = 0;
 	if (fast) {
-		if constexpr (SRC != SRC_XY) if (!(flags & ZC_F_NO_SEED)) {
+		if constexpr (SRC == SRC_CONST || SRC == SRC_NCO) if (!(flags & ZC_F_NO_SEED)) {
 			// 4-byte phase words and 8-byte (x,y) pairs: natural alignment is all this path needs
 			rc = seeded_rotate_try<SRC>(p, c, phase, xy_out, n, device, di.sms, st, flags, done);
 			if (rc != ZC_OK) return rc;
@@ -604,6 +605,17 @@ int zc_nco_rotate(const zc_params *p, int32_t x0, int32_t y0, uint32_t phase0, u
 	return zc_nco_rotate_ex(p, x0, y0, phase0, step, n0, xy, n, device, stream, ZC_F_DEFAULT);
 }
 
+int zc_nco_mix(const zc_params *p, const int32_t *xy_in, uint32_t phase0, uint32_t step, uint64_t n0,
+		int32_t *xy_out, size_t n, int device, void *stream) {
+	int rc = check_params(p, ZC_MODE_P2R);
+	if (rc != ZC_OK) return rc;
+	if (n && (!xy_in || !xy_out)) return set_error(ZC_EINVAL, "NULL buffer");
+	CoreConsts c;
+	fill_consts(p, c);
+	c.nco_phase0 = phase0; c.nco_step = step; c.nco_n0 = (uint32_t)n0;
+	return launch_rotate<SRC_MIX>(p, c, nullptr, xy_in, xy_out, n, device, stream, ZC_F_DEFAULT);
+}
+
 int zc_lut_sin(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int32_t *out, size_t n,
 		int device, void *stream) {
 	return launch_lut<false>(pw, ow, tbl_dev, phase32, out, n, device, stream);
@@ -716,6 +728,51 @@ static int lut_host(bool quarter, int pw, int ow, const uint32_t *tbl_host, cons
 		if (scope.enter(device) == ZC_OK) cudaFree(tbl_dev);
 	}
 	return rc;
+}
+
+int zc_nco_mix_host(const zc_params *p, const int32_t *xy_in, uint32_t phase0, uint32_t step, uint64_t n0,
+		int32_t *xy_out, size_t n, int device) {
+	int rc = check_params(p, ZC_MODE_P2R);
+	if (rc != ZC_OK) return rc;
+	if (n && (!xy_in || !xy_out)) return set_error(ZC_EINVAL, "NULL buffer");
+	const Lane in[2] = {{8, (const char *)xy_in, nullptr}, {0, nullptr, nullptr}};
+	const Lane out[2] = {{8, nullptr, (char *)xy_out}, {0, nullptr, nullptr}};
+	return host_pipeline(device, n, in, out,
+		[&](size_t off, size_t cnt, char *i0, char *, char *o0, char *, cudaStream_t st) {
+			return zc_nco_mix(p, (const int32_t *)i0, phase0, step, n0 + off, (int32_t *)o0, cnt, device, st);
+		});
+}
+
+// $readmemh files in the layout of sw/hexfile.cpp:78-89 ("@%08x " every 8 words, "%0*lx " per word)
+int zc_hex_write(const char *path, const uint32_t *words, size_t nwords, int bits) {
+	if (!path || !words || bits < 1 || bits > 32) return set_error(ZC_EINVAL, "bad argument");
+	FILE *fp = fopen(path, "w");
+	if (!fp) return set_error(ZC_EINVAL, "cannot open %s for writing", path);
+	const int nc = (bits + 3) / 4;
+	const uint32_t mask = (bits >= 32) ? 0xffffffffu : ((1u << bits) - 1u);
+	for (size_t k = 0; k < nwords; k++) {
+		if (k % 8 == 0) fprintf(fp, "%s@%08x ", k ? "\n" : "", (unsigned)k);
+		fprintf(fp, "%0*lx ", nc, (unsigned long)(words[k] & mask));
+	}
+	fprintf(fp, "\n");
+	fclose(fp);
+	return ZC_OK;
+}
+
+long zc_hex_read(const char *path, uint32_t *words, size_t max_words) {
+	if (!path || !words) return set_error(ZC_EINVAL, "bad argument");
+	FILE *fp = fopen(path, "r");
+	if (!fp) return set_error(ZC_EINVAL, "cannot open %s", path);
+	size_t addr = 0, count = 0;
+	char tok[64];
+	while (fscanf(fp, "%63s", tok) == 1) {
+		if (tok[0] == '@') { addr = strtoul(tok + 1, nullptr, 16); continue; }
+		if (addr >= max_words) { fclose(fp); return set_error(ZC_ERANGE, "%s holds more than %zu words", path, max_words); }
+		words[addr++] = (uint32_t)strtoul(tok, nullptr, 16);
+		if (addr > count) count = addr;
+	}
+	fclose(fp);
+	return (long)count;
 }
 
 int zc_quadtbl_sin_host(const zc_quadtbl *q, const uint32_t *phase32, int32_t *out, size_t n, int device) {

@@ -22,7 +22,8 @@
 
 namespace zc {
 
-enum Source { SRC_CONST = 0, SRC_XY = 1, SRC_NCO = 2 };
+// SRC_MIX: per-sample (x,y) like SRC_XY, phase from the NCO accumulator like SRC_NCO (a complex mixer)
+enum Source { SRC_CONST = 0, SRC_XY = 1, SRC_NCO = 2, SRC_MIX = 3 };
 
 // Per-launch constants (kernel parameter => constant bank).
 struct CoreConsts {
@@ -151,7 +152,7 @@ k_rotate(const int4 *__restrict__ phase4, const int4 *__restrict__ xyin4,
 	for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
 		uint32_t P[4];
 		int x[4], y[4];
-		if (SRC == SRC_NCO) {
+		if (SRC == SRC_NCO || SRC == SRC_MIX) {
 			const uint32_t base = c.nco_phase0 + (c.nco_n0 + (uint32_t)(g << 2)) * c.nco_step;
 			const uint32_t keep = ~((1u << c.pshift) - 1u);	// i_phase = phase32 >> (32-PW)
 #pragma unroll
@@ -163,7 +164,7 @@ k_rotate(const int4 *__restrict__ phase4, const int4 *__restrict__ xyin4,
 			P[2] = (uint32_t)pv.z << c.pshift; P[3] = (uint32_t)pv.w << c.pshift;
 		}
 		int ex[4], ey[4];
-		if (SRC == SRC_XY) {
+		if (SRC == SRC_XY || SRC == SRC_MIX) {
 			const int4 a = ldg_stream(xyin4 + 2 * g), b = ldg_stream(xyin4 + 2 * g + 1);
 			const int raw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -177,7 +178,7 @@ k_rotate(const int4 *__restrict__ phase4, const int4 *__restrict__ xyin4,
 		for (int s = 0; s < 4; s++) {
 			int p;
 			const int q = octant(P[s], p);
-			if (SRC == SRC_XY) {
+			if (SRC == SRC_XY || SRC == SRC_MIX) {
 				quarter_turn(q, ex[s], ey[s], x[s], y[s]);
 			} else {
 				const int xa = (q & 1) ? c.cx[1] : c.cx[0], ya = (q & 1) ? c.cy[1] : c.cy[0];
@@ -238,7 +239,7 @@ k_rotate_generic(const uint32_t *__restrict__ phase, const int32_t *__restrict__
 	const size_t stride = (size_t)gridDim.x * blockDim.x;
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
 		uint32_t P;
-		if (SRC == SRC_NCO) {
+		if (SRC == SRC_NCO || SRC == SRC_MIX) {
 			const uint32_t keep = ~((1u << c.pshift) - 1u);
 			P = (c.nco_phase0 + (c.nco_n0 + (uint32_t)i) * c.nco_step) & keep;
 		} else {
@@ -247,7 +248,7 @@ k_rotate_generic(const uint32_t *__restrict__ phase, const int32_t *__restrict__
 		int p;
 		const int q = octant(P, p);
 		int x, y;
-		if (SRC == SRC_XY) {
+		if (SRC == SRC_XY || SRC == SRC_MIX) {
 			const int ex = (xyin[2 * i] << c.in_shl) >> c.in_shr;
 			const int ey = (xyin[2 * i + 1] << c.in_shl) >> c.in_shr;
 			quarter_turn(q, ex, ey, x, y);

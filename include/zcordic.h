@@ -153,6 +153,10 @@ int zc_nco_rotate(const zc_params *p, int32_t x0, int32_t y0, uint32_t phase0, u
 		uint64_t n0, int32_t *xy, size_t n, int device, void *stream);
 int zc_nco_rotate_ex(const zc_params *p, int32_t x0, int32_t y0, uint32_t phase0, uint32_t step,
 		uint64_t n0, int32_t *xy, size_t n, int device, void *stream, uint32_t flags);
+/* NCO -> complex mixer: rotate the per-sample vector (xy_in[2i], xy_in[2i+1]) by the accumulating phase of
+ * zc_nco_rotate -- rtl/cordic.v fed by a phase accumulator, the down-converter the README's blog list builds. */
+int zc_nco_mix(const zc_params *p, const int32_t *xy_in, uint32_t phase0, uint32_t step, uint64_t n0,
+		int32_t *xy_out, size_t n, int device, void *stream);
 /* rtl/sintable.v:71-75 / rtl/quarterwav.v:92-109.  phase32 is a 32-bit NCO word; the core
  * sees i_phase = phase32 >> (32-pw).  tbl_dev: the table of zc_lut_build_* in device memory. */
 int zc_lut_sin(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int32_t *out,
@@ -182,6 +186,13 @@ int zc_lut_sin_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *ph
 int zc_lut_qwav_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32,
 		int32_t *out, size_t n, int device);
 int zc_quadtbl_sin_host(const zc_quadtbl *q, const uint32_t *phase32, int32_t *out, size_t n, int device);
+int zc_nco_mix_host(const zc_params *p, const int32_t *xy_in, uint32_t phase0, uint32_t step, uint64_t n0,
+		int32_t *xy_out, size_t n, int device);
+
+/* $readmemh files in the layout hextable() writes (sw/hexfile.cpp:78-89): exchange LUTs with FPGA flows.
+ * zc_hex_read returns the number of words read (>= 0) or a negative zc_status. */
+int  zc_hex_write(const char *path, const uint32_t *words, size_t nwords, int bits);
+long zc_hex_read(const char *path, uint32_t *words, size_t max_words);
 
 /* Number of kernel launches this library has enqueued from the calling process so far
  * (all devices); lets a benchmark report how many of OUR kernels ran in a timed region. */

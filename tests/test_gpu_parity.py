@@ -249,6 +249,19 @@ def test_nco_stream(flags):
         assert np.array_equal(got, want), (phase0, step, n0)
 
 
+def test_nco_mixer():
+    """zc_nco_mix == zc_rotate fed with the NCO's phases (and the oracle), including a ragged, offset stream."""
+    core, op = both_p2r(**P2R_CONFIGS["cfg1"])
+    rng = np.random.default_rng(SEED + 11)
+    n = (1 << 20) + 7
+    xy = rng.integers(-(1 << 17), 1 << 17, size=(n, 2), dtype=np.int64).astype(np.int32)
+    for phase0, step, n0 in [(0, 0x01234567, 0), (0xCAFEF00D, 0xFFFF0001, 999)]:
+        phase = ((phase0 + (n0 + np.arange(n, dtype=np.uint64)) * step) & 0xFFFFFFFF).astype(np.uint32) >> 8
+        want = zo.rotate(op, xy, phase)
+        assert np.array_equal(host(core.mix(dev(xy), phase0, step, n0=n0)), want)
+        assert np.array_equal(host(core.mix(dev(xy)[1:], phase0, step, n0=n0 + 1)), want[1:])
+
+
 def test_nco_chunks_concatenate():
     """Rank r of G computes n in [r*N/G, (r+1)*N/G) from phase0 + n*step alone."""
     core, op = both_p2r(**P2R_CONFIGS["cfg1"])

@@ -52,3 +52,23 @@ def test_reference_cordic_tb_cfg1_over_gpu():
     r = run("cordic_tb_gpu_cfg1", timeout=900)
     assert r.returncode == 0 and "SUCCESS!!" in r.stdout
     assert "AVG Err: 0.597045" in r.stdout and "MAX Err: 2.345266" in r.stdout and "SFDR =  124.03 dBc" in r.stdout
+
+
+def test_gpu_scoring_equals_the_test_bench_printout():
+    """cordic_b200.score restates the TB maths on the GPU; its figures must equal what the reference's own test
+    benches print for the same cores (the strings asserted above), to the printed precision."""
+    import cordic_b200 as zc
+    from cordic_b200 import score
+    r = score.score_rotation(zc.Cordic(iw=13, ow=13, xtra=2))
+    assert r["passed"] and abs(r["avg_err"] - 0.558302) < 2e-6 and abs(r["max_err"] - 1.924713) < 2e-6
+    assert abs(r["cnr_db"] - 78.63) < 0.006 and abs(r["sfdr_dbc"] - 93.88) < 0.006 and abs(r["alpha"] - 1.000001) < 2e-6
+    r = score.score_rotation(zc.Cordic(iw=18, ow=18, xtra=2, phase_bits=24, nstages=20))
+    assert r["passed"] and abs(r["avg_err"] - 0.597045) < 2e-6 and abs(r["max_err"] - 2.345266) < 2e-6
+    assert abs(r["cnr_db"] - 108.15) < 0.006 and abs(r["sfdr_dbc"] - 124.03) < 0.02
+    t = score.score_topolar(zc.Topolar(iw=13, ow=13, xtra=2))
+    assert t["passed"] and abs(t["max_phase_err"] - 6.40) < 0.006 and abs(t["max_mag_err"] - 0.870814) < 2e-6
+    t = score.score_topolar(zc.Topolar(iw=16, ow=16, xtra=2))
+    assert not t["passed"] and abs(t["max_phase_err"] - 9.23) < 0.006      # see test_oracle_golden: TB tuned for 13 bits
+    q = zc.QuadTbl(ow=13, phase_bits=18)
+    s = score.score_sine(q.lookup, 18, 13)
+    assert abs(s["max_err"] - 1.565887) < 2e-6 and (s["max"], s["min"]) == (4095, -4096) and abs(s["sfdr_dbc"] - 89.37) < 0.006

@@ -206,3 +206,14 @@ def test_zcordic_gen_quadtbl_matches_generator(name, tmp_path):
     for nm in "clq":
         words = zo.hex_load(os.path.join(str(tmp_path), "quadtbl_%stbl.hex" % nm), 4096)
         assert words.tolist() == g[nm + "tbl"]
+
+
+def test_hex_roundtrip_and_reference_layout(tmp_path):
+    """zc_hex_write produces the byte layout of sw/hexfile.cpp:78-89 and zc_hex_read parses it back."""
+    tbl = zc.build_sintable(17, 13)
+    path = os.path.join(str(tmp_path), "sintable.hex")
+    zc.hex_write(path, tbl, 13)
+    assert np.array_equal(zc.hex_read(path), tbl)
+    if os.path.exists("/root/reference/rtl/sintable.hex"):
+        assert open(path, "rb").read() == open("/root/reference/rtl/sintable.hex", "rb").read()
+        assert np.array_equal(zc.hex_read("/root/reference/rtl/quarterwav.hex"), zc.build_quarterwav(18, 24))

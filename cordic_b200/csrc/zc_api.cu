@@ -224,9 +224,10 @@ static int launch_rotate(const zc_params *p, CoreConsts &c, const uint32_t *phas
 	if (fast) {
 		if constexpr (SRC == SRC_CONST || SRC == SRC_NCO) if (!(flags & ZC_F_NO_SEED)) {
 			// 4-byte phase words and 8-byte (x,y) pairs: natural alignment is all this path needs
-			rc = seeded_rotate_try<SRC>(p, c, phase, xy_out, n, device, di.sms, st, flags, done);
+			int launched = 0;
+			rc = seeded_rotate_try<SRC>(p, c, phase, xy_out, n, device, di.sms, st, flags, done, launched);
 			if (rc != ZC_OK) return rc;
-			if (done) g_launches.fetch_add(1, std::memory_order_relaxed);
+			g_launches.fetch_add((uint64_t)launched, std::memory_order_relaxed);
 		}
 		const size_t groups = (n - done) / 4;
 		if (groups) {

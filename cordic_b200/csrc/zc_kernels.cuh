@@ -113,7 +113,7 @@ struct Unroll<N, N> {
 // Convergent rounding and truncation to OW bits (rtl/cordic.v:290-295,311-312).
 __device__ __forceinline__ int round_out(int v, const CoreConsts &c) {
 	const int b = (v >> c.D) & c.do_round;
-	return (v + c.rc + b) >> c.D;
+	return (int)((uint32_t)v + (uint32_t)c.rc + (uint32_t)b) >> c.D;	// unsigned add: WW may be 32
 }
 
 // Octant pre-rotation of the phase (rtl/cordic.v:131-188): returns the quarter-turn count q
@@ -259,15 +259,18 @@ k_rotate_generic(const uint32_t *__restrict__ phase, const int32_t *__restrict__
 		for (int k = 0; k < c.neff; k++) {
 			const int sh = (k + 1 > 31) ? 31 : (k + 1);
 			const int sy = y >> sh, sx = x >> sh;
+			const uint32_t ux = (uint32_t)x, uy = (uint32_t)y;	// unsigned: the sums may wrap (WW up to 32)
 			if (p < 0) {
-				x = wrapw(x + sy, c.wsh); y = wrapw(y - sx, c.wsh); p += (int)c.pa[k];
+				x = wrapw((int)(ux + (uint32_t)sy), c.wsh); y = wrapw((int)(uy - (uint32_t)sx), c.wsh);
+				p = (int)((uint32_t)p + c.pa[k]);
 			} else {
-				x = wrapw(x - sy, c.wsh); y = wrapw(y + sx, c.wsh); p -= (int)c.pa[k];
+				x = wrapw((int)(ux - (uint32_t)sy), c.wsh); y = wrapw((int)(uy + (uint32_t)sx), c.wsh);
+				p = (int)((uint32_t)p - c.pa[k]);
 			}
 		}
 		const int bx = (x >> c.D) & c.do_round, by = (y >> c.D) & c.do_round;
-		xyout[2 * i] = wrapw(x + c.rc + bx, c.wsh) >> c.D;
-		xyout[2 * i + 1] = wrapw(y + c.rc + by, c.wsh) >> c.D;
+		xyout[2 * i] = wrapw((int)((uint32_t)x + (uint32_t)c.rc + (uint32_t)bx), c.wsh) >> c.D;
+		xyout[2 * i + 1] = wrapw((int)((uint32_t)y + (uint32_t)c.rc + (uint32_t)by), c.wsh) >> c.D;
 	}
 }
 
@@ -280,23 +283,25 @@ k_topolar_generic(const int32_t *__restrict__ xyin, int32_t *__restrict__ mag,
 		const int ey = (xyin[2 * i + 1] << c.in_shl) >> c.in_shr;
 		const int xn = ex < 0, yn = ey < 0;
 		int x, y;
-		if (!xn && yn)      { x = ex - ey;  y = ex + ey; }
-		else if (xn && !yn) { x = -ex + ey; y = -ex - ey; }
-		else if (xn && yn)  { x = -ex - ey; y = ex - ey; }
-		else                { x = ex + ey;  y = -ex + ey; }
+		const uint32_t ax = (uint32_t)ex, ay = (uint32_t)ey;
+		if (!xn && yn)      { x = (int)(ax - ay);  y = (int)(ax + ay); }
+		else if (xn && !yn) { x = (int)(ay - ax);  y = (int)(0u - ax - ay); }
+		else if (xn && yn)  { x = (int)(0u - ax - ay); y = (int)(ax - ay); }
+		else                { x = (int)(ax + ay);  y = (int)(ay - ax); }
 		x = wrapw(x, c.wsh); y = wrapw(y, c.wsh);
 		uint32_t ph = c.e_phase[(xn << 1) | yn];
 		for (int k = 0; k < c.neff; k++) {
 			const int sh = (k + 1 > 31) ? 31 : (k + 1);
 			const int sy = y >> sh, sx = x >> sh;
+			const uint32_t ux = (uint32_t)x, uy = (uint32_t)y;
 			if (y < 0) {
-				x = wrapw(x - sy, c.wsh); y = wrapw(y + sx, c.wsh); ph -= c.pa[k];
+				x = wrapw((int)(ux - (uint32_t)sy), c.wsh); y = wrapw((int)(uy + (uint32_t)sx), c.wsh); ph -= c.pa[k];
 			} else {
-				x = wrapw(x + sy, c.wsh); y = wrapw(y - sx, c.wsh); ph += c.pa[k];
+				x = wrapw((int)(ux + (uint32_t)sy), c.wsh); y = wrapw((int)(uy - (uint32_t)sx), c.wsh); ph += c.pa[k];
 			}
 		}
 		const int b = (x >> c.D) & c.do_round;
-		mag[i] = wrapw(x + c.rc + b, c.wsh) >> c.D;
+		mag[i] = wrapw((int)((uint32_t)x + (uint32_t)c.rc + (uint32_t)b), c.wsh) >> c.D;
 		phout[i] = ph >> c.pshift;
 	}
 }

@@ -158,8 +158,11 @@ template <int NS, int SRC, bool RF, int TDM>
 __global__ void __launch_bounds__(1024, 1)
 k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, size_t nblocks,
 		const __grid_constant__ CoreConsts c, const __grid_constant__ SeedConsts s,
-		const uint4 *__restrict__ tables) {
+		const uint4 *__restrict__ tables, const int *__restrict__ gate) {
 	extern __shared__ __align__(128) unsigned char smem[];
+	// Auto-selection: both table flavours are enqueued behind a probe kernel that writes which one suits the
+	// data; the other returns here, before touching shared memory.
+	if (gate != nullptr && *gate != TDM) return;
 	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
 	const uint32_t mbar = sbase + s.total_bytes;		// 8-byte slot after the tables
 
@@ -265,6 +268,24 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 			stg_stream64(dst + (k << 5), make_int2(ox, oy));
 		}
 	}
+}
+
+// ---- probe: are neighbouring samples' phases neighbours? ------------------------------------------------
+// 8 windows of 32 consecutive samples spread over the stream; a pair counts as local when the circular phase
+// difference is at most one LSB (a sweep or a slow NCO: word rows are conflict-free), and the word flavour is
+// chosen when at least 7 pairs in 8 are.  Scattered phases get the byte-packed flavour.
+__global__ void k_seed_probe(const uint32_t *__restrict__ phase, size_t n, int pshift, int *gate) {
+	const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31u;
+	size_t off = ((n / 8) * w) & ~(size_t)31;
+	if (off + 33 > n) off = 0;
+	int local = 0;
+	if (n >= 34) {
+		const uint32_t a = phase[off + l], b = phase[off + l + 1];
+		const int d = (int)((b - a) << pshift) >> pshift;
+		local = (d >= -1 && d <= 1);
+	}
+	const int votes = __syncthreads_count(local);
+	if (threadIdx.x == 0) *gate = (votes * 8 >= (int)blockDim.x * 7) ? TD_TABLE : TD_PACKED;
 }
 
 // ---- host: plan construction and cache -----------------------------------------------------------
@@ -460,53 +481,95 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, bo
 template <int SRC, int NS>
 struct SeedTable {
 	static cudaError_t launch(int ns, int tdm, int grid, size_t smem, cudaStream_t st, const uint32_t *ph, int2 *out, size_t nblocks,
-			const CoreConsts &c, const SeedConsts &s, const uint4 *tables) {
+			const CoreConsts &c, const SeedConsts &s, const uint4 *tables, const int *gate) {
 		if (ns == NS) {
 			// float rounding needs every register value to fit 1.5*2^23 +- 2^22 and a rounding core (D >= 2)
 			const bool rf = c.do_round && c.wsh >= 9;
-			typedef void (*kern_t)(const uint32_t *, int2 *, size_t, const CoreConsts, const SeedConsts, const uint4 *);
+			typedef void (*kern_t)(const uint32_t *, int2 *, size_t, const CoreConsts, const SeedConsts, const uint4 *, const int *);
 			kern_t kern;
 			if (tdm == TD_TABLE) kern = rf ? k_rotate_seeded<NS, SRC, true, TD_TABLE> : k_rotate_seeded<NS, SRC, false, TD_TABLE>;
 			else if (tdm == TD_REGS) kern = rf ? k_rotate_seeded<NS, SRC, true, TD_REGS> : k_rotate_seeded<NS, SRC, false, TD_REGS>;
 			else kern = rf ? k_rotate_seeded<NS, SRC, true, TD_PACKED> : k_rotate_seeded<NS, SRC, false, TD_PACKED>;
 			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (e != cudaSuccess) return e;
-			kern<<<grid, 1024, smem, st>>>(ph, out, nblocks, c, s, tables);
+			kern<<<grid, 1024, smem, st>>>(ph, out, nblocks, c, s, tables, gate);
 			return cudaGetLastError();
 		}
-		return SeedTable<SRC, NS - 1>::launch(ns, tdm, grid, smem, st, ph, out, nblocks, c, s, tables);
+		return SeedTable<SRC, NS - 1>::launch(ns, tdm, grid, smem, st, ph, out, nblocks, c, s, tables, gate);
 	}
 };
 template <int SRC>
 struct SeedTable<SRC, -1> {
 	static cudaError_t launch(int, int, int, size_t, cudaStream_t, const uint32_t *, int2 *, size_t, const CoreConsts &,
-			const SeedConsts &, const uint4 *) { return cudaErrorInvalidValue; }
+			const SeedConsts &, const uint4 *, const int *) { return cudaErrorInvalidValue; }
 };
 
-// Tries the seeded path on the first floor(n/128)*128 samples.  done=0 means "not applicable here".
+// A small ring of device-side gate words per device for the auto-selected launches (stream-ordered use; a slot
+// is reused 1024 seeded calls later).
+static std::mutex g_gate_mu;
+static int *g_gate_ring[64] = {};
+static unsigned g_gate_next[64] = {};
+constexpr unsigned GATE_RING = 1024;
+
+static int gate_slot(int device, int **slot) {
+	std::lock_guard<std::mutex> lk(g_gate_mu);
+	if (!g_gate_ring[device]) {
+		cudaError_t e = cudaMalloc((void **)&g_gate_ring[device], GATE_RING * sizeof(int));
+		if (e != cudaSuccess) return set_error(ZC_ECUDA, "cudaMalloc(gate ring): %s", cudaGetErrorString(e));
+	}
+	*slot = g_gate_ring[device] + (g_gate_next[device]++ % GATE_RING);
+	return ZC_OK;
+}
+
+// Tries the seeded path on the first floor(n/128)*128 samples.  done=0 means "not applicable here"; launches
+// reports how many kernels were enqueued.
 template <int SRC>
 static int seeded_rotate_try(const zc_params *p, const CoreConsts &c, const uint32_t *phase, int32_t *xy_out,
-		size_t n, int device, int sms, cudaStream_t st, uint32_t flags, size_t &done) {
-	done = 0;
+		size_t n, int device, int sms, cudaStream_t st, uint32_t flags, size_t &done, int &launches) {
+	done = 0; launches = 0;
 	const size_t nblocks = n >> 7;
 	if (nblocks == 0) return ZC_OK;
 	if (!(flags & ZC_F_FORCE_SEED) && n < ((size_t)1 << 20)) return ZC_OK;	// not worth the table load
 	if (c.neff < 6 || p->pw < 12) return ZC_OK;
-	// Which flavour: the caller's flag, else -- for the NCO, whose phase pattern the host knows -- packed rows when
-	// neighbouring lanes land more than one table row apart (|step| >= 2 phase LSBs), word rows otherwise.
+	// Which flavour of direction table.  The caller's flag wins.  For the NCO the host knows the pattern: byte rows
+	// when neighbouring lanes land more than one table row apart (|step| >= 2 phase LSBs).  For a phase stream of
+	// 4 Mi samples or more, a probe kernel decides on the device and both flavours are enqueued behind it.
+	const bool forced = (flags & (ZC_F_SEED_REGS | ZC_F_SEED_PACKED | ZC_F_SEED_WORDS)) != 0;
 	int tdm = (flags & ZC_F_SEED_REGS) ? TD_REGS : (flags & ZC_F_SEED_PACKED) ? TD_PACKED : TD_TABLE;
-	if (SRC == SRC_NCO && !(flags & (ZC_F_SEED_REGS | ZC_F_SEED_PACKED | ZC_F_SEED_WORDS))) {
-		const int32_t sstep = (int32_t)c.nco_step;
-		const uint32_t mag = (uint32_t)(sstep < 0 ? -(int64_t)sstep : (int64_t)sstep);
-		if ((mag >> c.pshift) >= 2u) tdm = TD_PACKED;
+	bool probe = false;
+	if (!forced) {
+		if (SRC == SRC_NCO) {
+			const int32_t sstep = (int32_t)c.nco_step;
+			const uint32_t mag = (uint32_t)(sstep < 0 ? -(int64_t)sstep : (int64_t)sstep);
+			if ((mag >> c.pshift) >= 2u) tdm = TD_PACKED;
+		} else if (n >= ((size_t)1 << 22)) {
+			probe = true;
+		}
 	}
-	SeedPlan pl;
+	SeedPlan pl, pl2;
 	int rc = seed_plan_get(p, c, device, tdm == TD_PACKED, st, pl);
 	if (rc != ZC_OK) return rc;
 	if (!pl.usable) return ZC_OK;
-	const size_t smem = pl.s.total_bytes + 16;
-	cudaError_t e = SeedTable<SRC, SEED_MAX_NS>::launch(pl.NS, tdm, sms, smem, st, phase, (int2 *)xy_out, nblocks,
-		c, pl.s, (const uint4 *)pl.dev);
+	int *gate = nullptr;
+	if (probe) {
+		if ((rc = seed_plan_get(p, c, device, true, st, pl2)) != ZC_OK) return rc;
+		if (!pl2.usable) probe = false;
+	}
+	if (probe) {
+		if ((rc = gate_slot(device, &gate)) != ZC_OK) return rc;
+		k_seed_probe<<<1, 256, 0, st>>>(phase, n, c.pshift, gate);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) return set_error(ZC_ECUDA, "launch of k_seed_probe failed: %s", cudaGetErrorString(e));
+		launches++;
+	}
+	cudaError_t e = SeedTable<SRC, SEED_MAX_NS>::launch(pl.NS, tdm, sms, pl.s.total_bytes + 16, st, phase, (int2 *)xy_out,
+		nblocks, c, pl.s, (const uint4 *)pl.dev, gate);
+	if (e == cudaSuccess) launches++;
+	if (e == cudaSuccess && probe) {
+		e = SeedTable<SRC, SEED_MAX_NS>::launch(pl2.NS, TD_PACKED, sms, pl2.s.total_bytes + 16, st, phase, (int2 *)xy_out,
+			nblocks, c, pl2.s, (const uint4 *)pl2.dev, gate);
+		if (e == cudaSuccess) launches++;
+	}
 	if (e != cudaSuccess)
 		return set_error(ZC_ECUDA, "launch of k_rotate_seeded failed: %s", cudaGetErrorString(e));
 	done = nblocks << 7;

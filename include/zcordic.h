@@ -90,10 +90,11 @@ enum {
 	ZC_F_NO_SEED       = 2,	/* rotate_const/nco: run every stage in registers (no table-seeded prefix) */
 	ZC_F_FORCE_SEED    = 4,	/* rotate_const/nco: use the table-seeded prefix even for small n */
 	ZC_F_SEED_PACKED   = 8,	/* seeded kernel: suffix directions as one byte per stage (less shared-memory traffic: the better
-				   choice when neighbouring samples have scattered phases; default for NCO steps >= 2 LSBs) */
+				   choice when neighbouring samples have scattered phases) */
 	ZC_F_SEED_REGS     = 16,	/* seeded kernel: run the suffix phase recursion in registers (no direction table) */
-	ZC_F_SEED_WORDS    = 32	/* seeded kernel: suffix directions as one word per stage (default except for fast NCOs:
-				   fastest for phase sweeps and slow NCOs) */
+	ZC_F_SEED_WORDS    = 32	/* seeded kernel: suffix directions as one word per stage (fastest for phase sweeps, slow NCOs).
+				   With none of the three: NCO picks by step size on the host; phase streams of >= 4 Mi
+				   samples are probed on the device (one extra tiny launch + one skipped launch per call). */
 };
 
 int         zc_version(void);				/* major*1000 + minor */

@@ -80,6 +80,24 @@ def test_rotate_const_other_vectors_and_random_phase(flags):
         assert np.array_equal(got, want), (x0, y0)
 
 
+def test_rotate_const_auto_selected_table_flavour():
+    """Streams of >= 4 Mi phases are probed on the device: a sweep must take the word-table kernel, scattered
+    phases the byte-table kernel; either way the result is the oracle's, and three launches are enqueued
+    (probe + the chosen kernel + the one that returns at its gate)."""
+    core, op = both_p2r(**P2R_CONFIGS["cfg1"])
+    rng = np.random.default_rng(SEED + 31)
+    n = (1 << 22) + 5
+    for phase in (np.arange(n, dtype=np.uint32) & 0xFFFFFF,
+                  rng.integers(0, 1 << 24, size=n, dtype=np.uint64).astype(np.uint32),
+                  ((np.arange(n, dtype=np.uint64) * 3) & 0xFFFFFF).astype(np.uint32)):
+        before = zc.launch_count()
+        got = host(core.rotate_const(131071, 0, dev(phase)))
+        # probe + 2 seeded launches (one returns at its gate) + the 5-sample rest: one group of 4 on the plain
+        # fast kernel and one sample on the generic kernel
+        assert zc.launch_count() - before == 5
+        assert np.array_equal(got, zo.rotate_const(op, 131071, 0, phase))
+
+
 @pytest.mark.parametrize("name", sorted(P2R_CONFIGS))
 @pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_FORCE_GENERIC])
 def test_rotate_per_sample_inputs(name, flags):
@@ -113,6 +131,31 @@ def test_rotate_extreme_inputs_every_octant_boundary():
     phase = np.array(ph * len(corners), dtype=np.uint32)
     got = host(core.rotate(dev(xy), dev(phase)))
     assert np.array_equal(got, zo.rotate(op, xy, phase))
+
+
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_FORCE_GENERIC])
+def test_wide_cores(flags):
+    """The widest cores the 32-bit lanes hold: p2r 24/24 (WW27 PW31 N27), r2p 20/20 (WW28 PW28 N25), r2p 24/24
+    (WW32 PW32 N29: the working registers fill the whole lane, wrap = native overflow) and r2p 22/24 (WW30 PW31)."""
+    rng = np.random.default_rng(SEED + 21)
+    n = (1 << 20) + 3
+    core, op = both_p2r(iw=24, ow=24, xtra=2)
+    assert (core.WW, core.PW, core.NSTAGES) == (27, 31, 27)
+    xy = rng.integers(-(1 << 23), 1 << 23, size=(n, 2), dtype=np.int64).astype(np.int32)
+    xy[:4] = [(-(1 << 23), -(1 << 23)), ((1 << 23) - 1, (1 << 23) - 1), ((1 << 23) - 1, -(1 << 23)), (0, 0)]
+    phase = rng.integers(0, 1 << 31, size=n, dtype=np.uint64).astype(np.uint32)
+    assert np.array_equal(host(core.rotate(dev(xy), dev(phase), flags=flags)), zo.rotate(op, xy, phase))
+    assert np.array_equal(host(core.rotate_const((1 << 23) - 1, 0, dev(phase), flags=flags)),
+                          zo.rotate_const(op, (1 << 23) - 1, 0, phase))
+    for kw, lim in ((dict(iw=20, ow=20, xtra=2), 19), (dict(iw=24, ow=24, xtra=2), 23), (dict(iw=22, ow=24, xtra=1), 21)):
+        vcore, vop = both_r2p(**kw)
+        v = rng.integers(-(1 << lim), 1 << lim, size=(n, 2), dtype=np.int64).astype(np.int32)
+        lo, hi = -(1 << lim), (1 << lim) - 1
+        v[:6] = [(lo, lo), (hi, hi), (lo, hi), (hi, lo), (0, 0), (hi, 0)]
+        mag, ph = vcore.topolar(dev(v), flags=flags)
+        wm, wp = zo.topolar(vop, v)
+        assert np.array_equal(host(mag), wm), kw
+        assert np.array_equal(host(ph).view(np.uint32), wp), kw
 
 
 def test_rotate_narrow_core_wraps_like_the_rtl():

@@ -201,6 +201,7 @@ def main():
     ap.add_argument("--nco-step", type=lambda v: int(v, 0), default=NCO_STEP)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-exchange", action="store_true", help="skip the NCCL scatter/gather-inclusive figure (N>1)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -352,6 +353,50 @@ def main():
                "api": "zc_%s_host (pinned host buffers, chunked H2D->kernel->D2H pipeline)" % kind}
         hin.free(); hout.free()
 
+    # ---- N>1: the same stream held by rank 0, scattered and gathered over NCCL/NVLink each step --------------
+    # north_star: "NCCL over NVLink only as a trivial scatter/gather of independent chunks".  Reported next to the
+    # shard-resident figure above; rank 0's NVLink port (8 B/sample coming back) bounds it, not the kernels.
+    exchange = None
+    if world > 1 and kind == "rotate_const" and not args.no_exchange:
+        try:
+            nx = min(nper, 1 << 27)
+            chunk_in = torch.empty(nx, dtype=torch.int32, device=devname)
+            chunk_out = torch.empty((nx, 2), dtype=torch.int32, device=devname)
+            if rank == 0:
+                all_in = (torch.arange(world * nx, dtype=torch.int64, device=devname)).bitwise_and_(0xFFFFFF).to(torch.int32)
+                all_out = torch.empty((world * nx, 2), dtype=torch.int32, device=devname)
+                ins = list(all_in.split(nx)); outs = list(all_out.split(nx))
+            else:
+                ins = outs = None
+
+            def xstep():
+                dist.scatter(chunk_in, ins, src=0)
+                core.rotate_const(X0, Y0, chunk_in, out=chunk_out, flags=flags)
+                dist.gather(chunk_out, outs, dst=0)
+            xstep()
+            barrier()
+            x0e, x1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            xsteps = 5
+            x0e.record(stream)
+            for _ in range(xsteps):
+                xstep()
+            x1e.record(stream)
+            barrier()
+            tx = torch.tensor([x0e.elapsed_time(x1e)], dtype=torch.float64, device=devname)
+            dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+            xok = None
+            if rank == 0:
+                xok = all_out[:1 << 24].sum(dim=0, dtype=torch.int64).tolist() == [-39316, -39316] and \
+                    torch.equal(all_out[:nx], all_out[(world - 1) * nx:]) if nx % (1 << 24) == 0 else None
+            exchange = {"value": world * nx * xsteps / (float(tx.item()) * 1e-3) / 1e9, "unit": UNIT,
+                        "samples_per_gpu_per_step": nx, "steps": xsteps, "parity": xok,
+                        "what": "rank 0 owns the whole phase stream: dist.scatter -> kernel -> dist.gather (NCCL) inside the timed region"}
+            del chunk_in, chunk_out
+            if rank == 0:
+                del all_in, all_out, ins, outs
+        except Exception as e:                                   # never lose the main line over the extra figure
+            exchange = {"error": repr(e)[:200]}
+
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) --------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -371,8 +416,10 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        per_launch_s = ms * 1e-3 / max(launches, 1)          # rank-0 stream; one kernel launch per step
-        achieved = bytes_per * nper * args.steps / max(launches, 1) / per_launch_s / 1e9
+        # one dominant kernel launch per step (the seeded path adds a ~2 us probe and a launch that returns at its
+        # gate); its duration is the CUDA-event time of the timed region / steps
+        per_step_s = ms * 1e-3 / args.steps
+        achieved = bytes_per * nper / per_step_s / 1e9
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
@@ -387,8 +434,9 @@ def main():
                        "l2": "inputs+outputs per step are %.1f GiB per GPU, far larger than the 126 MB L2" % (bytes_per * nper / 2**30)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_sample": bytes_per, "kernel_ms": 1e3 * per_launch_s},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                         "algorithmic_bytes_per_sample": bytes_per, "kernel_ms": 1e3 * per_step_s,
+                         "launches_per_step": launches / args.steps},
+            "cpu_baseline": cpu, "e2e": e2e, "scatter_gather": exchange, "gpu_launches": int(launches), "clocks": clocks,
             "parity_spot_check": ok,
         }
         print(json.dumps(line), flush=True)

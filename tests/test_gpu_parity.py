@@ -158,6 +158,30 @@ def test_wide_cores(flags):
         assert np.array_equal(host(ph).view(np.uint32), wp), kw
 
 
+def test_fast_path_exactness_proof_exhaustively_on_a_small_core():
+    """The host only takes the non-wrapping fast kernels after bounding the register growth
+    (zc_api.cu: fast_path_is_exact).  For a 6-bit core (WW=9, PW=10, 30 nominal stages) that bound holds with
+    little margin, and every one of the 64*64*1024 (x, y, phase) inputs can be checked against the oracle,
+    which models the WW-bit wrap."""
+    core, op = both_p2r(iw=6, ow=6, xtra=2, pw=10, n=30)
+    assert core.WW == 9
+    v = np.arange(-32, 32, dtype=np.int32)
+    ph = np.arange(1 << 10, dtype=np.uint32)
+    X, Y, P = np.meshgrid(v, v, ph, indexing="ij")
+    xy = np.stack([X.ravel(), Y.ravel()], axis=1).astype(np.int32)
+    phase = P.ravel().astype(np.uint32)
+    want = zo.rotate(op, xy, phase)
+    assert np.array_equal(host(core.rotate(dev(xy), dev(phase))), want)                       # fast path
+    assert np.array_equal(host(core.rotate(dev(xy), dev(phase), flags=zc.F_FORCE_GENERIC)), want)
+    vcore, vop = both_r2p(iw=8, ow=8, xtra=0)                                                  # WW=12
+    v8 = np.arange(-128, 128, dtype=np.int32)
+    xy8 = np.stack(np.meshgrid(v8, v8, indexing="ij"), axis=-1).reshape(-1, 2)
+    wm, wp = zo.topolar(vop, xy8)
+    for fl in (zc.F_DEFAULT, zc.F_FORCE_GENERIC):
+        mag, ph8 = vcore.topolar(dev(xy8), flags=fl)
+        assert np.array_equal(host(mag), wm) and np.array_equal(host(ph8).view(np.uint32), wp)
+
+
 def test_rotate_narrow_core_wraps_like_the_rtl():
     """WW=5 is too narrow for the CORDIC gain: the RTL registers wrap.  The engine must detect
     that its non-wrapping fast path is not provably exact and reproduce the wrap."""

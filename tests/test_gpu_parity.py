@@ -182,6 +182,60 @@ def test_fast_path_exactness_proof_exhaustively_on_a_small_core():
         assert np.array_equal(host(mag), wm) and np.array_equal(host(ph8).view(np.uint32), wp)
 
 
+def test_random_configurations_differential():
+    """Property test over the generator's parameter surface: random (iw, ow, xtra, pw, nstages), random inputs,
+    every kernel-selection flag (fast / seeded word / seeded byte / seeded registers / generic) against the
+    oracle.  Exercises the seed-plan geometry (bucket width, prefix depth, residual range) far from cfg1."""
+    rng = np.random.default_rng(SEED + 41)
+    n = (1 << 16) + 3
+    tried = seeded_ok = 0
+    while tried < 48:
+        iw, ow = int(rng.integers(4, 25)), int(rng.integers(4, 25))
+        xtra = int(rng.integers(-1, 5))
+        pw = int(rng.choice([0, 0, int(rng.integers(8, 31))]))
+        ns = int(rng.choice([0, 0, int(rng.integers(3, 33))]))
+        rc, op = zo.derive_p2r(iw, ow, xtra, pw, ns)
+        if rc != 0:
+            continue
+        try:
+            core = zc.Cordic(iw, ow, xtra, pw, ns)
+        except zc.ZcError:
+            continue
+        tried += 1
+        phase = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+        lo, hi = -(1 << (iw - 1)), (1 << (iw - 1)) - 1
+        x0, y0 = int(rng.integers(lo, hi + 1)), int(rng.integers(lo, hi + 1))
+        want = zo.rotate_const(op, x0, y0, phase)
+        for fl in (zc.F_DEFAULT, zc.F_FORCE_SEED | zc.F_SEED_WORDS, zc.F_FORCE_SEED | zc.F_SEED_PACKED,
+                   zc.F_FORCE_SEED | zc.F_SEED_REGS, zc.F_FORCE_GENERIC):
+            got = host(core.rotate_const(x0, y0, dev(phase), flags=fl))
+            assert np.array_equal(got, want), (iw, ow, xtra, pw, ns, fl)
+        xy = rng.integers(lo, hi + 1, size=(n, 2), dtype=np.int64).astype(np.int32)
+        assert np.array_equal(host(core.rotate(dev(xy), dev(phase))), zo.rotate(op, xy, phase)), (iw, ow, xtra, pw, ns)
+        got = host(core.nco(x0, y0, 12345, 0x9E3779B1, n, n0=7, flags=zc.F_FORCE_SEED))
+        assert np.array_equal(got, zo.nco(op, x0, y0, 12345, 0x9E3779B1, n, n0=7)), (iw, ow, xtra, pw, ns)
+    tried = 0
+    while tried < 24:
+        iw, ow = int(rng.integers(4, 23)), int(rng.integers(4, 23))
+        xtra = int(rng.integers(-2, 4))
+        pw = int(rng.choice([0, 0, int(rng.integers(8, 31))]))
+        ns = int(rng.choice([0, 0, int(rng.integers(3, 33))]))
+        rc, op = zo.derive_r2p(iw, ow, xtra, pw, ns)
+        if rc != 0:
+            continue
+        try:
+            vcore = zc.Topolar(iw, ow, xtra, pw, ns)
+        except zc.ZcError:
+            continue
+        tried += 1
+        lo, hi = -(1 << (iw - 1)), (1 << (iw - 1)) - 1
+        xy = rng.integers(lo, hi + 1, size=(n, 2), dtype=np.int64).astype(np.int32)
+        wm, wp = zo.topolar(op, xy)
+        for fl in (zc.F_DEFAULT, zc.F_FORCE_GENERIC):
+            mag, ph = vcore.topolar(dev(xy), flags=fl)
+            assert np.array_equal(host(mag), wm) and np.array_equal(host(ph).view(np.uint32), wp), (iw, ow, xtra, pw, ns, fl)
+
+
 def test_rotate_narrow_core_wraps_like_the_rtl():
     """WW=5 is too narrow for the CORDIC gain: the RTL registers wrap.  The engine must detect
     that its non-wrapping fast path is not provably exact and reproduce the wrap."""

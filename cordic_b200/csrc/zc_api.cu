@@ -222,6 +222,12 @@ static int launch_rotate(const zc_params *p, CoreConsts &c, const uint32_t *phas
 		c.neff >= 1 && c.neff <= 32;
 	size_t done = 0;
 	if (fast) {
+		if constexpr (SRC == SRC_XY || SRC == SRC_MIX) if (!(flags & ZC_F_NO_SEED)) {
+			int launched = 0;
+			rc = dirs_rotate_try<SRC>(p, c, phase, xy_in, xy_out, n, device, di.sms, st, flags, done, launched);
+			if (rc != ZC_OK) return rc;
+			g_launches.fetch_add((uint64_t)launched, std::memory_order_relaxed);
+		}
 		if constexpr (SRC == SRC_CONST || SRC == SRC_NCO) if (!(flags & ZC_F_NO_SEED)) {
 			// 4-byte phase words and 8-byte (x,y) pairs: natural alignment is all this path needs
 			int launched = 0;

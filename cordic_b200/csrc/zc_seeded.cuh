@@ -121,6 +121,9 @@ struct Suffix<NS, NS> {
 };
 
 enum { TD_TABLE = 0, TD_REGS = 1, TD_PACKED = 2 };
+// plan flavours: word TD + x/y table, byte TD + x/y table, byte TD + per-interval prefix directions (no x/y table)
+enum { FL_WORDS = 0, FL_PACKED = 1, FL_DIRS = 2 };
+constexpr int DIRS_M = 12;	// prefix depth of the FL_DIRS flavour (its kernel unrolls the byte indices)
 
 // Sign-extends byte `b` of w with one PRMT (selector nibble 8|b replicates that byte's sign bit;
 // __byte_perm() masks the replicate bit off, hence the PTX).
@@ -294,35 +297,36 @@ struct SeedPlan {
 	int32_t x0c[4], y0c[4];		// the pre-rotated constant vector (identifies x0,y0 modulo IW)
 	int device = -1;
 	int NS = 0;
-	bool packed = false;
+	int flavour = FL_WORDS;
 	SeedConsts s;
 	void *dev = nullptr;		// tables, laid out as in shared memory
 	bool usable = false;		// false: geometry does not fit; cached so we do not retry
 	uint64_t stamp = 0;
 };
 
-struct Interval { int64_t lo, hi, S; };
+struct Interval { int64_t lo, hi, S; uint32_t neg; };	// neg: bit k set when stage k rotates clockwise (d_k = -1)
 
 // Enumerates the intervals of constant (d_0..d_{M-1}) over the reduced phase range
 // [-2^(PW-3), 2^(PW-3)), in ascending order.  Phase arithmetic only (rtl/cordic.v:265-279).
 static void seed_intervals(const zc_params *p, int M, std::vector<Interval> &iv) {
 	const int64_t half = (int64_t)1 << (p->pw - 3);
-	iv.assign(1, Interval{-half, half, 0});
+	iv.assign(1, Interval{-half, half, 0, 0u});
 	std::vector<Interval> next;
 	for (int k = 0; k < M; k++) {
 		next.clear();
 		const int64_t a = p->angle[k];
 		for (const Interval &it : iv) {
 			// residual = phase - S ; negative residual -> rotate clockwise, S' = S - angle
-			if (it.lo < it.S) next.push_back(Interval{it.lo, it.hi < it.S ? it.hi : it.S, it.S - a});
-			if (it.hi > it.S) next.push_back(Interval{it.lo > it.S ? it.lo : it.S, it.hi, it.S + a});
+			if (it.lo < it.S) next.push_back(Interval{it.lo, it.hi < it.S ? it.hi : it.S, it.S - a, it.neg | (1u << k)});
+			if (it.hi > it.S) next.push_back(Interval{it.lo > it.S ? it.lo : it.S, it.hi, it.S + a, it.neg});
 		}
 		iv.swap(next);
 	}
 }
 
-static bool seed_geometry(const zc_params *p, int neff, int M, bool packed, std::vector<Interval> &iv, SeedConsts &s,
+static bool seed_geometry(const zc_params *p, int neff, int M, int flavour, std::vector<Interval> &iv, SeedConsts &s,
 		int &NS, int64_t &rmin, int64_t &rmax) {
+	const bool packed = (flavour != FL_WORDS);
 	NS = neff - M;
 	if (NS < 0 || NS > SEED_MAX_NS) return false;
 	seed_intervals(p, M, iv);
@@ -344,7 +348,7 @@ static bool seed_geometry(const zc_params *p, int neff, int M, bool packed, std:
 	const size_t nres = (size_t)(rmax - rmin + 1);
 	// bytes per TD row slot: 16 (one int4 plane entry) or, packed, one signed byte per stage
 	const int lgrow = (packed && NS <= 8) ? 3 : 4;
-	const size_t b_t1 = (size_t)4 << LB, b_ts = (R * 4 + 15) & ~(size_t)15, b_t2 = R * 32,
+	const size_t b_t1 = (size_t)4 << LB, b_ts = (R * 4 + 15) & ~(size_t)15, b_t2 = R * (flavour == FL_DIRS ? 16 : 32),
 		     b_td = packed ? ((nres << lgrow) + 15) & ~(size_t)15 : nres * (size_t)nsp * 4;
 	const size_t total = b_t1 + b_ts + b_t2 + b_td;
 	if (total + 16 > SEED_SMEM_LIMIT) return false;
@@ -391,11 +395,12 @@ static void seed_release(SeedPlan &pl) {
 }
 
 // Builds (or finds) the plan for (p, constant vector, device).  Called with the device current.
-static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, bool packed, cudaStream_t st,
+static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, int flavour, cudaStream_t st,
 		SeedPlan &out) {
+	const bool packed = (flavour != FL_WORDS);
 	std::lock_guard<std::mutex> lk(g_seed_mu);
 	for (SeedPlan &pl : g_seed_cache) {
-		if (pl.device == device && pl.packed == packed && std::memcmp(&pl.p, p, sizeof(*p)) == 0 &&
+		if (pl.device == device && pl.flavour == flavour && std::memcmp(&pl.p, p, sizeof(*p)) == 0 &&
 		    std::memcmp(pl.x0c, c.cx, sizeof(pl.x0c)) == 0 && std::memcmp(pl.y0c, c.cy, sizeof(pl.y0c)) == 0) {
 			pl.stamp = ++g_seed_clock;
 			out = pl;
@@ -403,15 +408,19 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, bo
 		}
 	}
 	SeedPlan pl;
-	pl.p = *p; pl.device = device; pl.packed = packed; pl.stamp = ++g_seed_clock;
+	pl.p = *p; pl.device = device; pl.flavour = flavour; pl.stamp = ++g_seed_clock;
 	std::memcpy(pl.x0c, c.cx, sizeof(pl.x0c));
 	std::memcpy(pl.y0c, c.cy, sizeof(pl.y0c));
 	std::vector<Interval> iv;
 	int64_t rmin = 0, rmax = 0;
 	bool ok = false;
 	const int neff = c.neff;
-	for (int M = (neff < 13 ? neff : 13); M >= 6 && !ok; M--)
-		ok = seed_geometry(p, neff, M, packed, iv, pl.s, pl.NS, rmin, rmax);
+	if (flavour == FL_DIRS) {
+		if (neff >= DIRS_M) ok = seed_geometry(p, neff, DIRS_M, flavour, iv, pl.s, pl.NS, rmin, rmax);
+	} else {
+		for (int M = (neff < 13 ? neff : 13); M >= 6 && !ok; M--)
+			ok = seed_geometry(p, neff, M, flavour, iv, pl.s, pl.NS, rmin, rmax);
+	}
 	if (ok) {
 		const SeedConsts &s = pl.s;
 		const int pshift = c.pshift;
@@ -432,6 +441,12 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, bo
 			}
 			t1[b] = (uint32_t)(((uint64_t)r << s.lgw) + (uint64_t)(W - off) - ((uint64_t)b << s.lgw)) << s.lgrow;
 		}
+		if (flavour == FL_DIRS) {		// per-interval prefix directions, one signed byte per stage, 16-byte rows
+			unsigned char *tp = reinterpret_cast<unsigned char *>(host.data()) + s.off_t2;
+			for (size_t k = 0; k < R; k++)
+				for (int j = 0; j < DIRS_M; j++)
+					tp[k * 16 + j] = (unsigned char)(((iv[k].neg >> j) & 1u) ? 0xff : 0x01);
+		}
 		for (size_t k = 0; k < R && ok; k++) {
 			ts[k] = (uint32_t)(int32_t)((iv[k].S + half + rmin) * ((int64_t)1 << s.lgrow));
 			rep[k] = (uint32_t)((uint64_t)iv[k].lo << pshift);
@@ -451,7 +466,7 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, bo
 		if (ok) {
 			cudaError_t e = cudaMalloc(&pl.dev, host.size() * 4);
 			if (e == cudaSuccess) e = cudaMemcpyAsync(pl.dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st);
-			if (e == cudaSuccess) {
+			if (e == cudaSuccess && flavour != FL_DIRS) {
 				const uint32_t nthreads = 4u * (uint32_t)R;
 				k_seed_fill_xy<<<(nthreads + 255) / 256, 256, 0, st>>>(
 					reinterpret_cast<const uint32_t *>(pl.dev) + s.total_bytes / 4,
@@ -504,6 +519,157 @@ struct SeedTable<SRC, -1> {
 			const SeedConsts &, const uint4 *, const int *) { return cudaErrorInvalidValue; }
 };
 
+// ---- per-sample input vectors: every stage in registers, every direction from a table ----------------------
+// With (x, y) varying per sample the x/y table is gone, but the directions still depend on the phase alone: the
+// DIRS_M prefix directions come from the sample's interval (16-byte row of signed bytes), the rest from the
+// residual row as in the byte flavour above.  A stage is then PRMT + IMAD.MOV + 2 SHF + 2 IMAD (6 issue slots
+// instead of 8), and the phase recursion is gone altogether.
+template <int NS, int J = 0>
+struct DirStages {
+	static __device__ __forceinline__ void run(int &x, int &y, const uint32_t (&tp)[4], const uint32_t (&td)[4]) {
+		constexpr int S = (J + 1 > 31) ? 31 : (J + 1);
+		const int d = (J < DIRS_M) ? sext_byte(tp[J >> 2], J & 3) : sext_byte(td[(J - DIRS_M) >> 2], (J - DIRS_M) & 3);
+		const int nd = ineg(d);
+		const int sy = y >> S, sx = x >> S;
+		const int x1 = imad(sy, nd, x);
+		const int y1 = imad(sx, d, y);
+		x = x1; y = y1;
+		DirStages<NS, J + 1>::run(x, y, tp, td);
+	}
+};
+template <int NS>
+struct DirStages<NS, DIRS_M + NS> {
+	static __device__ __forceinline__ void run(int &, int &, const uint32_t (&)[4], const uint32_t (&)[4]) {}
+};
+
+__device__ __forceinline__ int2 ldg_stream64(const int2 *p) {
+	int2 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+	return r;
+}
+
+template <int NS, int SRC, bool RF>
+__global__ void __launch_bounds__(1024, 1)
+k_rotate_dirs(const uint32_t *__restrict__ phase, const int2 *__restrict__ xyin, int2 *__restrict__ xyout,
+		size_t nblocks, const __grid_constant__ CoreConsts c, const __grid_constant__ SeedConsts s,
+		const uint4 *__restrict__ tables) {
+	extern __shared__ __align__(128) unsigned char smem[];
+	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+	const uint32_t mbar = sbase + s.total_bytes;
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(s.total_bytes) : "memory");
+		const char *src = reinterpret_cast<const char *>(tables);
+		for (uint32_t off = 0; off < s.total_bytes; off += 32768u) {
+			const uint32_t len = (s.total_bytes - off < 32768u) ? (s.total_bytes - off) : 32768u;
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				:: "r"(sbase + off), "l"(src + off), "r"(len), "r"(mbar) : "memory");
+		}
+	}
+	__syncthreads();
+	{
+		uint32_t done = 0;
+		while (!done) {
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+				"selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar) : "memory");
+		}
+	}
+	const uint32_t *const T1 = reinterpret_cast<const uint32_t *>(smem);
+	const int32_t *const TS = reinterpret_cast<const int32_t *>(smem + s.off_ts);
+	const uint4 *const TP = reinterpret_cast<const uint4 *>(smem + s.off_t2);
+	const unsigned char *const TD = smem + s.off_td;
+	const uint32_t lane = threadIdx.x & 31u;
+	const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+	for (size_t blk = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < nblocks; blk += nwarps) {
+		const size_t base = (blk << 7) + lane;
+		uint32_t ph[4];
+		int2 v[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) v[k] = ldg_stream64(xyin + base + (k << 5));
+		if (SRC == SRC_MIX) {
+			const uint32_t p0 = c.nco_phase0 + (c.nco_n0 + (uint32_t)base) * c.nco_step;
+#pragma unroll
+			for (int k = 0; k < 4; k++) ph[k] = (p0 + (uint32_t)(k << 5) * c.nco_step) >> c.pshift;
+		} else {
+#pragma unroll
+			for (int k = 0; k < 4; k++) ph[k] = ldg_stream32(phase + base + (k << 5));
+		}
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const uint32_t tq = (uint32_t)imad((int)ph[k], (int)s.mul_q, 0x20000000);
+			const uint32_t tu = (uint32_t)imad((int)ph[k], (int)s.mul_u, (int)0x80000000u);
+			const uint32_t ur = tu >> s.ush;
+			const uint32_t rank = (T1[tu >> s.bsh] + ur) >> s.rsh;
+			const uint4 tpv = TP[rank];
+			const unsigned char *row = TD + (int)(ur - (uint32_t)TS[rank]);
+			const uint32_t tp[4] = {tpv.x, tpv.y, tpv.z, tpv.w};
+			uint32_t td[4] = {0, 0, 0, 0};
+			if (NS > 0 && NS <= 8) {
+				const int2 w = *reinterpret_cast<const int2 *>(row);
+				td[0] = (uint32_t)w.x; td[1] = (uint32_t)w.y;
+			} else if (NS > 8) {
+				const int4 w = *reinterpret_cast<const int4 *>(row);
+				td[0] = (uint32_t)w.x; td[1] = (uint32_t)w.y; td[2] = (uint32_t)w.z; td[3] = (uint32_t)w.w;
+			}
+			// rtl/cordic.v:85-86 (extend) and :131-188 (quarter turn selected by the octant)
+			const int ex = (v[k].x << c.in_shl) >> c.in_shr, ey = (v[k].y << c.in_shl) >> c.in_shr;
+			int x, y;
+			quarter_turn((int)(tq >> 30), ex, ey, x, y);
+			DirStages<NS>::run(x, y, tp, td);
+			const int ox = RF ? round_out_fma(x, s) : round_out(x, c);
+			const int oy = RF ? round_out_fma(y, s) : round_out(y, c);
+			stg_stream64(xyout + base + (k << 5), make_int2(ox, oy));
+		}
+	}
+}
+
+template <int SRC, int NS>
+struct DirsTable {
+	static cudaError_t launch(int ns, int grid, size_t smem, cudaStream_t st, const uint32_t *ph, const int2 *xin, int2 *out,
+			size_t nblocks, const CoreConsts &c, const SeedConsts &s, const uint4 *tables) {
+		if (ns == NS) {
+			const bool rf = c.do_round && c.wsh >= 9;
+			typedef void (*kern_t)(const uint32_t *, const int2 *, int2 *, size_t, const CoreConsts, const SeedConsts, const uint4 *);
+			kern_t kern = rf ? (kern_t)k_rotate_dirs<NS, SRC, true> : (kern_t)k_rotate_dirs<NS, SRC, false>;
+			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (e != cudaSuccess) return e;
+			kern<<<grid, 1024, smem, st>>>(ph, xin, out, nblocks, c, s, tables);
+			return cudaGetLastError();
+		}
+		return DirsTable<SRC, NS - 1>::launch(ns, grid, smem, st, ph, xin, out, nblocks, c, s, tables);
+	}
+};
+template <int SRC>
+struct DirsTable<SRC, -1> {
+	static cudaError_t launch(int, int, size_t, cudaStream_t, const uint32_t *, const int2 *, int2 *, size_t, const CoreConsts &,
+			const SeedConsts &, const uint4 *) { return cudaErrorInvalidValue; }
+};
+
+// Per-sample (x,y): tries the table-directed kernel on the first floor(n/128)*128 samples.
+template <int SRC>
+static int dirs_rotate_try(const zc_params *p, const CoreConsts &c, const uint32_t *phase, const int32_t *xy_in,
+		int32_t *xy_out, size_t n, int device, int sms, cudaStream_t st, uint32_t flags, size_t &done, int &launches) {
+	done = 0; launches = 0;
+	const size_t nblocks = n >> 7;
+	if (nblocks == 0) return ZC_OK;
+	if (!(flags & ZC_F_FORCE_SEED) && n < ((size_t)1 << 20)) return ZC_OK;
+	if (c.neff < DIRS_M || p->pw < 12) return ZC_OK;
+	CoreConsts key = c;		// the plan does not depend on the input vector
+	for (int q = 0; q < 4; q++) key.cx[q] = key.cy[q] = 0;
+	SeedPlan pl;
+	int rc = seed_plan_get(p, key, device, FL_DIRS, st, pl);
+	if (rc != ZC_OK) return rc;
+	if (!pl.usable) return ZC_OK;
+	cudaError_t e = DirsTable<SRC, SEED_MAX_NS>::launch(pl.NS, sms, pl.s.total_bytes + 16, st, phase, (const int2 *)xy_in,
+		(int2 *)xy_out, nblocks, c, pl.s, (const uint4 *)pl.dev);
+	if (e != cudaSuccess)
+		return set_error(ZC_ECUDA, "launch of k_rotate_dirs failed: %s", cudaGetErrorString(e));
+	launches = 1;
+	done = nblocks << 7;
+	return ZC_OK;
+}
+
 // A small ring of device-side gate words per device for the auto-selected launches (stream-ordered use; a slot
 // is reused 1024 seeded calls later).
 static std::mutex g_gate_mu;
@@ -547,12 +713,12 @@ static int seeded_rotate_try(const zc_params *p, const CoreConsts &c, const uint
 		}
 	}
 	SeedPlan pl, pl2;
-	int rc = seed_plan_get(p, c, device, tdm == TD_PACKED, st, pl);
+	int rc = seed_plan_get(p, c, device, tdm == TD_PACKED ? FL_PACKED : FL_WORDS, st, pl);
 	if (rc != ZC_OK) return rc;
 	if (!pl.usable) return ZC_OK;
 	int *gate = nullptr;
 	if (probe) {
-		if ((rc = seed_plan_get(p, c, device, true, st, pl2)) != ZC_OK) return rc;
+		if ((rc = seed_plan_get(p, c, device, FL_PACKED, st, pl2)) != ZC_OK) return rc;
 		if (!pl2.usable) probe = false;
 	}
 	if (probe) {

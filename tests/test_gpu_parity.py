@@ -99,7 +99,7 @@ def test_rotate_const_auto_selected_table_flavour():
 
 
 @pytest.mark.parametrize("name", sorted(P2R_CONFIGS))
-@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_FORCE_GENERIC])
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED, zc.F_NO_SEED])
 def test_rotate_per_sample_inputs(name, flags):
     core, op = both_p2r(**P2R_CONFIGS[name])
     rng = np.random.default_rng(SEED + 1)
@@ -145,6 +145,7 @@ def test_wide_cores(flags):
     xy[:4] = [(-(1 << 23), -(1 << 23)), ((1 << 23) - 1, (1 << 23) - 1), ((1 << 23) - 1, -(1 << 23)), (0, 0)]
     phase = rng.integers(0, 1 << 31, size=n, dtype=np.uint64).astype(np.uint32)
     assert np.array_equal(host(core.rotate(dev(xy), dev(phase), flags=flags)), zo.rotate(op, xy, phase))
+    assert np.array_equal(host(core.rotate(dev(xy), dev(phase), flags=flags | zc.F_FORCE_SEED)), zo.rotate(op, xy, phase))
     assert np.array_equal(host(core.rotate_const((1 << 23) - 1, 0, dev(phase), flags=flags)),
                           zo.rotate_const(op, (1 << 23) - 1, 0, phase))
     for kw, lim in ((dict(iw=20, ow=20, xtra=2), 19), (dict(iw=24, ow=24, xtra=2), 23), (dict(iw=22, ow=24, xtra=1), 21)):
@@ -211,7 +212,9 @@ def test_random_configurations_differential():
             got = host(core.rotate_const(x0, y0, dev(phase), flags=fl))
             assert np.array_equal(got, want), (iw, ow, xtra, pw, ns, fl)
         xy = rng.integers(lo, hi + 1, size=(n, 2), dtype=np.int64).astype(np.int32)
-        assert np.array_equal(host(core.rotate(dev(xy), dev(phase))), zo.rotate(op, xy, phase)), (iw, ow, xtra, pw, ns)
+        wxy = zo.rotate(op, xy, phase)
+        for fl in (zc.F_DEFAULT, zc.F_FORCE_SEED):        # plain fast kernel / table-directed kernel
+            assert np.array_equal(host(core.rotate(dev(xy), dev(phase), flags=fl)), wxy), (iw, ow, xtra, pw, ns, fl)
         got = host(core.nco(x0, y0, 12345, 0x9E3779B1, n, n0=7, flags=zc.F_FORCE_SEED))
         assert np.array_equal(got, zo.nco(op, x0, y0, 12345, 0x9E3779B1, n, n0=7)), (iw, ow, xtra, pw, ns)
     tried = 0

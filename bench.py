@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -82,10 +82,11 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, power = [], None, set(), []
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
+                power.append(float(r[2]))
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -93,6 +94,7 @@ class ClockSampler:
                     reasons.add(name)
         busy = [v for v in sm if mx and v > 0.5 * mx] or sm
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx,
+                "sm_mhz_min_under_load": min(busy) if busy else None, "power_w_max": max(power) if power else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
@@ -191,7 +193,7 @@ def run_reference(args, kind, nper):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="rotate_cfg1", choices=sorted(WORKLOADS))

@@ -161,6 +161,7 @@ static void fill_const_xy(const zc_params *p, int32_t x0, int32_t y0, CoreConsts
 }
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
 static int grid_for(size_t work, const DeviceInfo &di, int per_sm) {
 	size_t blocks = (work + 255) / 256;
@@ -217,24 +218,22 @@ static int launch_rotate(const zc_params *p, CoreConsts &c, const uint32_t *phas
 	cudaStream_t st = (cudaStream_t)stream;
 
 	constexpr bool has_phase = (SRC == SRC_CONST || SRC == SRC_XY), has_xy = (SRC == SRC_XY || SRC == SRC_MIX);
+	// non-wrapping arithmetic must be provably exact for this configuration, else the generic kernel does it all
+	const bool math_ok = !(flags & ZC_F_FORCE_GENERIC) && fast_path_is_exact(p) && c.neff >= 1 && c.neff <= 32;
+	// the table kernels move 4-byte phases and 8-byte (x,y) pairs; the plain fast kernel moves 16-byte vectors
+	const bool pair_ok = aligned8(xy_out) && (!has_xy || aligned8(xy_in));
 	const bool vec_ok = aligned16(xy_out) && (!has_phase || aligned16(phase)) && (!has_xy || aligned16(xy_in));
-	const bool fast = !(flags & ZC_F_FORCE_GENERIC) && fast_path_is_exact(p) && vec_ok &&
-		c.neff >= 1 && c.neff <= 32;
 	size_t done = 0;
-	if (fast) {
-		if constexpr (SRC == SRC_XY || SRC == SRC_MIX) if (!(flags & ZC_F_NO_SEED)) {
-			int launched = 0;
+	if (math_ok && pair_ok && !(flags & ZC_F_NO_SEED)) {
+		int launched = 0;
+		if constexpr (SRC == SRC_XY || SRC == SRC_MIX)
 			rc = dirs_rotate_try<SRC>(p, c, phase, xy_in, xy_out, n, device, di.sms, st, flags, done, launched);
-			if (rc != ZC_OK) return rc;
-			g_launches.fetch_add((uint64_t)launched, std::memory_order_relaxed);
-		}
-		if constexpr (SRC == SRC_CONST || SRC == SRC_NCO) if (!(flags & ZC_F_NO_SEED)) {
-			// 4-byte phase words and 8-byte (x,y) pairs: natural alignment is all this path needs
-			int launched = 0;
+		else
 			rc = seeded_rotate_try<SRC>(p, c, phase, xy_out, n, device, di.sms, st, flags, done, launched);
-			if (rc != ZC_OK) return rc;
-			g_launches.fetch_add((uint64_t)launched, std::memory_order_relaxed);
-		}
+		if (rc != ZC_OK) return rc;
+		g_launches.fetch_add((uint64_t)launched, std::memory_order_relaxed);
+	}
+	if (math_ok && vec_ok) {		// `done` is a multiple of 128 samples: the remainder keeps the base alignment
 		const size_t groups = (n - done) / 4;
 		if (groups) {
 			CoreConsts t = c;

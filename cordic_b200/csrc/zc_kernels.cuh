@@ -57,9 +57,8 @@ __device__ __forceinline__ int ineg(int a) {
 
 // ---- one micro-rotation, rotation mode (rtl/cordic.v:263-279) ---------------------------
 // d = +1 when the residual phase is >= 0, else -1.  x' = x - d*(y>>>k); y' = y + d*(x>>>k);
-// p' = p - d*angle.  Both updates read the OLD x and y.  Written so that the two multiplies
-// by +-1 go to the FMA pipe (IMAD) and the shifts/sign tests to the ALU pipe.
-template <int K, int FORM>
+// p' = p - d*angle.  Both updates read the OLD x and y.
+template <int K>
 __device__ __forceinline__ void rot_step(int &x, int &y, int &p, const int na) {
 	constexpr int S = (K + 1 > 31) ? 31 : (K + 1);
 	// Pipe budget per stage (profiles/ubench_r1.txt): the ALU pipe (shifts, LEA/IADD3) and the heavy FMA pipe
@@ -79,7 +78,7 @@ __device__ __forceinline__ void rot_step(int &x, int &y, int &p, const int na) {
 // ---- one micro-rotation, vectoring mode (rtl/topolar.v:227-243) --------------------------
 // s = -1 when y is below the axis (yv[WW-1]), else +1 (y == 0 counts as above).
 // x' = x + s*(y>>>k); y' = y - s*(x>>>k); ph' = ph + s*angle.
-template <int K, int FORM>
+template <int K>
 __device__ __forceinline__ void vec_step(int &x, int &y, uint32_t &ph, const int pa) {
 	constexpr int S = (K + 1 > 31) ? 31 : (K + 1);
 	const int md = y >> 31;
@@ -96,11 +95,11 @@ __device__ __forceinline__ void vec_step(int &x, int &y, uint32_t &ph, const int
 template <int N, int K = 0>
 struct Unroll {
 	static __device__ __forceinline__ void rot(int &x, int &y, int &p, const CoreConsts &c) {
-		rot_step<K, (K & 1)>(x, y, p, c.na[K]);
+		rot_step<K>(x, y, p, c.na[K]);
 		Unroll<N, K + 1>::rot(x, y, p, c);
 	}
 	static __device__ __forceinline__ void vec(int &x, int &y, uint32_t &ph, const CoreConsts &c) {
-		vec_step<K, (K & 1)>(x, y, ph, (int)c.pa[K]);
+		vec_step<K>(x, y, ph, (int)c.pa[K]);
 		Unroll<N, K + 1>::vec(x, y, ph, c);
 	}
 };

@@ -75,22 +75,6 @@ __global__ void k_seed_fill_xy(const uint32_t *__restrict__ rep_phase /* left-ju
 	t2[i] = make_int2(x, y);
 }
 
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-	uint32_t v;
-	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-	return v;
-}
-__device__ __forceinline__ int2 lds64(uint32_t addr) {
-	int2 v;
-	asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-	return v;
-}
-__device__ __forceinline__ int4 lds128(uint32_t addr) {
-	int4 v;
-	asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-	return v;
-}
-
 template <int NS, int J = 0>
 struct Suffix {
 	// directions from the table: 2 shifts + 2 multiply-adds by +-1 + one negation per stage

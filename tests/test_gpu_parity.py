@@ -417,6 +417,27 @@ def test_ragged_sizes_and_misaligned_buffers(n):
         assert np.array_equal(host(mag), wm) and np.array_equal(host(ph).view(np.uint32), wp)
 
 
+def test_large_buffers_off_the_16_byte_grid():
+    """Big streams whose pointers are only naturally aligned (4-byte phases, 8-byte pairs): the table kernels take
+    them; the ragged rest goes through the generic kernel.  Same words as the oracle."""
+    core, op = both_p2r(**P2R_CONFIGS["cfg1"])
+    rng = np.random.default_rng(SEED + 51)
+    n = (1 << 20) + 131
+    phase = rng.integers(0, 1 << 24, size=n + 1, dtype=np.uint64).astype(np.uint32)
+    xy = rng.integers(-(1 << 17), 1 << 17, size=(n + 1, 2), dtype=np.int64).astype(np.int32)
+    dphase, dxy = dev(phase), dev(xy)
+    out = torch.empty((n + 1, 2), dtype=torch.int32, device="cuda")
+    before = zc.launch_count()
+    core.rotate_const(131071, 0, dphase[1:], out=out[1:])
+    assert zc.launch_count() - before == 2                     # seeded kernel + generic rest
+    assert np.array_equal(host(out[1:]), zo.rotate_const(op, 131071, 0, phase[1:]))
+    core.rotate(dxy[1:], dphase[1:], out=out[1:])
+    assert np.array_equal(host(out[1:]), zo.rotate(op, xy[1:], phase[1:]))
+    core.mix(dxy[1:], 77, 0x01234567, n0=5, out=out[1:])
+    ph = (((77 + (5 + np.arange(n, dtype=np.uint64)) * 0x01234567) & 0xFFFFFFFF).astype(np.uint32)) >> 8
+    assert np.array_equal(host(out[1:]), zo.rotate(op, xy[1:], ph))
+
+
 @pytest.mark.parametrize("name", [k for k in sorted(KATS) if not k.startswith("_")])
 def test_survey_known_answers_on_gpu(name):
     """tests/golden/survey_kats.json straight through the CUDA path (no oracle involved)."""

@@ -173,3 +173,24 @@ def test_cuda_path_reproduces_the_simulated_rtl(name):
         core = (zc.SinTable if v["kind"] == "tbl" else zc.QuarterWav)(phase_bits=d["pw"], ow=d["ow"])
         words = (np.array(v["in"], dtype=np.uint64) << (32 - core.PW)).astype(np.uint32)
         assert ((host(core.lookup(dev(words))) & mask(core.OW)) == np.array(v["out"], dtype=np.int64)).all()
+
+
+@pytest.mark.skipif(not has_reference(), reason="reference tree not mounted")
+def test_pipeline_latencies_match_what_the_adaptors_assume():
+    """o_aux comes out NSTAGES+2 clocks after i_aux goes in for the CORDIC cores, 6 for quadtbl,
+    1 for sintable, 3 for quarterwav -- the latencies the Verilator-shaped adaptors (oracle/shim, cordic_b200/vshim)
+    are built around."""
+    from oracle import vsim
+    want = {"cordic.v": lambda m: m.consts["NSTAGES"] + 2, "topolar.v": lambda m: m.consts["NSTAGES"] + 2,
+            "quadtbl.v": lambda m: 6, "sintable.v": lambda m: 1, "quarterwav.v": lambda m: 3}
+    for fname, lat in want.items():
+        m = vsim.Module(os.path.join("/root/reference/rtl", fname))
+        m.set(i_reset=1, i_ce=1)
+        m.tick()
+        m.set(i_reset=0, i_aux=1)
+        n = 0
+        while not m.get("o_aux"):
+            m.tick()
+            n += 1
+            assert n < 100
+        assert n == lat(m), fname

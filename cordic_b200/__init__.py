@@ -84,6 +84,7 @@ _SIGNATURES = {
     "zc_last_error": (ctypes.c_char_p, []),
     "zc_device_count": (ctypes.c_int, []),
     "zc_launch_count": (ctypes.c_uint64, []),
+    "zc_trim": (ctypes.c_int, [ctypes.c_int]),
     "zc_derive_p2r": (ctypes.c_int, [ctypes.c_int] * 5 + [ctypes.POINTER(Params)]),
     "zc_derive_r2p": (ctypes.c_int, [ctypes.c_int] * 5 + [ctypes.POINTER(Params)]),
     "zc_derive_tbl": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 2),
@@ -168,6 +169,11 @@ def _check(rc):
 
 def launch_count():
     return int(lib().zc_launch_count())
+
+
+def trim(device=-1):
+    """Releases the library's cached device allocations (tables, staging buffers) -- zc_trim."""
+    _check(lib().zc_trim(int(device)))
 
 
 # ---- configuration ------------------------------------------------------------------------

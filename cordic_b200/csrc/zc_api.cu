@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -323,7 +324,7 @@ static int launch_lut(int pw, int ow, const uint32_t *tbl, const uint32_t *phase
 
 // ---- quadtbl ------------------------------------------------------------------------------------
 // Device copies of coefficient tables, keyed by content (the zc_quadtbl is caller memory).
-struct QtDevTable { int device; uint64_t hash; int ntbl; int32_t *dev; bool nowrap; uint64_t stamp; };
+struct QtDevTable { int device; uint64_t hash; int ntbl; std::shared_ptr<void> dev; bool nowrap; uint64_t stamp; };
 static std::mutex g_qt_mu;
 static std::vector<QtDevTable> g_qt_cache;
 static uint64_t g_qt_clock = 0;
@@ -342,7 +343,7 @@ static inline int32_t sext32(uint32_t w, int bits) { return (int32_t)(w << (32 -
 // Uploads (once) the coefficient tables sign-extended, and decides whether the register wraps can be skipped:
 // |lsum| <= |l| + |q| (dx < 2^(DXBITS-1), so the renormalised product is at most |q|) must fit LBITS, and
 // |r| <= |c| + |l| + |q| must fit CBITS, entry by entry.
-static int qt_device_tables(const zc_quadtbl *q, int device, cudaStream_t st, const int32_t **out, bool *nowrap) {
+static int qt_device_tables(const zc_quadtbl *q, int device, cudaStream_t st, std::shared_ptr<void> *out, bool *nowrap) {
 	const uint64_t h = qt_hash(q);
 	const int n = 1 << q->lgtbl;
 	std::lock_guard<std::mutex> lk(g_qt_mu);
@@ -364,14 +365,13 @@ static int qt_device_tables(const zc_quadtbl *q, int device, cudaStream_t st, co
 	cudaError_t e = cudaMemcpyAsync(dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
 	if (e != cudaSuccess) { cudaFree(dev); return set_error(ZC_ECUDA, "quadtbl table upload failed: %s", cudaGetErrorString(e)); }
-	if (g_qt_cache.size() >= 16) {
+	if (g_qt_cache.size() >= 16) {		// evict the least recently used; its memory goes with the last user's copy
 		size_t victim = 0;
 		for (size_t k = 1; k < g_qt_cache.size(); k++) if (g_qt_cache[k].stamp < g_qt_cache[victim].stamp) victim = k;
-		cudaFree(g_qt_cache[victim].dev);
 		g_qt_cache.erase(g_qt_cache.begin() + victim);
 	}
-	g_qt_cache.push_back(QtDevTable{device, h, n, dev, safe, ++g_qt_clock});
-	*out = dev; *nowrap = safe;
+	g_qt_cache.push_back(QtDevTable{device, h, n, std::shared_ptr<void>(dev, DevFree()), safe, ++g_qt_clock});
+	*out = g_qt_cache.back().dev; *nowrap = safe;
 	return ZC_OK;
 }
 
@@ -385,9 +385,10 @@ static int launch_quadtbl(const zc_quadtbl *q, const uint32_t *phase32, int32_t 
 	DeviceScope scope;
 	if ((rc = scope.enter(device)) != ZC_OK) return rc;
 	cudaStream_t st = (cudaStream_t)stream;
-	const int32_t *tables = nullptr;
+	std::shared_ptr<void> hold;
 	bool nowrap = false;
-	if ((rc = qt_device_tables(q, device, st, &tables, &nowrap)) != ZC_OK) return rc;
+	if ((rc = qt_device_tables(q, device, st, &hold, &nowrap)) != ZC_OK) return rc;
+	const int32_t *tables = static_cast<const int32_t *>(hold.get());
 	QtConsts c;
 	c.pshift = 32 - q->pw; c.dxs = q->dxbits - 1; c.dxmask = (1u << (q->dxbits - 1)) - 1u;
 	c.qsh = 32 - q->qbits; c.lsh = 32 - q->lbits; c.csh = 32 - q->cbits;
@@ -414,6 +415,87 @@ static int launch_quadtbl(const zc_quadtbl *q, const uint32_t *phase32, int32_t 
 // stream)` enqueues the device entry point for one chunk.
 struct Lane { size_t bytes_per_sample; const char *host_in; char *host_out; };
 
+// Device staging buffers, streams and events are kept between calls (at most two sets per device):
+// a test bench that sends batch after batch should not pay cudaMalloc + stream creation every time.
+constexpr int PIPE_NBUF = 3;
+struct PipeCtx {
+	int device = -1;
+	char *pool = nullptr;
+	size_t pool_bytes = 0;
+	cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+	cudaEvent_t ev_in[PIPE_NBUF] = {}, ev_k[PIPE_NBUF] = {}, ev_out[PIPE_NBUF] = {};
+};
+static std::mutex g_pipe_mu;
+static std::vector<PipeCtx *> g_pipe_free;
+
+// Called with ctx->device current.
+static void pipe_destroy(PipeCtx *ctx) {
+	for (int b = 0; b < PIPE_NBUF; b++) {
+		if (ctx->ev_in[b]) cudaEventDestroy(ctx->ev_in[b]);
+		if (ctx->ev_k[b]) cudaEventDestroy(ctx->ev_k[b]);
+		if (ctx->ev_out[b]) cudaEventDestroy(ctx->ev_out[b]);
+	}
+	if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+	if (ctx->s_k) cudaStreamDestroy(ctx->s_k);
+	if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+	if (ctx->pool) cudaFree(ctx->pool);
+	delete ctx;
+}
+
+// Called with `device` current.  Returns a context whose pool holds at least `bytes`.
+static int pipe_acquire(int device, size_t bytes, PipeCtx **out) {
+	PipeCtx *ctx = nullptr;
+	{
+		std::lock_guard<std::mutex> lk(g_pipe_mu);
+		size_t pick = g_pipe_free.size();
+		for (size_t k = 0; k < g_pipe_free.size(); k++)
+			if (g_pipe_free[k]->device == device &&
+			    (pick == g_pipe_free.size() || g_pipe_free[k]->pool_bytes > g_pipe_free[pick]->pool_bytes)) pick = k;
+		if (pick < g_pipe_free.size()) {
+			ctx = g_pipe_free[pick];
+			g_pipe_free.erase(g_pipe_free.begin() + pick);
+		}
+	}
+	cudaError_t e = cudaSuccess;
+	if (!ctx) {
+		ctx = new PipeCtx();
+		ctx->device = device;
+		e = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_k, cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
+		for (int b = 0; b < PIPE_NBUF && e == cudaSuccess; b++) {
+			e = cudaEventCreateWithFlags(&ctx->ev_in[b], cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_k[b], cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming);
+		}
+	}
+	if (e == cudaSuccess && ctx->pool_bytes < bytes) {
+		if (ctx->pool) cudaFree(ctx->pool);
+		ctx->pool = nullptr; ctx->pool_bytes = 0;
+		e = cudaMalloc((void **)&ctx->pool, bytes);
+		if (e == cudaSuccess) ctx->pool_bytes = bytes;
+	}
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		pipe_destroy(ctx);
+		return set_error(e == cudaErrorMemoryAllocation ? ZC_ENOMEM : ZC_ECUDA,
+			"host pipeline setup (%zu staging bytes) failed: %s", bytes, cudaGetErrorString(e));
+	}
+	*out = ctx;
+	return ZC_OK;
+}
+
+// Called with ctx->device current and all of its streams idle.
+static void pipe_release(PipeCtx *ctx) {
+	{
+		std::lock_guard<std::mutex> lk(g_pipe_mu);
+		int kept = 0;
+		for (PipeCtx *f : g_pipe_free) kept += (f->device == ctx->device);
+		if (kept < 2) { g_pipe_free.push_back(ctx); return; }
+	}
+	pipe_destroy(ctx);
+}
+
 template <class Launch>
 static int host_pipeline(int device, size_t n, const Lane in[2], const Lane out[2], Launch launch) {
 	DeviceInfo di;
@@ -422,85 +504,92 @@ static int host_pipeline(int device, size_t n, const Lane in[2], const Lane out[
 	if (n == 0) return ZC_OK;
 	DeviceScope scope;
 	if ((rc = scope.enter(device)) != ZC_OK) return rc;
-	constexpr int NBUF = 3;
+	constexpr int NBUF = PIPE_NBUF;
 	const size_t chunk = (n < ((size_t)4 << 20)) ? ((n + 3) & ~(size_t)3) : ((size_t)4 << 20);
+	const size_t sizes[4] = {in[0].bytes_per_sample * chunk, in[1].bytes_per_sample * chunk,
+		out[0].bytes_per_sample * chunk, out[1].bytes_per_sample * chunk};
 	size_t per_buf = 0;
-	for (int k = 0; k < 2; k++) per_buf += (in[k].bytes_per_sample + out[k].bytes_per_sample) * chunk;
-	// every sub-buffer 256-byte aligned
-	per_buf += 4 * 256;
-	char *pool = nullptr;
-	cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-	cudaEvent_t ev_in[NBUF] = {}, ev_k[NBUF] = {}, ev_out[NBUF] = {};
-	auto cleanup = [&]() {
-		for (int b = 0; b < NBUF; b++) {
-			if (ev_in[b]) cudaEventDestroy(ev_in[b]);
-			if (ev_k[b]) cudaEventDestroy(ev_k[b]);
-			if (ev_out[b]) cudaEventDestroy(ev_out[b]);
-		}
-		if (s_in) cudaStreamDestroy(s_in);
-		if (s_k) cudaStreamDestroy(s_k);
-		if (s_out) cudaStreamDestroy(s_out);
-		if (pool) cudaFree(pool);
-	};
+	for (int k = 0; k < 4; k++) per_buf += (sizes[k] + 255) & ~(size_t)255;	// every sub-buffer 256-byte aligned
+	PipeCtx *ctx = nullptr;
+	if ((rc = pipe_acquire(device, per_buf * NBUF, &ctx)) != ZC_OK) return rc;
+	const cudaStream_t s_in = ctx->s_in, s_k = ctx->s_k, s_out = ctx->s_out;
 #define ZC_PIPE(call)                                                                          \
 	do {                                                                                   \
 		cudaError_t e_ = (call);                                                       \
 		if (e_ != cudaSuccess) {                                                       \
 			cudaDeviceSynchronize();                                               \
-			cleanup();                                                             \
+			cudaGetLastError();                                                    \
+			pipe_destroy(ctx);                                                     \
 			return set_error(ZC_ECUDA, "%s failed: %s (%s:%d)", #call,             \
 				cudaGetErrorString(e_), __FILE__, __LINE__);                    \
 		}                                                                              \
 	} while (0)
-	ZC_PIPE(cudaMalloc((void **)&pool, per_buf * NBUF));
-	ZC_PIPE(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-	ZC_PIPE(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
-	ZC_PIPE(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-	for (int b = 0; b < NBUF; b++) {
-		ZC_PIPE(cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming));
-		ZC_PIPE(cudaEventCreateWithFlags(&ev_k[b], cudaEventDisableTiming));
-		ZC_PIPE(cudaEventCreateWithFlags(&ev_out[b], cudaEventDisableTiming));
-	}
 	auto sub = [&](int b, int which) -> char * {	// which: 0,1 = in ; 2,3 = out
 		size_t off = 0;
-		const size_t sizes[4] = {in[0].bytes_per_sample * chunk, in[1].bytes_per_sample * chunk,
-			out[0].bytes_per_sample * chunk, out[1].bytes_per_sample * chunk};
 		for (int k = 0; k < which; k++) off += (sizes[k] + 255) & ~(size_t)255;
-		return pool + per_buf * b + off;
+		return ctx->pool + per_buf * b + off;
 	};
 	size_t ci = 0;
 	for (size_t off = 0; off < n; off += chunk, ci++) {
 		const int b = (int)(ci % NBUF);
 		const size_t cnt = (n - off < chunk) ? (n - off) : chunk;
 		if (ci >= NBUF) {	// the buffer's previous contents must have left the device
-			ZC_PIPE(cudaStreamWaitEvent(s_in, ev_out[b], 0));
+			ZC_PIPE(cudaStreamWaitEvent(s_in, ctx->ev_out[b], 0));
 		}
 		for (int k = 0; k < 2; k++)
 			if (in[k].bytes_per_sample)
 				ZC_PIPE(cudaMemcpyAsync(sub(b, k), in[k].host_in + off * in[k].bytes_per_sample,
 					cnt * in[k].bytes_per_sample, cudaMemcpyHostToDevice, s_in));
-		ZC_PIPE(cudaEventRecord(ev_in[b], s_in));
-		ZC_PIPE(cudaStreamWaitEvent(s_k, ev_in[b], 0));
-		if (ci >= NBUF) ZC_PIPE(cudaStreamWaitEvent(s_k, ev_out[b], 0));
+		ZC_PIPE(cudaEventRecord(ctx->ev_in[b], s_in));
+		ZC_PIPE(cudaStreamWaitEvent(s_k, ctx->ev_in[b], 0));
+		if (ci >= NBUF) ZC_PIPE(cudaStreamWaitEvent(s_k, ctx->ev_out[b], 0));
 		rc = launch(off, cnt, sub(b, 0), sub(b, 1), sub(b, 2), sub(b, 3), s_k);
 		if (rc != ZC_OK) {
 			cudaDeviceSynchronize();
-			cleanup();
+			pipe_destroy(ctx);
 			return rc;
 		}
-		ZC_PIPE(cudaEventRecord(ev_k[b], s_k));
-		ZC_PIPE(cudaStreamWaitEvent(s_out, ev_k[b], 0));
+		ZC_PIPE(cudaEventRecord(ctx->ev_k[b], s_k));
+		ZC_PIPE(cudaStreamWaitEvent(s_out, ctx->ev_k[b], 0));
 		for (int k = 0; k < 2; k++)
 			if (out[k].bytes_per_sample)
 				ZC_PIPE(cudaMemcpyAsync(out[k].host_out + off * out[k].bytes_per_sample, sub(b, 2 + k),
 					cnt * out[k].bytes_per_sample, cudaMemcpyDeviceToHost, s_out));
-		ZC_PIPE(cudaEventRecord(ev_out[b], s_out));
+		ZC_PIPE(cudaEventRecord(ctx->ev_out[b], s_out));
 	}
 	ZC_PIPE(cudaStreamSynchronize(s_out));
 	ZC_PIPE(cudaStreamSynchronize(s_k));
 	ZC_PIPE(cudaStreamSynchronize(s_in));
 #undef ZC_PIPE
-	cleanup();
+	pipe_release(ctx);
+	return ZC_OK;
+}
+
+// Frees the cached device allocations of `device` (all devices when negative): staging pools, seed tables,
+// quadtbl tables.  Safe at any time: cudaFree lets in-flight work finish first.
+static int trim_caches(int device) {
+	std::vector<PipeCtx *> victims;
+	{
+		std::lock_guard<std::mutex> lk(g_pipe_mu);
+		for (size_t k = 0; k < g_pipe_free.size();) {
+			if (device < 0 || g_pipe_free[k]->device == device) {
+				victims.push_back(g_pipe_free[k]);
+				g_pipe_free.erase(g_pipe_free.begin() + k);
+			} else k++;
+		}
+	}
+	for (PipeCtx *ctx : victims) {
+		DeviceScope scope;
+		if (scope.enter(ctx->device) == ZC_OK) pipe_destroy(ctx);
+	}
+	{
+		std::lock_guard<std::mutex> lk(g_qt_mu);
+		for (size_t k = 0; k < g_qt_cache.size();) {
+			if (device < 0 || g_qt_cache[k].device == device) g_qt_cache.erase(g_qt_cache.begin() + k);
+			else k++;
+		}
+	}
+	seed_trim(device);
 	return ZC_OK;
 }
 
@@ -538,6 +627,8 @@ int zc_device_count(void) {
 }
 
 uint64_t zc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int zc_trim(int device) { return trim_caches(device); }
 
 int zc_derive_p2r(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *out) {
 	return derive_p2r(iw, ow, xtra_user, pw, nstages, out);

@@ -31,7 +31,9 @@
 #include "zc_kernels.cuh"
 
 #include <cstring>
+#include <memory>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 namespace zc {
@@ -284,6 +286,7 @@ struct SeedPlan {
 	int flavour = FL_WORDS;
 	SeedConsts s;
 	void *dev = nullptr;		// tables, laid out as in shared memory
+	std::shared_ptr<void> hold;	// owns `dev`: a copy of the plan keeps the tables alive across a cache eviction
 	bool usable = false;		// false: geometry does not fit; cached so we do not retry
 	uint64_t stamp = 0;
 };
@@ -367,16 +370,8 @@ static std::mutex g_seed_mu;
 static std::vector<SeedPlan> g_seed_cache;
 static uint64_t g_seed_clock = 0;
 
-static void seed_release(SeedPlan &pl) {
-	if (pl.dev) {
-		int prev = -1;
-		cudaGetDevice(&prev);
-		cudaSetDevice(pl.device);
-		cudaFree(pl.dev);
-		if (prev >= 0) cudaSetDevice(prev);
-		pl.dev = nullptr;
-	}
-}
+// cudaFree waits for the device to go idle, so kernels already enqueued on the tables finish first.
+struct DevFree { void operator()(void *ptr) const { if (ptr) cudaFree(ptr); } };
 
 // Builds (or finds) the plan for (p, constant vector, device).  Called with the device current.
 static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, int flavour, cudaStream_t st,
@@ -449,6 +444,7 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, in
 		}
 		if (ok) {
 			cudaError_t e = cudaMalloc(&pl.dev, host.size() * 4);
+			if (e == cudaSuccess) pl.hold = std::shared_ptr<void>(pl.dev, DevFree());
 			if (e == cudaSuccess) e = cudaMemcpyAsync(pl.dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st);
 			if (e == cudaSuccess && flavour != FL_DIRS) {
 				const uint32_t nthreads = 4u * (uint32_t)R;
@@ -459,7 +455,7 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, in
 			}
 			if (e == cudaSuccess) e = cudaStreamSynchronize(st);	// tables complete before any stream uses them
 			if (e != cudaSuccess) {
-				seed_release(pl);
+				cudaGetLastError();
 				return set_error(ZC_ECUDA, "seed table setup failed: %s", cudaGetErrorString(e));
 			}
 		}
@@ -469,12 +465,42 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, in
 		size_t victim = 0;
 		for (size_t k = 1; k < g_seed_cache.size(); k++)
 			if (g_seed_cache[k].stamp < g_seed_cache[victim].stamp) victim = k;
-		seed_release(g_seed_cache[victim]);
-		g_seed_cache.erase(g_seed_cache.begin() + victim);
+		g_seed_cache.erase(g_seed_cache.begin() + victim);	// the tables go when the last user's copy does
 	}
 	g_seed_cache.push_back(pl);
 	out = pl;
 	return ZC_OK;
+}
+
+// cudaFuncSetAttribute once per (device, kernel, size): launches of a configured kernel then consist of the
+// launch alone, which keeps them legal inside a stream capture.
+static cudaError_t ensure_dynamic_smem(const void *kern, size_t smem) {
+	static std::mutex mu;
+	static std::vector<std::pair<std::pair<int, const void *>, size_t>> seen;
+	int device = 0;
+	cudaError_t e = cudaGetDevice(&device);
+	if (e != cudaSuccess) return e;
+	std::lock_guard<std::mutex> lk(mu);
+	for (auto &it : seen)
+		if (it.first.first == device && it.first.second == kern) {
+			if (it.second >= smem) return cudaSuccess;
+			e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (e == cudaSuccess) it.second = smem;
+			return e;
+		}
+	e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e == cudaSuccess) seen.push_back({{device, kern}, smem});
+	return e;
+}
+
+// Drops the cached plans of `device` (all devices when negative).  The gate ring stays: 4 KB per device, and a
+// launch already enqueued may still read its slot.
+static void seed_trim(int device) {
+	std::lock_guard<std::mutex> lk(g_seed_mu);
+	for (size_t k = 0; k < g_seed_cache.size();) {
+		if (device < 0 || g_seed_cache[k].device == device) g_seed_cache.erase(g_seed_cache.begin() + k);
+		else k++;
+	}
 }
 
 template <int SRC, int NS>
@@ -489,7 +515,7 @@ struct SeedTable {
 			if (tdm == TD_TABLE) kern = rf ? k_rotate_seeded<NS, SRC, true, TD_TABLE> : k_rotate_seeded<NS, SRC, false, TD_TABLE>;
 			else if (tdm == TD_REGS) kern = rf ? k_rotate_seeded<NS, SRC, true, TD_REGS> : k_rotate_seeded<NS, SRC, false, TD_REGS>;
 			else kern = rf ? k_rotate_seeded<NS, SRC, true, TD_PACKED> : k_rotate_seeded<NS, SRC, false, TD_PACKED>;
-			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			cudaError_t e = ensure_dynamic_smem((const void *)kern, smem);
 			if (e != cudaSuccess) return e;
 			kern<<<grid, 1024, smem, st>>>(ph, out, nblocks, c, s, tables, gate);
 			return cudaGetLastError();
@@ -616,7 +642,7 @@ struct DirsTable {
 			const bool rf = c.do_round && c.wsh >= 9;
 			typedef void (*kern_t)(const uint32_t *, const int2 *, int2 *, size_t, const CoreConsts, const SeedConsts, const uint4 *);
 			kern_t kern = rf ? (kern_t)k_rotate_dirs<NS, SRC, true> : (kern_t)k_rotate_dirs<NS, SRC, false>;
-			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			cudaError_t e = ensure_dynamic_smem((const void *)kern, smem);
 			if (e != cudaSuccess) return e;
 			kern<<<grid, 1024, smem, st>>>(ph, xin, out, nblocks, c, s, tables);
 			return cudaGetLastError();

@@ -199,6 +199,14 @@ long zc_hex_read(const char *path, uint32_t *words, size_t max_words);
  * (all devices); lets a benchmark report how many of OUR kernels ran in a timed region. */
 uint64_t zc_launch_count(void);
 
+/* The library keeps a few device allocations between calls: the seed/direction tables of recently used
+ * configurations, quadtbl coefficient tables, and the staging buffers + streams of the *_host pipelines
+ * (the model the reference's test bench `new`s once and clocks many times, bench/cpp/testb.h:56-63).
+ * zc_trim releases those of `device` (every device when negative); work already enqueued finishes first.
+ * The first call for a new configuration uploads its tables and synchronises the stream -- warm up before
+ * capturing calls into a CUDA graph. */
+int zc_trim(int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,145 @@
+"""GPU tier: the library's runtime behaviour around the kernels -- stream ordering (CUDA graph capture and
+replay), the caches (`zc_trim`, eviction under concurrent use) and repeated host pipelines.  Results stay
+bit-exact against the oracle throughout.  Marked ``gpu``."""
+import threading
+
+import numpy as np
+import pytest
+
+import cordic_b200 as zc
+from . import zo
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+SEED = 20261017
+CFG1 = dict(iw=18, ow=18, xtra=2, pw=24, n=20)
+
+
+def both_p2r(iw=0, ow=0, xtra=2, pw=0, n=0):
+    core = zc.Cordic(iw, ow, xtra, pw, n)
+    rc, op = zo.derive_p2r(iw, ow, xtra, pw, n)
+    assert rc == 0
+    return core, op
+
+
+@pytest.mark.parametrize("n", [1 << 16, (1 << 22) + 77])
+def test_rotate_const_cuda_graph_replay(n):
+    """Every device entry point only enqueues work on the caller's stream, so once the tables of a
+    configuration exist a call can be captured into a CUDA graph and replayed on fresh inputs (small n: one
+    plain kernel; large n: probe + both gated table kernels + tail)."""
+    core, op = both_p2r(**CFG1)
+    rng = np.random.default_rng(SEED)
+    phase = torch.zeros(n, dtype=torch.int32, device="cuda")
+    out = torch.empty((n, 2), dtype=torch.int32, device="cuda")
+    core.rotate_const(131071, 0, phase, out=out)          # warm-up: builds and caches the tables
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        core.rotate_const(131071, 0, phase, out=out)      # picks up the capture stream via current_stream()
+    for rnd in range(3):
+        ph = rng.integers(0, 1 << 24, size=n, dtype=np.uint64).astype(np.uint32) if rnd else \
+            (np.arange(n, dtype=np.uint32) & 0xFFFFFF)
+        phase.copy_(torch.from_numpy(ph.view(np.int32)))
+        out.fill_(-1)
+        g.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), zo.rotate_const(op, 131071, 0, ph)), rnd
+
+
+def test_topolar_and_rotate_xy_cuda_graph_replay():
+    core, op = both_p2r(**CFG1)
+    tcore = zc.Topolar(16, 16, 2)
+    rc, top = zo.derive_r2p(16, 16, 2, 0, 0)
+    n = (1 << 20) + 5
+    rng = np.random.default_rng(SEED + 1)
+    xy = torch.zeros((n, 2), dtype=torch.int32, device="cuda")
+    phase = torch.zeros(n, dtype=torch.int32, device="cuda")
+    core.rotate(xy, phase)
+    tcore.topolar(xy)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        rot = core.rotate(xy, phase)
+        mag, ang = tcore.topolar(xy)
+    hxy = rng.integers(-32768, 32768, size=(n, 2), dtype=np.int64).astype(np.int32)
+    hph = rng.integers(0, 1 << 24, size=n, dtype=np.uint64).astype(np.uint32)
+    xy.copy_(torch.from_numpy(hxy))
+    phase.copy_(torch.from_numpy(hph.view(np.int32)))
+    g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(rot.cpu().numpy(), zo.rotate(op, hxy, hph))
+    wmag, wang = zo.topolar(top, hxy)
+    assert np.array_equal(mag.cpu().numpy(), wmag)
+    assert np.array_equal(ang.cpu().numpy().view(np.uint32), wang)
+
+
+def test_trim_between_calls():
+    """zc_trim drops tables and staging buffers; the next call rebuilds them and the results do not change."""
+    core, op = both_p2r(**CFG1)
+    n = (1 << 21) + 9
+    ph = (np.arange(n, dtype=np.uint64) * 2654435761 % (1 << 24)).astype(np.uint32)
+    want = zo.rotate_const(op, 131071, 0, ph)
+    out = np.empty((n, 2), dtype=np.int32)
+    for rnd in range(3):
+        out.fill(-1)
+        core.rotate_const_host(131071, 0, ph, out)
+        assert np.array_equal(out, want), rnd
+        got = core.rotate_const(131071, 0, torch.from_numpy(ph.view(np.int32)).cuda())
+        torch.cuda.synchronize()
+        assert np.array_equal(got.cpu().numpy(), want), rnd
+        zc.trim(0 if rnd else -1)
+
+
+def test_host_pipeline_reuses_staging():
+    """Back-to-back host calls of different shapes share the cached staging pool (it only ever grows)."""
+    core, op = both_p2r(**CFG1)
+    tcore = zc.Topolar(16, 16, 2)
+    rc, top = zo.derive_r2p(16, 16, 2, 0, 0)
+    rng = np.random.default_rng(SEED + 2)
+    for n in [1000, (1 << 22) + 3, 17, (9 << 20) + 1, 4096]:
+        ph = rng.integers(0, 1 << 24, size=n, dtype=np.uint64).astype(np.uint32)
+        out = np.empty((n, 2), dtype=np.int32)
+        core.rotate_const_host(131071, 0, ph, out)
+        assert np.array_equal(out, zo.rotate_const(op, 131071, 0, ph)), n
+        m = min(n, 1 << 20)
+        xy = rng.integers(-32768, 32768, size=(m, 2), dtype=np.int64).astype(np.int32)
+        mag = np.empty(m, dtype=np.int32)
+        ang = np.empty(m, dtype=np.uint32)
+        tcore.topolar_host(xy, mag, ang)
+        wmag, wang = zo.topolar(top, xy)
+        assert np.array_equal(mag, wmag) and np.array_equal(ang, wang), n
+
+
+def test_concurrent_threads_with_plan_eviction():
+    """Four host threads, each on its own stream, cycling through more constant vectors than the plan cache
+    holds (16): plans are evicted while other threads still hold and use them.  Every result is checked."""
+    core, op = both_p2r(**CFG1)
+    n = 1 << 20
+    ph = (np.arange(n, dtype=np.uint32) * 16) & 0xFFFFFF
+    dph = torch.from_numpy(ph.view(np.int32)).cuda()
+    vectors = [(131071 - 97 * k, 13 * k - 40) for k in range(24)]
+    want = {v: zo.rotate_const(op, v[0], v[1], ph) for v in vectors}
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(tid):
+        try:
+            st = torch.cuda.Stream()
+            out = torch.empty((n, 2), dtype=torch.int32, device="cuda")
+            for rnd in range(2):
+                for k in range(tid, len(vectors) + tid):
+                    v = vectors[(k * 5) % len(vectors)]
+                    core.rotate_const(v[0], v[1], dph, out=out, stream=st, flags=zc.F_FORCE_SEED)
+                    st.synchronize()
+                    if not np.array_equal(out.cpu().numpy(), want[v]):
+                        errors.append((tid, rnd, v))
+        except Exception as e:          # noqa: BLE001 - reported below
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]

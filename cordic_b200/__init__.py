@@ -40,7 +40,7 @@ class Params(ctypes.Structure):
     _fields_ = [
         ("mode", ctypes.c_int32), ("iw", ctypes.c_int32), ("ow", ctypes.c_int32),
         ("nextra", ctypes.c_int32), ("ww", ctypes.c_int32), ("pw", ctypes.c_int32),
-        ("nstages", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("nstages", ctypes.c_int32), ("seq", ctypes.c_int32),
         ("angle", ctypes.c_uint32 * ZC_MAX_STAGES),
         ("gain", ctypes.c_double), ("cordic_gain", ctypes.c_double), ("qvar", ctypes.c_double),
         ("pvar_rad", ctypes.c_double), ("best_cnr", ctypes.c_double),
@@ -56,6 +56,8 @@ class Params(ctypes.Structure):
                  PHASE_VARIANCE_RAD=self.pvar_rad, GAIN=self.gain)
         if self.mode == MODE_P2R:
             h["BEST_POSSIBLE_CNR"] = self.best_cnr
+        if self.seq:
+            h["CLOCKS_PER_OUTPUT"] = int(lib().zc_clocks_per_output(ctypes.byref(self)))
         return h
 
 
@@ -87,6 +89,10 @@ _SIGNATURES = {
     "zc_trim": (ctypes.c_int, [ctypes.c_int]),
     "zc_derive_p2r": (ctypes.c_int, [ctypes.c_int] * 5 + [ctypes.POINTER(Params)]),
     "zc_derive_r2p": (ctypes.c_int, [ctypes.c_int] * 5 + [ctypes.POINTER(Params)]),
+    "zc_derive_sp2r": (ctypes.c_int, [ctypes.c_int] * 5 + [ctypes.POINTER(Params)]),
+    "zc_derive_sr2p": (ctypes.c_int, [ctypes.c_int] * 5 + [ctypes.POINTER(Params)]),
+    "zc_iterations": (ctypes.c_int, [ctypes.POINTER(Params)]),
+    "zc_clocks_per_output": (ctypes.c_int, [ctypes.POINTER(Params)]),
     "zc_derive_tbl": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 2),
     "zc_derive_qtr": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 2),
     "zc_lut_build_sintable": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
@@ -189,6 +195,20 @@ def derive_r2p(iw=0, ow=0, xtra=2, pw=0, nstages=0):
     """``gencordic -t r2p ...`` (sw/main.cpp:312-328, sw/topolar.cpp:67-75)."""
     p = Params()
     _check(lib().zc_derive_r2p(iw or 0, ow or 0, xtra, pw or 0, nstages or 0, ctypes.byref(p)))
+    return p
+
+
+def derive_sp2r(iw=0, ow=0, xtra=2, pw=0, nstages=0):
+    """``gencordic -t sp2r ...``: the sequential core rtl/seqcordic.v (zc_params.seq = 1)."""
+    p = Params()
+    _check(lib().zc_derive_sp2r(iw or 0, ow or 0, xtra, pw or 0, nstages or 0, ctypes.byref(p)))
+    return p
+
+
+def derive_sr2p(iw=0, ow=0, xtra=2, pw=0, nstages=0):
+    """``gencordic -t sr2p ...``: the sequential core rtl/seqpolar.v (zc_params.seq = 1)."""
+    p = Params()
+    _check(lib().zc_derive_sr2p(iw or 0, ow or 0, xtra, pw or 0, nstages or 0, ctypes.byref(p)))
     return p
 
 
@@ -311,8 +331,9 @@ class PinnedBuffer:
 class Cordic:
     """Rotation-mode core: the function of rtl/cordic.v (phase -> rotated (x, y))."""
 
-    def __init__(self, iw=0, ow=0, xtra=2, phase_bits=0, nstages=0):
-        self.params = derive_p2r(iw, ow, xtra, phase_bits, nstages)
+    def __init__(self, iw=0, ow=0, xtra=2, phase_bits=0, nstages=0, sequential=False):
+        """``sequential=True``: the function of rtl/seqcordic.v (``-t sp2r``) instead."""
+        self.params = (derive_sp2r if sequential else derive_p2r)(iw, ow, xtra, phase_bits, nstages)
         for k, v in self.params.header().items():
             setattr(self, k, v)
 
@@ -385,8 +406,9 @@ class Cordic:
 class Topolar:
     """Vectoring-mode core: the function of rtl/topolar.v ((x, y) -> magnitude, phase)."""
 
-    def __init__(self, iw=0, ow=0, xtra=2, phase_bits=0, nstages=0):
-        self.params = derive_r2p(iw, ow, xtra, phase_bits, nstages)
+    def __init__(self, iw=0, ow=0, xtra=2, phase_bits=0, nstages=0, sequential=False):
+        """``sequential=True``: the function of rtl/seqpolar.v (``-t sr2p``) instead."""
+        self.params = (derive_sr2p if sequential else derive_r2p)(iw, ow, xtra, phase_bits, nstages)
         for k, v in self.params.header().items():
             setattr(self, k, v)
 

@@ -93,15 +93,35 @@ int check_params(const zc_params *p, int want_mode) {
 			p->iw, p->ow, p->ww, p->pw, p->nstages);
 	if (want_mode == ZC_MODE_P2R ? (p->ww - p->iw < 1) : (p->ww - p->iw < 2))
 		return set_error(ZC_ERANGE, "working width %d too small for IW=%d", p->ww, p->iw);
+	if (p->seq != 0 && p->seq != 1)
+		return set_error(ZC_EINVAL, "zc_params.seq=%d (0: pipelined core, 1: sequential core)", p->seq);
+	if (p->seq && (want_mode == ZC_MODE_P2R ? p->nstages < 3 : (p->nstages < 1 || ((p->nstages + 1) & p->nstages) == 0)))
+		return set_error(ZC_ERANGE, "sequential core with NSTAGES=%d does not exist in the reference", p->nstages);
 	return ZC_OK;
+}
+
+// Stage updates that reach the output.  Pipelined cores: NSTAGES (of which some may be pass-through).  Sequential
+// cores: rtl/seqcordic.v:319-324 registers its outputs two iterations early; rtl/seqpolar.v runs all NSTAGES.
+int iterations(const zc_params *p) {
+	if (!p->seq) return p->nstages;
+	return p->mode == ZC_MODE_P2R ? p->nstages - 2 : p->nstages;
 }
 
 // Stages i with cordic_angle[i]==0 or i>=WW are pass-through (rtl/cordic.v:253).  The angle
 // table is non-increasing, so the live stages are a prefix; its length is what we unroll.
+// The sequential machines have no such test (rtl/seqcordic.v:281-299): every iteration counts there.
 static int live_stages(const zc_params *p) {
+	if (p->seq) return iterations(p);
 	int n = 0;
 	while (n < p->nstages && n < p->ww && p->angle[n] != 0) n++;
 	return n;
+}
+
+// The table kernels derive the directions from strictly positive angles; a sequential core may run zero ones.
+static bool angles_all_live(const zc_params *p, int neff) {
+	for (int k = 0; k < neff; k++)
+		if (k >= ZC_MAX_STAGES || p->angle[k] == 0) return false;
+	return true;
 }
 
 // True when 32-bit non-wrapping arithmetic provably equals the RTL's WW-bit wrapping
@@ -225,7 +245,7 @@ static int launch_rotate(const zc_params *p, CoreConsts &c, const uint32_t *phas
 	const bool pair_ok = aligned8(xy_out) && (!has_xy || aligned8(xy_in));
 	const bool vec_ok = aligned16(xy_out) && (!has_phase || aligned16(phase)) && (!has_xy || aligned16(xy_in));
 	size_t done = 0;
-	if (math_ok && pair_ok && !(flags & ZC_F_NO_SEED)) {
+	if (math_ok && pair_ok && !(flags & ZC_F_NO_SEED) && (!p->seq || angles_all_live(p, c.neff))) {
 		int launched = 0;
 		if constexpr (SRC == SRC_XY || SRC == SRC_MIX)
 			rc = dirs_rotate_try<SRC>(p, c, phase, xy_in, xy_out, n, device, di.sms, st, flags, done, launched);
@@ -635,6 +655,21 @@ int zc_derive_p2r(int iw, int ow, int xtra_user, int pw, int nstages, zc_params 
 }
 int zc_derive_r2p(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *out) {
 	return derive_r2p(iw, ow, xtra_user, pw, nstages, out);
+}
+int zc_derive_sp2r(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *out) {
+	return derive_sp2r(iw, ow, xtra_user, pw, nstages, out);
+}
+int zc_derive_sr2p(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *out) {
+	return derive_sr2p(iw, ow, xtra_user, pw, nstages, out);
+}
+int zc_iterations(const zc_params *p) {
+	if (!p) return set_error(ZC_EINVAL, "NULL zc_params");
+	return iterations(p);
+}
+int zc_clocks_per_output(const zc_params *p) {
+	if (!p) return set_error(ZC_EINVAL, "NULL zc_params");
+	if (!p->seq) return 1;
+	return p->mode == ZC_MODE_P2R ? p->nstages + 1 : p->nstages + 3;	// sw/seqcordic.cpp:459, sw/seqpolar.cpp:396
 }
 int zc_derive_tbl(int iw, int pw, int ow, int *pw_out, int *ow_out) {
 	return derive_lut(false, iw, pw, ow, pw_out, ow_out);

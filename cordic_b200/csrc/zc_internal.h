@@ -12,6 +12,8 @@ int set_error(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3
 
 int derive_p2r(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *o);
 int derive_r2p(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *o);
+int derive_sp2r(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *o);
+int derive_sr2p(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *o);
 int derive_lut(bool quarter, int iw, int pw, int ow, int *pw_out, int *ow_out);
 int check_lut(bool quarter, int pw, int ow);
 int build_sintable(int pw, int ow, uint32_t *tbl);

@@ -259,12 +259,13 @@ k_rotate_generic(const uint32_t *__restrict__ phase, const int32_t *__restrict__
 			const int sh = (k + 1 > 31) ? 31 : (k + 1);
 			const int sy = y >> sh, sx = x >> sh;
 			const uint32_t ux = (uint32_t)x, uy = (uint32_t)y;	// unsigned: the sums may wrap (WW up to 32)
+			const uint32_t ak = (k < 32) ? c.pa[k] : 0u;		// sequential cores iterate past the last angle
 			if (p < 0) {
 				x = wrapw((int)(ux + (uint32_t)sy), c.wsh); y = wrapw((int)(uy - (uint32_t)sx), c.wsh);
-				p = (int)((uint32_t)p + c.pa[k]);
+				p = (int)((uint32_t)p + ak);
 			} else {
 				x = wrapw((int)(ux - (uint32_t)sy), c.wsh); y = wrapw((int)(uy + (uint32_t)sx), c.wsh);
-				p = (int)((uint32_t)p - c.pa[k]);
+				p = (int)((uint32_t)p - ak);
 			}
 		}
 		const int bx = (x >> c.D) & c.do_round, by = (y >> c.D) & c.do_round;
@@ -293,10 +294,11 @@ k_topolar_generic(const int32_t *__restrict__ xyin, int32_t *__restrict__ mag,
 			const int sh = (k + 1 > 31) ? 31 : (k + 1);
 			const int sy = y >> sh, sx = x >> sh;
 			const uint32_t ux = (uint32_t)x, uy = (uint32_t)y;
+			const uint32_t ak = (k < 32) ? c.pa[k] : 0u;
 			if (y < 0) {
-				x = wrapw((int)(ux - (uint32_t)sy), c.wsh); y = wrapw((int)(uy + (uint32_t)sx), c.wsh); ph -= c.pa[k];
+				x = wrapw((int)(ux - (uint32_t)sy), c.wsh); y = wrapw((int)(uy + (uint32_t)sx), c.wsh); ph -= ak;
 			} else {
-				x = wrapw((int)(ux + (uint32_t)sy), c.wsh); y = wrapw((int)(uy - (uint32_t)sx), c.wsh); ph += c.pa[k];
+				x = wrapw((int)(ux + (uint32_t)sy), c.wsh); y = wrapw((int)(uy - (uint32_t)sx), c.wsh); ph += ak;
 			}
 		}
 		const int b = (x >> c.D) & c.do_round;

@@ -144,6 +144,29 @@ int derive_r2p(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *o)
 }
 
 // sw/main.cpp:358-379 (tbl) / :401-422 (qtr).  In main() "not given" is -1; here <=0.
+// -t sp2r / -t sr2p (sw/main.cpp:183-198): the constants are those of the pipelined core (same branch of main(),
+// sw/seqcordic.cpp:455-498 and sw/seqpolar.cpp:393-415 print the same set plus CLOCKS_PER_OUTPUT); what changes is
+// the schedule the state machine runs (include/zcordic.h, zc_params.seq).
+int derive_sp2r(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *o) {
+	int rc = derive_p2r(iw, ow, xtra_user, pw, nstages, o);
+	if (rc != ZC_OK) return rc;
+	if (o->nstages < 3)
+		return set_error(ZC_ERANGE, "sequential p2r needs NSTAGES >= 3 (got %d): its output is taken two iterations early",
+			o->nstages);
+	o->seq = 1;
+	return ZC_OK;
+}
+
+int derive_sr2p(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *o) {
+	int rc = derive_r2p(iw, ow, xtra_user, pw, nstages, o);
+	if (rc != ZC_OK) return rc;
+	if (o->nstages < 1 || ((o->nstages + 1) & o->nstages) == 0)
+		return set_error(ZC_ERANGE, "sequential r2p with NSTAGES=%d: the reference's state register "
+			"(nextlg(NSTAGES+1) bits, sw/seqpolar.cpp:158-159) cannot reach NSTAGES+1, o_done never rises", o->nstages);
+	o->seq = 1;
+	return ZC_OK;
+}
+
 int derive_lut(bool quarter, int iw, int pw, int ow, int *pw_out, int *ow_out) {
 	if (!pw_out || !ow_out) return set_error(ZC_EINVAL, "NULL output");
 	if (iw <= 0) iw = -1;

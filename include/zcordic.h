@@ -58,7 +58,7 @@ typedef struct zc_params {
 	int32_t	 iw, ow;		/* IW, OW                                          */
 	int32_t	 nextra;		/* NEXTRA as printed (already incremented)          */
 	int32_t	 ww, pw, nstages;	/* WW, PW, NSTAGES                                  */
-	int32_t	 reserved;
+	int32_t	 seq;			/* 0: pipelined core; 1: sequential core (zc_derive_sp2r/_sr2p), see below */
 	uint32_t angle[ZC_MAX_STAGES];	/* cordic_angle[k], PW-bit, truncated               */
 	double	 gain;			/* GAIN                                             */
 	double	 cordic_gain;		/* prod sqrt(1+2^-2(k+1)) (== GAIN for p2r)         */
@@ -111,6 +111,23 @@ int         zc_device_count(void);			/* >=0, or ZC_ECUDA */
 int zc_derive_p2r(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *out);
 /* gencordic -t r2p ...   sw/main.cpp:312-328, sw/topolar.cpp:67-75 (nxtra added twice), :428-446 */
 int zc_derive_r2p(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *out);
+/* gencordic -t sp2r / -t sr2p ...  the sequential cores rtl/seqcordic.v, rtl/seqpolar.v (sw/main.cpp:183-198,
+ * sw/seqcordic.cpp, sw/seqpolar.cpp): one sample every CLOCKS_PER_OUTPUT clocks behind an i_stb/o_busy/o_done
+ * handshake (rtl/seqcordic.v:63-70).  The constants are those of the pipelined core; zc_params.seq = 1 selects the
+ * schedule the state machine really runs, which is NOT that of the pipelined core:
+ *   - every iteration executes, zero cordic_angle or shift >= WW included (no pass-through test;
+ *     rtl/seqcordic.v:281-299, rtl/seqpolar.v),
+ *   - seqcordic registers o_xval/o_yval when state == NSTAGES-1 (rtl/seqcordic.v:319-324), i.e. after NSTAGES-2
+ *     iterations; seqpolar's last_state is state >= NSTAGES+1, i.e. NSTAGES iterations.
+ * A batch call with such a zc_params returns, per sample, exactly what the sequential core would present with
+ * o_done.  zc_derive_sr2p returns ZC_ERANGE when NSTAGES+1 is a power of two: the reference's state register
+ * (sw/seqpolar.cpp:158-159) cannot count that far and the core never finishes. */
+int zc_derive_sp2r(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *out);
+int zc_derive_sr2p(int iw, int ow, int xtra_user, int pw, int nstages, zc_params *out);
+/* Stage updates that reach the output (NSTAGES; NSTAGES-2 for sp2r) and CLOCKS_PER_OUTPUT as printed in
+ * rtl/seqcordic.h:49 / rtl/seqpolar.h:49 (1 for the pipelined cores). */
+int zc_iterations(const zc_params *p);
+int zc_clocks_per_output(const zc_params *p);
 /* gencordic -t tbl [-i n] [-p pw] [-o ow]   sw/main.cpp:358-379 ; limit sw/sintable.cpp:62 */
 int zc_derive_tbl(int iw, int pw, int ow, int *pw_out, int *ow_out);
 /* gencordic -t qtr ...                       sw/main.cpp:401-422 ; limit sw/sintable.cpp:190 */

@@ -408,7 +408,12 @@ class Module:
         self.comb = []          # (kind, compiled) continuous assigns and always @(*) blocks
         self.seq = []           # compiled always @(posedge ...) bodies
         self.clock = None
+        self.inits = []         # compiled `initial x = value;` statements, run once after elaboration
         self._elab(items, {})
+        upd = []
+        for f in self.inits:
+            f(self.state, upd)
+        self._commit(upd)
         self.settle()
 
     # ---- constant expressions ----------------------------------------------------------------
@@ -497,7 +502,8 @@ class Module:
                 else:
                     words[addr] = int(tok, 16) & _mask(self.sigs[mem].width)
                     addr += 1
-        # initial x = 0: registers start at zero anyway
+        elif st[0] in ("ba", "nba"):            # initial x = value;  (rtl/seqcordic.v:204-219, :230)
+            self.inits.append(self.c_assign(st, env))
 
     # ---- expression typing (IEEE 1364-2005 table 5-22) ---------------------------------------
     def typ(self, e, env):
@@ -868,4 +874,33 @@ def run_pipeline(mod, inputs, outputs, ce="i_ce", aux_in="i_aux", aux_out="o_aux
         mod.tick()
         if mod.get(aux_out):
             got.append(tuple(mod.get(o) for o in outputs))
+    return got
+
+
+def run_handshake(mod, inputs, outputs, clocks_per_output, reset="i_reset", aux_in="i_aux", aux_out="o_aux"):
+    """Drives a sequential core the way bench/cpp/cordic_tb.cpp:146-158 does when CLOCKS_PER_OUTPUT is defined:
+    i_stb for one clock, CLOCKS_PER_OUTPUT ticks per sample, o_done low until the last tick and high on it.
+    Returns the `outputs` port words per sample, or None as soon as a sample breaks that protocol (the core never
+    finishes, or finishes early)."""
+    names = set(mod.sigs)
+    if reset in names:
+        mod.set(**{reset: 1, "i_stb": 0})
+        mod.tick()
+        mod.set(**{reset: 0})
+    got = []
+    for vec in inputs:
+        kw = dict(vec)
+        kw["i_stb"] = 1
+        if aux_in in names:
+            kw[aux_in] = 1
+        mod.set(**kw)
+        for _ in range(clocks_per_output - 1):
+            mod.tick()
+            mod.set(i_stb=0)
+            if mod.get("o_done"):
+                return None
+        mod.tick()
+        if not mod.get("o_done") or (aux_out in names and not mod.get(aux_out)):
+            return None
+        got.append(tuple(mod.get(o) for o in outputs))
     return got

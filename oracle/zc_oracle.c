@@ -241,6 +241,39 @@ int zo_derive_qtr(int iw, int pw, int ow, int *pw_out, int *ow_out) {
 /* ---- rotation core: rtl/cordic.v --------------------------------------- */
 
 /* rtl/cordic.v:85-86 (extend) and :131-188 (octant pre-rotation) */
+/* ---- sequential cores: rtl/seqcordic.v, rtl/seqpolar.v ----------------------- */
+int zo_derive_sp2r(int iw, int ow, int xtra_user, int pw, int nstages, zo_params *p) {
+	int rc = zo_derive_p2r(iw, ow, xtra_user, pw, nstages, p);	/* same branch of sw/main.cpp:260-279 */
+	if (rc != 0)
+		return rc;
+	if (p->nstages < 3)
+		return -2;
+	p->sequential = 1;
+	return 0;
+}
+
+int zo_derive_sr2p(int iw, int ow, int xtra_user, int pw, int nstages, zo_params *p) {
+	int rc = zo_derive_r2p(iw, ow, xtra_user, pw, nstages, p);	/* sw/main.cpp:312-328 */
+	if (rc != 0)
+		return rc;
+	if (p->nstages < 1 || ((p->nstages + 1) & p->nstages) == 0)	/* state register too narrow: never done */
+		return -2;
+	p->sequential = 1;
+	return 0;
+}
+
+int zo_iterations(const zo_params *p) {
+	if (!p->sequential)
+		return p->nstages;
+	return p->vectoring ? p->nstages : p->nstages - 2;
+}
+
+int zo_clocks_per_output(const zo_params *p) {
+	if (!p->sequential)
+		return 1;
+	return p->vectoring ? p->nstages + 3 : p->nstages + 1;	/* sw/seqpolar.cpp:396, sw/seqcordic.cpp:459 */
+}
+
 void zo_rotate_pre(const zo_params *p, int32_t ix, int32_t iy, uint32_t phase,
 		int32_t *x, int32_t *y, uint32_t *ph) {
 	const int WW = p->ww, IW = p->iw, PW = p->pw;
@@ -269,11 +302,13 @@ void zo_rotate_pre(const zo_params *p, int32_t ix, int32_t iy, uint32_t phase,
 /* rtl/cordic.v:253-280 */
 void zo_rotate_stage(const zo_params *p, int i, int32_t *x, int32_t *y, uint32_t *ph) {
 	const int WW = p->ww, PW = p->pw;
-	if (p->angle[i] == 0 || i >= WW)
+	/* the sequential machine has no such test: rtl/seqcordic.v:281-299 runs every state */
+	if (!p->sequential && (p->angle[i] == 0 || i >= WW))
 		return;
 	int64_t xv = *x, yv = *y;
 	uint64_t pv = *ph;
-	int64_t xs = xv >> (i + 1), ys = yv >> (i + 1);	/* >>> on signed regs */
+	const int sh = (i + 1 > 62) ? 62 : (i + 1);	/* >>> by WW or more leaves the sign */
+	int64_t xs = xv >> sh, ys = yv >> sh;	/* >>> on signed regs */
 	if ((pv >> (PW - 1)) & 1) {	/* negative phase */
 		*x = (int32_t)sx(xv + ys, WW);
 		*y = (int32_t)sx(yv - xs, WW);
@@ -303,7 +338,8 @@ void zo_rotate1(const zo_params *p, int32_t ix, int32_t iy, uint32_t phase,
 	int32_t x, y;
 	uint32_t ph;
 	zo_rotate_pre(p, ix, iy, phase, &x, &y, &ph);
-	for (int i = 0; i < p->nstages; i++)
+	const int n = zo_iterations(p);
+	for (int i = 0; i < n; i++)
 		zo_rotate_stage(p, i, &x, &y, &ph);
 	*ox = zo_round_out(p, x);
 	*oy = zo_round_out(p, y);
@@ -347,11 +383,12 @@ void zo_topolar_pre(const zo_params *p, int32_t ix, int32_t iy,
 /* rtl/topolar.v:217-243 */
 void zo_topolar_stage(const zo_params *p, int i, int32_t *x, int32_t *y, uint32_t *ph) {
 	const int WW = p->ww, PW = p->pw;
-	if (p->angle[i] == 0 || i >= WW)
+	if (!p->sequential && (p->angle[i] == 0 || i >= WW))	/* rtl/seqpolar.v runs every state */
 		return;
 	int64_t xv = *x, yv = *y;
 	uint64_t pv = *ph;
-	int64_t xs = xv >> (i + 1), ys = yv >> (i + 1);
+	const int sh = (i + 1 > 62) ? 62 : (i + 1);
+	int64_t xs = xv >> sh, ys = yv >> sh;
 	if (yv < 0) {		/* yv[WW-1]: below the axis */
 		*x = (int32_t)sx(xv - ys, WW);
 		*y = (int32_t)sx(yv + xs, WW);
@@ -369,7 +406,8 @@ void zo_topolar1(const zo_params *p, int32_t ix, int32_t iy,
 	int32_t x, y;
 	uint32_t ph;
 	zo_topolar_pre(p, ix, iy, &x, &y, &ph);
-	for (int i = 0; i < p->nstages; i++)
+	const int n = zo_iterations(p);
+	for (int i = 0; i < n; i++)
 		zo_topolar_stage(p, i, &x, &y, &ph);
 	*omag = zo_round_out(p, x);
 	*ophase = ph;

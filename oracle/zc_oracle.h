@@ -43,6 +43,7 @@ typedef struct zo_params {
 	int	pw;		/* phase width					*/
 	int	nstages;
 	int	vectoring;	/* 0: rtl/cordic.v (p2r), 1: rtl/topolar.v (r2p)	*/
+	int	sequential;	/* 1: rtl/seqcordic.v / rtl/seqpolar.v (one sample at a time) */
 	uint32_t angle[ZO_MAX_STAGES];
 	double	gain;		/* GAIN constant of rtl/X.h			*/
 	double	cordic_gain;	/* raw prod sqrt(1+2^-2(k+1))			*/
@@ -64,6 +65,18 @@ int	zo_calc_phase_bits(int ow);				/* :246-268 */
 int	zo_derive_p2r(int iw, int ow, int xtra_user, int pw, int nstages, zo_params *p);
 /* sw/main.cpp:312-328 + sw/topolar.cpp:67-75,428-446 */
 int	zo_derive_r2p(int iw, int ow, int xtra_user, int pw, int nstages, zo_params *p);
+/* -t sp2r / -t sr2p (sw/main.cpp:183-198,301-304,347-350): the same constants, emitted by sw/seqcordic.cpp /
+ * sw/seqpolar.cpp as a one-sample-at-a-time state machine.  What that machine computes differs from the
+ * pipelined core (established by executing rtl/seqcordic.v, rtl/seqpolar.v and generated variants under
+ * oracle/vsim.py): every iteration runs, zero angle or not (no pass-through test); seqcordic registers its
+ * outputs when state == NSTAGES-1, before the last two iterations land (rtl/seqcordic.v:319-324), so
+ * NSTAGES-2 iterations count; seqpolar's last_state is state >= NSTAGES+1 (rtl/seqpolar.v), NSTAGES
+ * iterations.  sr2p returns -2 when NSTAGES+1 is a power of two: the reference's state register
+ * (nextlg(NSTAGES+1) bits, sw/seqpolar.cpp:158-159) cannot reach NSTAGES+1 and o_done never rises. */
+int	zo_derive_sp2r(int iw, int ow, int xtra_user, int pw, int nstages, zo_params *p);
+int	zo_derive_sr2p(int iw, int ow, int xtra_user, int pw, int nstages, zo_params *p);
+int	zo_iterations(const zo_params *p);	/* stage updates that reach the output */
+int	zo_clocks_per_output(const zo_params *p);	/* CLOCKS_PER_OUTPUT of rtl/seq*.h; 1 for the pipelined cores */
 /* sw/main.cpp:358-379 (tbl) and :401-422 (qtr): resolves (pw, ow) from -i/-p/-o */
 int	zo_derive_tbl(int iw, int pw, int ow, int *pw_out, int *ow_out);
 int	zo_derive_qtr(int iw, int pw, int ow, int *pw_out, int *ow_out);

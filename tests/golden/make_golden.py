@@ -79,6 +79,22 @@ QTBL_MATRIX = [
 ]
 
 
+# (name, mode, iw, ow, xtra, pw, nstages) for the sequential cores (-t sp2r / -t sr2p)
+SEQ_MATRIX = [
+    ("sp2r_shipped", "sp2r", 13, 13, 2, None, None),          # sw/Makefile:142-144
+    ("sp2r_cfg0", "sp2r", 16, 16, 2, 16, None),
+    ("sp2r_cfg1", "sp2r", 18, 18, 2, 24, 20),
+    ("sp2r_12_16_x1", "sp2r", 12, 16, 1, None, None),
+    ("sp2r_manystages", "sp2r", 6, 6, 2, 10, 30),
+    ("sp2r_24_24", "sp2r", 24, 24, 2, None, None),
+    ("sr2p_shipped", "sr2p", 13, 13, 2, None, None),          # sw/Makefile:122-124
+    ("sr2p_cfg2", "sr2p", 16, 16, 2, None, None),
+    ("sr2p_8_8_x0", "sr2p", 8, 8, 0, None, None),
+    ("sr2p_10_10_p14_n20", "sr2p", 10, 10, 2, 14, 20),
+    ("sr2p_20_20", "sr2p", 20, 20, 2, None, None),
+]
+
+
 def run_gen(args, cwd):
     r = subprocess.run([GEN] + args, cwd=cwd, capture_output=True, text=True)
     return r.returncode, r.stdout + r.stderr
@@ -196,13 +212,34 @@ def main():
                 "ltbl": load_hex(os.path.join(d, "quadtbl_ltbl.hex")),
                 "qtbl": load_hex(os.path.join(d, "quadtbl_qtbl.hex")),
             }
+        seqs = {}
+        for name, mode, iw, ow, x, pw, n in SEQ_MATRIX:
+            d = os.path.join(td, name)
+            os.makedirs(d)
+            fname = "seqcordic.v" if mode == "sp2r" else "seqpolar.v"
+            args = ["-vca", "-t", mode, "-f", fname, "-c"]
+            if iw is not None: args += ["-i", str(iw)]
+            if ow is not None: args += ["-o", str(ow)]
+            if x is not None: args += ["-x", str(x)]
+            if pw is not None: args += ["-p", str(pw)]
+            if n is not None: args += ["-n", str(n)]
+            rc, log = run_gen(args, d)
+            assert rc == 0, (name, log)
+            hpath = os.path.join(d, fname[:-2] + ".h")
+            hdr = parse_header(hpath)
+            cpo = int(re.search(r"#define\s+CLOCKS_PER_OUTPUT\s+(\d+)", open(hpath).read()).group(1))
+            angles, _ = parse_verilog(os.path.join(d, fname))
+            seqs[name] = {"mode": mode, "args": {"iw": iw, "ow": ow, "xtra": x, "pw": pw, "nstages": n},
+                          "cmdline": " ".join(args), "header": hdr, "clocks_per_output": cpo, "angles": angles}
+    with open(os.path.join(HERE, "gen_seq.json"), "w") as f:
+        json.dump(seqs, f, indent=1, sort_keys=True)
     with open(os.path.join(HERE, "gen_quadtbl.json"), "w") as f:
         json.dump(qtbls, f, indent=1, sort_keys=True)
     with open(os.path.join(HERE, "gen_params.json"), "w") as f:
         json.dump(params, f, indent=1, sort_keys=True)
     with open(os.path.join(HERE, "gen_luts.json"), "w") as f:
         json.dump(luts, f, indent=1, sort_keys=True)
-    print("wrote", len(params), "cordic configs,", len(luts), "LUT configs and", len(qtbls), "quadtbl configs")
+    print("wrote", len(params), "cordic configs,", len(luts), "LUT configs,", len(qtbls), "quadtbl configs and", len(seqs), "sequential configs")
 
 
 if __name__ == "__main__":

@@ -13,6 +13,7 @@ box has no reference tree); the JSON is committed.
 import json
 import os
 import random
+import re
 import subprocess
 import sys
 import tempfile
@@ -54,6 +55,27 @@ QTBL = {
     "qtbl_o10_p14_x1": ("-o 10 -p 14 -x 1", None, dict(iw=0, ow=10, xtra=1, pw=14)),
     "qtbl_o20_p24": ("-o 20 -p 24", None, dict(iw=0, ow=20, xtra=2, pw=24)),
 }
+# the sequential cores (-t sp2r / -t sr2p; rtl/seqcordic.v, rtl/seqpolar.v), driven through their i_stb/o_done handshake
+SP2R = {
+    "sp2r_shipped": (None, "seqcordic.v", dict(iw=13, ow=13, xtra=2, pw=0, nstages=0)),
+    "sp2r_cfg0": ("-i 16 -o 16 -p 16 -x 2", None, dict(iw=16, ow=16, xtra=2, pw=16, nstages=0)),
+    "sp2r_cfg1": ("-i 18 -o 18 -p 24 -n 20 -x 2", None, dict(iw=18, ow=18, xtra=2, pw=24, nstages=20)),
+    "sp2r_12_16_x1": ("-i 12 -o 16 -x 1", None, dict(iw=12, ow=16, xtra=1, pw=0, nstages=0)),
+    "sp2r_manystages": ("-i 6 -o 6 -x 2 -p 10 -n 30", None, dict(iw=6, ow=6, xtra=2, pw=10, nstages=30)),
+    "sp2r_n17": ("-i 10 -o 10 -x 2 -n 17", None, dict(iw=10, ow=10, xtra=2, pw=0, nstages=17)),
+    "sp2r_8_8_x0": ("-i 8 -o 8 -x 0", None, dict(iw=8, ow=8, xtra=0, pw=0, nstages=0)),
+}
+SR2P = {
+    "sr2p_shipped": (None, "seqpolar.v", dict(iw=13, ow=13, xtra=2, pw=0, nstages=0)),
+    "sr2p_cfg2": ("-i 16 -o 16 -x 2", None, dict(iw=16, ow=16, xtra=2, pw=0, nstages=0)),
+    "sr2p_8_8_x0": ("-i 8 -o 8 -x 0", None, dict(iw=8, ow=8, xtra=0, pw=0, nstages=0)),
+    "sr2p_12_16_x1": ("-i 12 -o 16 -x 1", None, dict(iw=12, ow=16, xtra=1, pw=0, nstages=0)),
+    "sr2p_10_10_p14_n20": ("-i 10 -o 10 -x 2 -p 14 -n 20", None, dict(iw=10, ow=10, xtra=2, pw=14, nstages=20)),
+    "sr2p_n14": ("-i 10 -o 10 -x 2 -n 14", None, dict(iw=10, ow=10, xtra=2, pw=0, nstages=14)),
+    "sr2p_n15_never_done": ("-i 10 -o 10 -x 2 -n 15", None, dict(iw=10, ow=10, xtra=2, pw=0, nstages=15)),
+}
+NSEQ = 384
+
 LUT = {
     "tbl_shipped": (None, "sintable.v", dict(pw=17, ow=13)),
     "qtr_shipped": (None, "quarterwav.v", dict(pw=18, ow=24)),
@@ -67,7 +89,7 @@ def rtl_file(td, name, mode, gen_args, checked_in, fname):
         return os.path.join(REF_RTL, checked_in)
     d = os.path.join(td, name)
     os.makedirs(d)
-    args = [GEN, "-a"] + gen_args.split() + (["-t", mode] if "-t" not in gen_args else []) + ["-f", fname]
+    args = [GEN, "-a", "-c"] + gen_args.split() + (["-t", mode] if "-t" not in gen_args else []) + ["-f", fname]
     r = subprocess.run(args, cwd=d, capture_output=True, text=True)
     assert r.returncode == 0, (name, r.stderr)
     return os.path.join(d, fname)
@@ -134,6 +156,36 @@ def main():
             assert len(got) == len(vecs)
             out[name] = {"kind": mode, "derive": derive, "params": {"PW": PW, "OW": m.consts["OW"]},
                          "in": vecs, "out": [g[0] for g in got]}
+        # sequential cores last, so the vectors above keep their random draws
+        for table, mode, fname, ins, outs in ((SP2R, "sp2r", "seqcordic.v", ("i_xval", "i_yval", "i_phase"), ("o_xval", "o_yval")),
+                                              (SR2P, "sr2p", "seqpolar.v", ("i_xval", "i_yval"), ("o_mag", "o_phase"))):
+            for name, (gen_args, checked_in, derive) in table.items():
+                path = rtl_file(td, name, mode, gen_args, checked_in, fname)
+                hdr = open(path[:-2] + ".h").read()
+                cpo = int(re.search(r"#define\s+CLOCKS_PER_OUTPUT\s+(\d+)", hdr).group(1))
+                try:
+                    m = vsim.Module(path)
+                except (SyntaxError, KeyError) as e:
+                    # WW == OW+1: sw/seqcordic.cpp's "no rounding" branch tests an i_ce the sequential core does
+                    # not have; the emitted Verilog references an undeclared net and cannot be elaborated.
+                    out[name] = {"kind": mode, "derive": derive, "unusable_rtl": repr(e)}
+                    continue
+                IW, PW = m.consts["IW"], m.consts["PW"]
+                widths = [IW, IW, PW][:len(ins)]
+                vecs = [tuple(v) for v in ([(x, y, p) for x in corners(IW)[:4] for y in corners(IW)[:4]
+                                            for p in (0, (1 << PW) - 1, 1 << (PW - 1), (3 << (PW - 3)) - 1)]
+                                           if len(ins) == 3 else [(x, y) for x in corners(IW) for y in corners(IW)])]
+                while len(vecs) < NSEQ:
+                    vecs.append(tuple(rng.randrange(1 << w) for w in widths))
+                got = vsim.run_handshake(m, [dict(zip(ins, v)) for v in vecs], list(outs), cpo)
+                entry = {"kind": mode, "derive": derive, "clocks_per_output": cpo,
+                         "params": {k: m.consts[k] for k in ("IW", "OW", "WW", "PW")}}
+                if got is None:        # the core broke the TB's protocol (o_done never rose within CLOCKS_PER_OUTPUT)
+                    entry["never_done"] = True
+                else:
+                    entry["in"] = [list(v) for v in vecs]
+                    entry["out"] = [list(g) for g in got]
+                out[name] = entry
     with open(os.path.join(HERE, "rtl_vectors.json"), "w") as f:
         json.dump(out, f, separators=(",", ":"), sort_keys=True)
     print("wrote", sum(len(v.get("in", [])) for k, v in out.items() if not k.startswith("_")), "vectors for", len(out) - 1, "cores")

@@ -239,6 +239,54 @@ def test_random_configurations_differential():
             assert np.array_equal(host(mag), wm) and np.array_equal(host(ph).view(np.uint32), wp), (iw, ow, xtra, pw, ns, fl)
 
 
+SEQ_P2R = {
+    "shipped": dict(iw=13, ow=13, xtra=2),                       # rtl/seqcordic.v: NSTAGES 16, 14 iterations count
+    "cfg1": dict(iw=18, ow=18, xtra=2, pw=24, n=20),
+    "manystages": dict(iw=6, ow=6, xtra=2, pw=10, n=30),         # zero angles and shifts >= WW still rotate (x, y)
+    "n64": dict(iw=10, ow=10, xtra=2, pw=16, n=64),              # more iterations than the fast kernels unroll
+}
+
+
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED,
+                                   zc.F_FORCE_SEED | zc.F_SEED_PACKED])
+@pytest.mark.parametrize("name", sorted(SEQ_P2R))
+def test_sequential_rotation_full_phase_sweep(name, flags):
+    """zc_params.seq = 1 (rtl/seqcordic.v): every phase, constant and per-sample inputs, every kernel choice."""
+    kw = SEQ_P2R[name]
+    core = zc.Cordic(kw["iw"], kw["ow"], kw["xtra"], kw.get("pw", 0), kw.get("n", 0), sequential=True)
+    rc, op = zo.derive_sp2r(kw["iw"], kw["ow"], kw["xtra"], kw.get("pw", 0), kw.get("n", 0))
+    assert rc == 0 and core.params.seq == 1
+    n = 1 << core.PW
+    phase = np.arange(n, dtype=np.uint32)
+    x0 = (1 << (core.IW - 1)) - 1
+    assert np.array_equal(host(core.rotate_const(x0, 0, dev(phase), flags=flags)), zo.rotate_const(op, x0, 0, phase))
+    rng = np.random.default_rng(SEED + 77)
+    m = min(n, 1 << 20)
+    xy = rng.integers(-(1 << (core.IW - 1)), 1 << (core.IW - 1), size=(m, 2), dtype=np.int64).astype(np.int32)
+    assert np.array_equal(host(core.rotate(dev(xy), dev(phase[:m]), flags=flags)), zo.rotate(op, xy, phase[:m]))
+    # and it is not the pipelined core's function
+    rcp, pp = zo.derive_p2r(kw["iw"], kw["ow"], kw["xtra"], kw.get("pw", 0), kw.get("n", 0))
+    assert not np.array_equal(zo.rotate_const(pp, x0, 0, phase), zo.rotate_const(op, x0, 0, phase))
+
+
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_FORCE_GENERIC])
+@pytest.mark.parametrize("kw", [dict(iw=13, ow=13, xtra=2), dict(iw=16, ow=16, xtra=2), dict(iw=10, ow=10, xtra=2, pw=14, n=20),
+                                dict(iw=8, ow=8, xtra=0), dict(iw=10, ow=10, xtra=2, pw=12, n=40)])
+def test_sequential_vectoring(kw, flags):
+    """zc_params.seq = 1 (rtl/seqpolar.v): all NSTAGES iterations run, zero angles included."""
+    core = zc.Topolar(kw["iw"], kw["ow"], kw["xtra"], kw.get("pw", 0), kw.get("n", 0), sequential=True)
+    rc, op = zo.derive_sr2p(kw["iw"], kw["ow"], kw["xtra"], kw.get("pw", 0), kw.get("n", 0))
+    assert rc == 0
+    rng = np.random.default_rng(SEED + 78)
+    n = (1 << 20) + 3
+    lo, hi = -(1 << (core.IW - 1)), (1 << (core.IW - 1)) - 1
+    xy = rng.integers(lo, hi + 1, size=(n, 2), dtype=np.int64).astype(np.int32)
+    xy[:4] = [[lo, lo], [hi, hi], [0, 0], [lo, hi]]
+    mag, ph = core.topolar(dev(xy), flags=flags)
+    wm, wp = zo.topolar(op, xy)
+    assert np.array_equal(host(mag), wm) and np.array_equal(host(ph).view(np.uint32), wp)
+
+
 def test_rotate_narrow_core_wraps_like_the_rtl():
     """WW=5 is too narrow for the CORDIC gain: the RTL registers wrap.  The engine must detect
     that its non-wrapping fast path is not provably exact and reproduce the wrap."""

@@ -13,7 +13,8 @@ import pytest
 import cordic_b200 as zc
 from . import zo
 from .conftest import ROOT
-from .test_oracle_golden import LUTS, PARAMS, QTBLS, check_against_generator, check_quadtbl_against_generator
+from .test_oracle_golden import (LUTS, PARAMS, QTBLS, SEQS, check_against_generator, check_quadtbl_against_generator,
+                                 check_seq_against_generator)
 
 
 @pytest.mark.parametrize("name", sorted(PARAMS))
@@ -41,6 +42,51 @@ def test_derive_matches_oracle_bitwise(name):
     for f in ("gain", "cordic_gain", "qvar", "pvar_rad", "best_cnr"):
         assert getattr(p, f) == getattr(o, f), f       # same libm, same order of operations
     assert list(p.angle) == list(o.angle)
+
+
+@pytest.mark.parametrize("name", sorted(SEQS))
+def test_sequential_derive_matches_generator(name):
+    """zc_derive_sp2r / zc_derive_sr2p against `gencordic -t sp2r|sr2p` (header, angle table, CLOCKS_PER_OUTPUT)."""
+    g = SEQS[name]
+    a = g["args"]
+    p = (zc.derive_sp2r if g["mode"] == "sp2r" else zc.derive_sr2p)(a["iw"], a["ow"], a["xtra"], a["pw"], a["nstages"])
+    assert p.seq == 1 and p.mode == (zc.MODE_P2R if g["mode"] == "sp2r" else zc.MODE_R2P)
+    check_seq_against_generator(name, p, zc.lib().zc_clocks_per_output(ctypes.byref(p)))
+    assert p.header()["CLOCKS_PER_OUTPUT"] == g["clocks_per_output"]
+    want_iters = p.nstages - 2 if g["mode"] == "sp2r" else p.nstages
+    assert zc.lib().zc_iterations(ctypes.byref(p)) == want_iters
+
+
+def test_sequential_configurations_the_reference_cannot_run():
+    """sr2p with NSTAGES+1 a power of two never raises o_done in the reference's RTL (vector file:
+    sr2p_n15_never_done); sp2r takes its output two iterations early and needs three stages."""
+    for n in (15, 31):
+        with pytest.raises(zc.ZcError) as e:
+            zc.derive_sr2p(10, 10, 2, 0, n)
+        assert e.value.code == -2 and "o_done never rises" in str(e.value)      # ZC_ERANGE
+    assert zc.derive_sr2p(10, 10, 2, 0, 14).seq == 1
+    with pytest.raises(zc.ZcError):
+        zc.derive_sp2r(10, 10, 2, 0, 2)
+    pipe = zc.derive_p2r(13, 13, 2)
+    assert pipe.seq == 0 and zc.lib().zc_clocks_per_output(ctypes.byref(pipe)) == 1
+    assert zc.lib().zc_iterations(ctypes.byref(pipe)) == pipe.nstages
+
+
+@pytest.mark.parametrize("name", sorted(SEQS))
+def test_zcordic_gen_sequential_header_matches_generator(name, tmp_path):
+    g = SEQS[name]
+    a = g["args"]
+    fname = "seqcordic.v" if g["mode"] == "sp2r" else "seqpolar.v"
+    args = ["-ca", "-t", g["mode"], "-f", fname]
+    for flag, key in (("-i", "iw"), ("-o", "ow"), ("-x", "xtra"), ("-p", "pw"), ("-n", "nstages")):
+        if a[key] is not None:
+            args += [flag, str(a[key])]
+    r = _gen(args, str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    text = open(os.path.join(str(tmp_path), fname[:-2] + ".h")).read()
+    got = {m.group(2): m.group(3).strip() for m in re.finditer(r"const\s+(int|double|bool)\s+(\w+)\s*=\s*([^;]+);", text)}
+    assert got == g["header"]
+    assert int(re.search(r"#define\s+CLOCKS_PER_OUTPUT\s+(\d+)", text).group(1)) == g["clocks_per_output"]
 
 
 @pytest.mark.parametrize("name", sorted(LUTS))

@@ -60,6 +60,32 @@ def test_oracle_params_match_generator(name):
     check_against_generator(name, p, g["mode"])
 
 
+SEQS = json.load(open(os.path.join(ROOT, "tests", "golden", "gen_seq.json")))
+
+
+def check_seq_against_generator(name, p, clocks):
+    """`gencordic -t sp2r|sr2p`: header constants as printed, the cordic_angle table (the arctan sequence continued
+    to a power-of-two length, sw/cordiclib.cpp:146; only entries below NSTAGES ever reach an output) and
+    CLOCKS_PER_OUTPUT."""
+    g = SEQS[name]
+    mode = "p2r" if g["mode"] == "sp2r" else "r2p"
+    want = {k: v for k, v in g["header"].items() if k not in ("HAS_RESET", "HAS_AUX")}
+    assert header_strings(p, mode) == want, name
+    table = [int(p.angle[k]) for k in range(p.nstages)]
+    rc, longer = zo.derive_p2r(p.iw, p.ow, 2, p.pw, len(g["angles"]))
+    assert rc == 0 and g["angles"][:p.nstages] == table and g["angles"] == list(longer.angle)[:len(g["angles"])], name
+    assert clocks == g["clocks_per_output"], name
+
+
+@pytest.mark.parametrize("name", sorted(SEQS))
+def test_oracle_sequential_params_match_generator(name):
+    g = SEQS[name]
+    a = g["args"]
+    rc, p = (zo.derive_sp2r if g["mode"] == "sp2r" else zo.derive_sr2p)(a["iw"], a["ow"], a["xtra"], a["pw"], a["nstages"])
+    assert rc == 0 and p.sequential == 1
+    check_seq_against_generator(name, p, zo.clocks_per_output(p))
+
+
 @pytest.mark.parametrize("name", sorted(LUTS))
 def test_oracle_lut_matches_generator(name):
     g = LUTS[name]
@@ -203,6 +229,40 @@ def test_reference_quadtbl_tb_passes_over_oracle():
     assert r.returncode == 0, r.stdout
     assert "SUCCESS!!" in r.stdout and "MXERR: 1.565887" in r.stdout
     assert "MXVAL: 0x00000fff" in r.stdout and "MNVAL: 0xfffff000" in r.stdout
+
+
+def test_reference_seqcordic_tb_passes_over_oracle():
+    """bench/cpp/cordic_tb.cpp -DCLOCKS_PER_OUTPUT (the reference's seqcordic_tb, bench/cpp/Makefile:94-95),
+    unmodified, over the clock-by-clock model of rtl/seqcordic.v: the handshake asserts (:146-158) hold on
+    every one of the 2^20 samples and its thresholds pass.  The statistics differ from cordic_tb's because
+    the sequential core's output is taken after NSTAGES-2 iterations."""
+    r = _run_tb("seqcordic_tb_shipped")
+    assert r.returncode == 0, r.stdout
+    assert "SUCCESS!!" in r.stdout
+    assert "AVG Err: 0.544040" in r.stdout and "MAX Err: 1.730838" in r.stdout and "CNR    : 78.85 dB" in r.stdout
+
+
+def test_reference_seqpolar_tb_passes_over_oracle():
+    """bench/cpp/topolar_tb.cpp -DCLOCKS_PER_OUTPUT (seqpolar_tb, bench/cpp/Makefile:100-101), unmodified, over
+    the clock-by-clock model of rtl/seqpolar.v.  Same figures as topolar_tb: NSTAGES iterations, none of them
+    a zero angle in the shipped configuration."""
+    r = _run_tb("seqpolar_tb_shipped")
+    assert r.returncode == 0, r.stdout
+    assert "SUCCESS" in r.stdout and "Max phase     error: 6.40" in r.stdout
+    assert "Max magnitude error:  0.870814" in r.stdout
+
+
+def test_sequential_header_constants_equal_the_pipelined_ones():
+    """sw/seqcordic.cpp:455-498 / sw/seqpolar.cpp:393-415 print the same constant set as the pipelined emitters plus
+    CLOCKS_PER_OUTPUT (rtl/seqcordic.h:49 = 17, rtl/seqpolar.h:49 = 21)."""
+    for seq, pipe, cpo, kw in ((zo.derive_sp2r, zo.derive_p2r, 17, dict(iw=13, ow=13, xtra=2)),
+                               (zo.derive_sr2p, zo.derive_r2p, 21, dict(iw=13, ow=13, xtra=2))):
+        (rc1, a), (rc2, b) = seq(**kw), pipe(**kw)
+        assert rc1 == 0 and rc2 == 0 and a.sequential == 1 and b.sequential == 0
+        for f in ("iw", "ow", "nextra", "ww", "pw", "nstages", "gain", "qvar", "pvar_rad", "best_cnr"):
+            assert getattr(a, f) == getattr(b, f), f
+        assert list(a.angle) == list(b.angle)
+        assert zo.clocks_per_output(a) == cpo and zo.clocks_per_output(b) == 1
 
 
 def test_reference_topolar_tb_cfg2_is_out_of_its_tuned_range():

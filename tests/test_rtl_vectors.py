@@ -22,17 +22,42 @@ def mask(w):
 
 def test_vector_file_covers_every_core_family():
     kinds = {VEC[k]["kind"] for k in CORES}
-    assert kinds == {"p2r", "r2p", "qtbl", "tbl", "qtr"}
-    assert sum(len(VEC[k]["in"]) for k in CORES) >= 16000
+    assert kinds == {"p2r", "r2p", "qtbl", "tbl", "qtr", "sp2r", "sr2p"}
+    assert sum(len(VEC[k]["in"]) for k in CORES) >= 21000
     # the two no-rounding command lines yield Verilog no tool can load (generator bug, sw/basiccordic.cpp:419-420)
     assert {k for k, v in VEC.items() if "unparseable_rtl" in v} == {"p2r_8_8_x0", "p2r_negx"}
+    # sequential flavours of the same trouble: the no-rounding branch of sw/seqcordic.cpp tests an i_ce the core
+    # does not have, and a seqpolar whose NSTAGES+1 is a power of two never raises o_done
+    assert {k for k, v in VEC.items() if "unusable_rtl" in v} == {"sp2r_8_8_x0"}
+    assert {k for k, v in VEC.items() if isinstance(v, dict) and v.get("never_done")} == {"sr2p_n15_never_done"}
+
+
+def test_sequential_cores_the_reference_cannot_run_are_refused():
+    d = VEC["sr2p_n15_never_done"]["derive"]
+    rc, _ = zo.derive_sr2p(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"])
+    assert rc != 0
+    assert zo.derive_sr2p(10, 10, 2, 0, 31)[0] != 0 and zo.derive_sr2p(10, 10, 2, 0, 14)[0] == 0
+    assert zo.derive_sp2r(10, 10, 2, 0, 2)[0] != 0          # output taken two iterations early: needs >= 3
 
 
 @pytest.mark.parametrize("name", CORES)
 def test_oracle_reproduces_the_simulated_rtl(name):
     v = VEC[name]
     d, prm = v["derive"], v["params"]
-    if v["kind"] == "p2r":
+    if v["kind"] in ("sp2r", "sr2p"):
+        # rtl/seqcordic.v, rtl/seqpolar.v and generated variants, driven through i_stb/o_done as the TB does
+        rc, p = (zo.derive_sp2r if v["kind"] == "sp2r" else zo.derive_sr2p)(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"])
+        assert rc == 0 and p.sequential == 1 and (p.iw, p.ow, p.ww, p.pw) == (prm["IW"], prm["OW"], prm["WW"], prm["PW"])
+        assert zo.clocks_per_output(p) == v["clocks_per_output"]
+        inp = np.array(v["in"], dtype=np.int64)
+        want = np.array(v["out"], dtype=np.int64)
+        if v["kind"] == "sp2r":
+            got = zo.rotate(p, inp[:, :2].astype(np.int32), inp[:, 2].astype(np.uint32))
+            assert ((got.astype(np.int64) & mask(p.ow)) == want).all()
+        else:
+            mag, ph = zo.topolar(p, inp.astype(np.int32))
+            assert ((mag.astype(np.int64) & mask(p.ow)) == want[:, 0]).all() and (ph.astype(np.int64) == want[:, 1]).all()
+    elif v["kind"] == "p2r":
         rc, p = zo.derive_p2r(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"])
         assert rc == 0 and (p.iw, p.ow, p.ww, p.pw, p.nstages) == (prm["IW"], prm["OW"], prm["WW"], prm["PW"], prm["NSTAGES"])
         inp = np.array(v["in"], dtype=np.int64)
@@ -146,8 +171,10 @@ def test_cuda_path_reproduces_the_simulated_rtl(name):
         torch.cuda.synchronize()
         return t.cpu().numpy().astype(np.int64)
 
-    if v["kind"] == "p2r":
-        core = zc.Cordic(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"])
+    if v["kind"] in ("p2r", "sp2r"):
+        core = zc.Cordic(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"], sequential=(v["kind"] == "sp2r"))
+        if v["kind"] == "sp2r":
+            assert core.CLOCKS_PER_OUTPUT == v["clocks_per_output"]
         inp = np.array(v["in"], dtype=np.int64)
         want = np.array(v["out"], dtype=np.int64)
         for fl in (zc.F_DEFAULT, zc.F_FORCE_SEED, zc.F_FORCE_GENERIC):
@@ -159,8 +186,8 @@ def test_cuda_path_reproduces_the_simulated_rtl(name):
         for fl in (zc.F_DEFAULT, zc.F_FORCE_SEED | zc.F_SEED_WORDS, zc.F_FORCE_SEED | zc.F_SEED_PACKED):
             got = host(core.rotate_const(x0, y0, dev(inp[sel, 2].astype(np.uint32)), flags=fl))
             assert ((got & mask(core.OW)) == want[sel]).all(), fl
-    elif v["kind"] == "r2p":
-        core = zc.Topolar(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"])
+    elif v["kind"] in ("r2p", "sr2p"):
+        core = zc.Topolar(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"], sequential=(v["kind"] == "sr2p"))
         want = np.array(v["out"], dtype=np.int64)
         for fl in (zc.F_DEFAULT, zc.F_FORCE_GENERIC):
             mag, ph = core.topolar(dev(np.array(v["in"], dtype=np.int64).astype(np.int32)), flags=fl)

@@ -10,7 +10,7 @@ _lib = None
 
 class ZoParams(ctypes.Structure):
     _fields_ = [("iw", ctypes.c_int), ("ow", ctypes.c_int), ("nextra", ctypes.c_int), ("ww", ctypes.c_int),
-                ("pw", ctypes.c_int), ("nstages", ctypes.c_int), ("vectoring", ctypes.c_int),
+                ("pw", ctypes.c_int), ("nstages", ctypes.c_int), ("vectoring", ctypes.c_int), ("sequential", ctypes.c_int),
                 ("angle", ctypes.c_uint32 * 64), ("gain", ctypes.c_double), ("cordic_gain", ctypes.c_double),
                 ("qvar", ctypes.c_double), ("pvar_rad", ctypes.c_double), ("best_cnr", ctypes.c_double)]
 
@@ -30,6 +30,10 @@ def lib():
         P, vp, sz, i32, u32, ci = ctypes.POINTER(ZoParams), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_uint32, ctypes.c_int
         L.zo_derive_p2r.argtypes = [ci] * 5 + [P]
         L.zo_derive_r2p.argtypes = [ci] * 5 + [P]
+        L.zo_derive_sp2r.argtypes = [ci] * 5 + [P]
+        L.zo_derive_sr2p.argtypes = [ci] * 5 + [P]
+        L.zo_iterations.argtypes = [P]
+        L.zo_clocks_per_output.argtypes = [P]
         L.zo_derive_tbl.argtypes = [ci] * 3 + [ctypes.POINTER(ci)] * 2
         L.zo_derive_qtr.argtypes = [ci] * 3 + [ctypes.POINTER(ci)] * 2
         L.zo_rotate1.argtypes = [P, i32, i32, u32, ctypes.POINTER(i32), ctypes.POINTER(i32)]
@@ -65,6 +69,22 @@ def derive_r2p(iw=0, ow=0, xtra=2, pw=0, nstages=0):
     p = ZoParams()
     rc = lib().zo_derive_r2p(iw or 0, ow or 0, xtra, pw or 0, nstages or 0, ctypes.byref(p))
     return rc, p
+
+
+def derive_sp2r(iw=0, ow=0, xtra=2, pw=0, nstages=0):
+    p = ZoParams()
+    rc = lib().zo_derive_sp2r(iw or 0, ow or 0, xtra, pw or 0, nstages or 0, ctypes.byref(p))
+    return rc, p
+
+
+def derive_sr2p(iw=0, ow=0, xtra=2, pw=0, nstages=0):
+    p = ZoParams()
+    rc = lib().zo_derive_sr2p(iw or 0, ow or 0, xtra, pw or 0, nstages or 0, ctypes.byref(p))
+    return rc, p
+
+
+def clocks_per_output(p):
+    return lib().zo_clocks_per_output(ctypes.byref(p))
 
 
 def derive_lut(mode, iw=0, pw=0, ow=0):

@@ -14,13 +14,14 @@
  *    reference's own generator built from /root/reference/sw (oracle/_ref/gencordic) and against the checked-in
  *    rtl/ artefacts (tests/golden/gen_*.json);
  *  - the datapaths are pinned per sample against the reference's RTL TEXT EXECUTED: oracle/vsim.py simulates
- *    rtl/cordic.v, topolar.v, quadtbl.v, sintable.v, quarterwav.v as checked in and the Verilog the real generator
- *    prints for 17 further command lines, and every one of its 16,896 vectors (tests/golden/rtl_vectors.json) is
+ *    rtl/cordic.v, topolar.v, seqcordic.v, seqpolar.v, quadtbl.v, sintable.v, quarterwav.v as checked in and the
+ *    Verilog the real generator prints for 29 further command lines, and every one of its 21,504 vectors (tests/golden/rtl_vectors.json) is
  *    reproduced by this file (tests/test_rtl_vectors.py).  The reference itself holds no per-sample vectors (its
  *    tests are statistical, bench/cpp/cordic_tb.cpp:285-337, topolar_tb.cpp:303-315) and Verilator is not in this
  *    image, so "the reference run here" means: its generator run for real, its RTL run under our simulator;
  *  - the reference's own unmodified test benches compiled against oracle/shim/ and run over this oracle print
- *    SUCCESS with their own thresholds (oracle/_ref/cordic_tb_*, topolar_tb_*, quadtbl_tb_*).
+ *    SUCCESS with their own thresholds (oracle/_ref/cordic_tb_*, topolar_tb_*, quadtbl_tb_*, seqcordic_tb_*,
+ *    seqpolar_tb_*).
  *
  * All citations are relative to /root/reference.
  */

@@ -202,6 +202,7 @@ def main():
     ap.add_argument("--seed-mode", default="auto", choices=["auto", "words", "packed", "regs"])
     ap.add_argument("--nco-step", type=lambda v: int(v, 0), default=NCO_STEP)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-tail", action="store_true", help="topolar: every stage in its full form (A/B of the short late stages)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-exchange", action="store_true", help="skip the NCCL scatter/gather-inclusive figure (N>1)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -267,7 +268,7 @@ def main():
         elif kind == "nco":
             core.nco(X0, Y0, 0, args.nco_step, nper, n0=first, out=o_xy, flags=flags)
         elif kind == "topolar":
-            vcore.topolar(xy, mag=o_mag, phase=o_ph)
+            vcore.topolar(xy, mag=o_mag, phase=o_ph, flags=zc.F_NO_TAIL if args.no_tail else zc.F_DEFAULT)
         else:
             lut.lookup(phase, out=o_val)
 

@@ -25,6 +25,7 @@ F_FORCE_SEED = 4
 F_SEED_PACKED = 8
 F_SEED_REGS = 16
 F_SEED_WORDS = 32
+F_NO_TAIL = 64
 
 MODE_P2R, MODE_R2P = 0, 1
 
@@ -93,6 +94,7 @@ _SIGNATURES = {
     "zc_derive_sr2p": (ctypes.c_int, [ctypes.c_int] * 5 + [ctypes.POINTER(Params)]),
     "zc_iterations": (ctypes.c_int, [ctypes.POINTER(Params)]),
     "zc_clocks_per_output": (ctypes.c_int, [ctypes.POINTER(Params)]),
+    "zc_topolar_tail_stages": (ctypes.c_int, [ctypes.POINTER(Params)]),
     "zc_derive_tbl": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 2),
     "zc_derive_qtr": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 2),
     "zc_lut_build_sintable": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),

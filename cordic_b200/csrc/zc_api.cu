@@ -214,18 +214,52 @@ struct RotTable<SRC, 0> {
 	static void launch(int, int, cudaStream_t, const int4 *, const int4 *, int4 *, size_t, const CoreConsts &) {}
 };
 
+// NTAIL is quantised to even counts (at most 16) to bound the number of instantiations
+template <int N, int T>
+struct VecTail {
+	static void launch(int ntail, int grid, cudaStream_t st, const int4 *xin, int4 *mag, int4 *ph,
+			size_t groups, const CoreConsts &c) {
+		if constexpr (T > N) VecTail<N, T - 2>::launch(ntail, grid, st, xin, mag, ph, groups, c);
+		else if (ntail >= T) k_topolar<N, T><<<grid, 256, 0, st>>>(xin, mag, ph, groups, c);
+		else VecTail<N, T - 2>::launch(ntail, grid, st, xin, mag, ph, groups, c);
+	}
+};
+template <int N>
+struct VecTail<N, 0> {
+	static void launch(int, int grid, cudaStream_t st, const int4 *xin, int4 *mag, int4 *ph,
+			size_t groups, const CoreConsts &c) {
+		k_topolar<N, 0><<<grid, 256, 0, st>>>(xin, mag, ph, groups, c);
+	}
+};
+
 template <int N>
 struct VecTable {
-	static void launch(int neff, int grid, cudaStream_t st, const int4 *xin, int4 *mag, int4 *ph,
+	static void launch(int neff, int ntail, int grid, cudaStream_t st, const int4 *xin, int4 *mag, int4 *ph,
 			size_t groups, const CoreConsts &c) {
-		if (neff == N) k_topolar<N><<<grid, 256, 0, st>>>(xin, mag, ph, groups, c);
-		else VecTable<N - 1>::launch(neff, grid, st, xin, mag, ph, groups, c);
+		if (neff == N) VecTail<N, 16>::launch(ntail, grid, st, xin, mag, ph, groups, c);
+		else VecTable<N - 1>::launch(neff, ntail, grid, st, xin, mag, ph, groups, c);
 	}
 };
 template <>
 struct VecTable<0> {
-	static void launch(int, int, cudaStream_t, const int4 *, int4 *, int4 *, size_t, const CoreConsts &) {}
+	static void launch(int, int, int, cudaStream_t, const int4 *, int4 *, int4 *, size_t, const CoreConsts &) {}
 };
+
+// First vectoring stage from which y>>>(i+1) is provably 0 or -1 for every input, so that the short stage form
+// (zc_kernels.cuh: vec_step_tail) is the same function.  After the +-45 degree turn of rtl/topolar.v:122-152,
+// x_0 >= 0 and |y_0| <= x_0.  A stage (rtl/topolar.v:227-243, shift s = i+1) never decreases x, and
+// |y_i| <= x_i*2^-i + i follows by induction (x>>>s lies in (x/2^s - 1, x/2^s]).  With X an upper bound of x
+// over all stages (the one fast_path_is_exact() uses), -2^(i+1) <= y_i < 2^(i+1) holds once
+// X < 2^(2i+1) - i*2^i.  Only meaningful when the fast path is exact (no WW-bit wrap), hence never for WW = 32.
+static int vec_tail_start(const zc_params *p, int neff) {
+	if (p->ww >= 32 || !fast_path_is_exact(p)) return neff;
+	const double xb = (double)(1ull << (p->ww - 2)) * 1.1645 + 1.7 * (double)p->nstages + 2.0;
+	for (int i = 1; i < neff && i < 31; i++) {
+		const double lim = (double)(1ull << (2 * i + 1 > 62 ? 62 : 2 * i + 1)) - (double)i * (double)(1ull << i);
+		if (xb < lim) return i;
+	}
+	return neff;
+}
 
 template <int SRC>
 static int launch_rotate(const zc_params *p, CoreConsts &c, const uint32_t *phase, const int32_t *xy_in,
@@ -297,7 +331,8 @@ static int launch_topolar(const zc_params *p, const int32_t *xy_in, int32_t *mag
 	if (fast) {
 		const size_t groups = n / 4;
 		if (groups) {
-			VecTable<32>::launch(c.neff, grid_for(groups, di, 16), st, (const int4 *)xy_in, (int4 *)mag,
+			const int ntail = (flags & ZC_F_NO_TAIL) ? 0 : c.neff - vec_tail_start(p, c.neff);
+			VecTable<32>::launch(c.neff, ntail, grid_for(groups, di, 16), st, (const int4 *)xy_in, (int4 *)mag,
 				(int4 *)phase, groups, c);
 			if ((rc = post_launch("k_topolar")) != ZC_OK) return rc;
 			done = groups * 4;
@@ -665,6 +700,15 @@ int zc_derive_sr2p(int iw, int ow, int xtra_user, int pw, int nstages, zc_params
 int zc_iterations(const zc_params *p) {
 	if (!p) return set_error(ZC_EINVAL, "NULL zc_params");
 	return iterations(p);
+}
+int zc_topolar_tail_stages(const zc_params *p) {
+	if (!p) return set_error(ZC_EINVAL, "NULL zc_params");
+	if (p->mode != ZC_MODE_R2P) return 0;
+	const int neff = live_stages(p);
+	if (neff < 1 || neff > 32) return 0;
+	int t = neff - vec_tail_start(p, neff);
+	t &= ~1;
+	return t > 16 ? 16 : t;
 }
 int zc_clocks_per_output(const zc_params *p) {
 	if (!p) return set_error(ZC_EINVAL, "NULL zc_params");

@@ -92,20 +92,40 @@ __device__ __forceinline__ void vec_step(int &x, int &y, uint32_t &ph, const int
 	y = y1;
 }
 
+// ---- one micro-rotation, vectoring mode, once y has converged below the shift -----------------------------
+// The same assignments as vec_step<K>, for a stage where the host has PROVED -2^S <= y < 2^S for every input
+// (zc_api.cu: vec_tail_start; |y_i| <= x_i*2^-i + i by induction over rtl/topolar.v:227-243).  Then y>>>S is
+// 0 or -1, i.e. equal to the sign word md, and s*(y>>>S) == -md: x' = x - md.  Six issue slots instead of
+// eight: SHF, SHF, IMAD (-s straight from md), IMAD (y'), IADD3 (x'), IMAD (phase, -s * -angle).
+template <int K>
+__device__ __forceinline__ void vec_step_tail(int &x, int &y, uint32_t &ph, const int na) {
+	constexpr int S = (K + 1 > 31) ? 31 : (K + 1);
+	const int md = y >> 31;
+	const int ns = imad(md, -2, -1);
+	const int sx = x >> S;
+	y = imad(sx, ns, y);
+	x = x - md;
+	ph = (uint32_t)imad(ns, na, (int)ph);
+}
+
 template <int N, int K = 0>
 struct Unroll {
 	static __device__ __forceinline__ void rot(int &x, int &y, int &p, const CoreConsts &c) {
 		rot_step<K>(x, y, p, c.na[K]);
 		Unroll<N, K + 1>::rot(x, y, p, c);
 	}
+	// stages K0.. take the short form (K0 == N: none do)
+	template <int K0>
 	static __device__ __forceinline__ void vec(int &x, int &y, uint32_t &ph, const CoreConsts &c) {
-		vec_step<K>(x, y, ph, (int)c.pa[K]);
-		Unroll<N, K + 1>::vec(x, y, ph, c);
+		if (K >= K0) vec_step_tail<K>(x, y, ph, c.na[K]);
+		else vec_step<K>(x, y, ph, (int)c.pa[K]);
+		Unroll<N, K + 1>::template vec<K0>(x, y, ph, c);
 	}
 };
 template <int N>
 struct Unroll<N, N> {
 	static __device__ __forceinline__ void rot(int &, int &, int &, const CoreConsts &) {}
+	template <int K0>
 	static __device__ __forceinline__ void vec(int &, int &, uint32_t &, const CoreConsts &) {}
 };
 
@@ -195,7 +215,8 @@ k_rotate(const int4 *__restrict__ phase4, const int4 *__restrict__ xyin4,
 }
 
 // ---- vectoring mode, fast path ---------------------------------------------------------------
-template <int NEFF>
+// NTAIL: how many of the last stages run in the short form (vec_step_tail)
+template <int NEFF, int NTAIL>
 __global__ void __launch_bounds__(256)
 k_topolar(const int4 *__restrict__ xyin4, int4 *__restrict__ mag4, int4 *__restrict__ ph4,
 		size_t ngroups, const __grid_constant__ CoreConsts c) {
@@ -219,7 +240,7 @@ k_topolar(const int4 *__restrict__ xyin4, int4 *__restrict__ mag4, int4 *__restr
 			x = xn ? -((yn) ? sum : dif) : x;
 			y = xn ? ((yn) ? dif : -sum) : y;
 			uint32_t ph = c.e_phase[(xn & 2) | (yn & 1)];
-			Unroll<NEFF>::vec(x, y, ph, c);
+			Unroll<NEFF>::template vec<NEFF - NTAIL>(x, y, ph, c);
 			om[s] = round_out(x, c);
 			op[s] = (int)(ph >> c.pshift);
 		}

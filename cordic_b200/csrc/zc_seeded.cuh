@@ -39,6 +39,7 @@
 namespace zc {
 
 constexpr int SEED_MAX_NS = 16;
+constexpr size_t SEED_MAX_BLOCKS = 0xF0000000u;	// the table kernels count 128-sample blocks in 32 bits (2^38.9 samples)
 constexpr size_t SEED_SMEM_LIMIT = 227 * 1024 - 64;	// opt-in maximum per CTA minus the mbarrier slot
 
 struct SeedConsts {
@@ -137,6 +138,12 @@ __device__ __forceinline__ int round_out_fma(int v, const SeedConsts &s) {
 	return __float_as_int(r) - 0x4B400000;
 }
 
+__device__ __forceinline__ int4 lds128(uint32_t addr) {
+	int4 r;
+	asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+	return r;
+}
+
 // `nblocks` blocks of 128 consecutive samples; warp w of the grid takes blocks w, w+W, w+2W, ...
 // TDM: where the suffix directions come from.  TD_TABLE: one 32-bit word per stage from the TD table (no unpacking;
 // fastest when neighbouring lanes read neighbouring rows -- sweeps, slow NCOs -- but two 16-byte reads per sample
@@ -181,29 +188,37 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 	const int2 *const T2 = reinterpret_cast<const int2 *>(smem + s.off_t2);
 	const unsigned char *const TD = smem + s.off_td;
 	const uint32_t lane = threadIdx.x & 31u;
-	const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
-	size_t blk = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	uint32_t pin[4] = {0, 0, 0, 0};
-	if (SRC == SRC_CONST && blk < nblocks) {
+	// Shared-window address of each TD plane, kept opaque so that ptxas holds one uniform register per plane and reads
+	// [row + UR] instead of re-adding the plane stride per sample.
+	uint32_t tdbase[SEED_MAX_NS / 4];
 #pragma unroll
-		for (int k = 0; k < 4; k++) pin[k] = ldg_stream32(phase + (blk << 7) + (k << 5) + lane);
+	for (int j = 0; j < SEED_MAX_NS / 4; j++)
+		asm("mov.b32 %0, %1;" : "=r"(tdbase[j]) : "r"(sbase + s.off_td + (uint32_t)(j * s.td_plane)));
+	// 32-bit block counters (the host keeps nblocks + nwarps below 2^32): one IADD/ISETP per iteration, not pairs
+	const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+	const uint32_t nblk = (uint32_t)nblocks;
+	uint32_t blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	uint32_t pin[4] = {0, 0, 0, 0};
+	if (SRC == SRC_CONST && blk < nblk) {
+#pragma unroll
+		for (int k = 0; k < 4; k++) pin[k] = ldg_stream32(phase + ((size_t)blk << 7) + (k << 5) + lane);
 	}
-	for (; blk < nblocks; blk += nwarps) {
+	for (; blk < nblk; blk += nwarps) {
 		uint32_t ph[4];
 		if (SRC == SRC_NCO) {
-			const uint32_t base = c.nco_phase0 + (c.nco_n0 + (uint32_t)(blk << 7) + lane) * c.nco_step;
+			const uint32_t base = c.nco_phase0 + (c.nco_n0 + (blk << 7) + lane) * c.nco_step;
 #pragma unroll
 			for (int k = 0; k < 4; k++) ph[k] = (base + (uint32_t)(k << 5) * c.nco_step) >> c.pshift;
 		} else {
 #pragma unroll
 			for (int k = 0; k < 4; k++) ph[k] = pin[k];
-			const size_t nb = blk + nwarps;		// software prefetch of the next block
-			if (nb < nblocks) {
+			const uint32_t nb = blk + nwarps;		// software prefetch of the next block
+			if (nb < nblk) {
 #pragma unroll
-				for (int k = 0; k < 4; k++) pin[k] = ldg_stream32(phase + (nb << 7) + (k << 5) + lane);
+				for (int k = 0; k < 4; k++) pin[k] = ldg_stream32(phase + ((size_t)nb << 7) + (k << 5) + lane);
 			}
 		}
-		int2 *const dst = xyout + (blk << 7) + lane;
+		int2 *const dst = xyout + ((size_t)blk << 7) + lane;
 		int x[4], y[4];
 		uint32_t row16[4];
 #pragma unroll
@@ -221,11 +236,11 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 		for (int k = 0; k < 4; k++) {
 			if (NS > 0) {
 				if (TDM == TD_TABLE) {
-					const unsigned char *row = TD + (int)row16[k];
 					int d[SEED_MAX_NS];
 #pragma unroll
 					for (int j = 0; j < NS; j += 4) {
-						const int4 dv = *reinterpret_cast<const int4 *>(row + (j >> 2) * s.td_plane);
+						// one uniform shared-window base per plane, so every plane is read as [row + uniform register]
+						const int4 dv = lds128(row16[k] + tdbase[j >> 2]);
 						d[j] = dv.x;
 						if (j + 1 < SEED_MAX_NS) d[j + 1] = dv.y;
 						if (j + 2 < SEED_MAX_NS) d[j + 2] = dv.z;
@@ -590,9 +605,9 @@ k_rotate_dirs(const uint32_t *__restrict__ phase, const int2 *__restrict__ xyin,
 	const uint4 *const TP = reinterpret_cast<const uint4 *>(smem + s.off_t2);
 	const unsigned char *const TD = smem + s.off_td;
 	const uint32_t lane = threadIdx.x & 31u;
-	const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
-	for (size_t blk = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < nblocks; blk += nwarps) {
-		const size_t base = (blk << 7) + lane;
+	const uint32_t nwarps = gridDim.x * (blockDim.x >> 5), nblk = (uint32_t)nblocks;	// see k_rotate_seeded
+	for (uint32_t blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < nblk; blk += nwarps) {
+		const size_t base = ((size_t)blk << 7) + lane;
 		uint32_t ph[4];
 		int2 v[4];
 #pragma unroll
@@ -662,7 +677,7 @@ static int dirs_rotate_try(const zc_params *p, const CoreConsts &c, const uint32
 		int32_t *xy_out, size_t n, int device, int sms, cudaStream_t st, uint32_t flags, size_t &done, int &launches) {
 	done = 0; launches = 0;
 	const size_t nblocks = n >> 7;
-	if (nblocks == 0) return ZC_OK;
+	if (nblocks == 0 || nblocks > SEED_MAX_BLOCKS) return ZC_OK;
 	if (!(flags & ZC_F_FORCE_SEED) && n < ((size_t)1 << 20)) return ZC_OK;
 	if (c.neff < DIRS_M || p->pw < 12) return ZC_OK;
 	CoreConsts key = c;		// the plan does not depend on the input vector
@@ -704,7 +719,7 @@ static int seeded_rotate_try(const zc_params *p, const CoreConsts &c, const uint
 		size_t n, int device, int sms, cudaStream_t st, uint32_t flags, size_t &done, int &launches) {
 	done = 0; launches = 0;
 	const size_t nblocks = n >> 7;
-	if (nblocks == 0) return ZC_OK;
+	if (nblocks == 0 || nblocks > SEED_MAX_BLOCKS) return ZC_OK;
 	if (!(flags & ZC_F_FORCE_SEED) && n < ((size_t)1 << 20)) return ZC_OK;	// not worth the table load
 	if (c.neff < 6 || p->pw < 12) return ZC_OK;
 	// Which flavour of direction table.  The caller's flag wins.  For the NCO the host knows the pattern: byte rows

@@ -92,6 +92,8 @@ enum {
 	ZC_F_SEED_PACKED   = 8,	/* seeded kernel: suffix directions as one byte per stage (less shared-memory traffic: the better
 				   choice when neighbouring samples have scattered phases) */
 	ZC_F_SEED_REGS     = 16,	/* seeded kernel: run the suffix phase recursion in registers (no direction table) */
+	ZC_F_NO_TAIL       = 64,	/* topolar: every stage in its full form (by default the late stages, where y has provably
+				   converged below the shift, run a shorter instruction sequence with identical results) */
 	ZC_F_SEED_WORDS    = 32	/* seeded kernel: suffix directions as one word per stage (fastest for phase sweeps, slow NCOs).
 				   With none of the three: NCO picks by step size on the host; phase streams of >= 4 Mi
 				   samples are probed on the device (one extra tiny launch + one skipped launch per call). */
@@ -128,6 +130,10 @@ int zc_derive_sr2p(int iw, int ow, int xtra_user, int pw, int nstages, zc_params
  * rtl/seqcordic.h:49 / rtl/seqpolar.h:49 (1 for the pipelined cores). */
 int zc_iterations(const zc_params *p);
 int zc_clocks_per_output(const zc_params *p);
+/* Diagnostic: how many of the last vectoring stages zc_topolar runs in the short form (0 for rotation cores).  From
+ * stage i on the engine has proved -2^(i+1) <= y < 2^(i+1) for every input, so rtl/topolar.v:227-243's
+ * y>>>(i+1) is the sign word and x' = x - sign: identical results, six instructions instead of eight. */
+int zc_topolar_tail_stages(const zc_params *p);
 /* gencordic -t tbl [-i n] [-p pw] [-o ow]   sw/main.cpp:358-379 ; limit sw/sintable.cpp:62 */
 int zc_derive_tbl(int iw, int pw, int ow, int *pw_out, int *ow_out);
 /* gencordic -t qtr ...                       sw/main.cpp:401-422 ; limit sw/sintable.cpp:190 */

@@ -357,6 +357,33 @@ def test_topolar_exhaustive_8bit():
     assert np.array_equal(host(ph).view(np.uint32), wp)
 
 
+TAIL_CASES = [dict(iw=8, ow=8, xtra=2), dict(iw=10, ow=10, xtra=2), dict(iw=13, ow=13, xtra=2), dict(iw=16, ow=16, xtra=2),
+              dict(iw=12, ow=20, xtra=1), dict(iw=18, ow=18, xtra=2), dict(iw=22, ow=20, xtra=1),
+              dict(iw=16, ow=16, xtra=2, pw=30, n=28), dict(iw=16, ow=16, xtra=2, seq=True), dict(iw=8, ow=8, xtra=2, seq=True)]
+
+
+@pytest.mark.parametrize("kw", TAIL_CASES, ids=lambda k: "_".join("%s%s" % kv for kv in k.items()))
+def test_topolar_short_late_stages(kw):
+    """The kernel runs its last zc_topolar_tail_stages() stages in a six-instruction form that is only valid because
+    |y| has provably converged below the shift (tests/test_tail_stages.py checks the proof on the CPU).  Exhaustive
+    inputs for IW <= 10, otherwise corners, random, near-axis and near-diagonal vectors; default (short) and
+    ZC_F_NO_TAIL (every stage in full) must both equal the oracle."""
+    from .test_tail_stages import _inputs
+    seq = kw.get("seq", False)
+    core = zc.Topolar(kw["iw"], kw["ow"], kw["xtra"], kw.get("pw", 0), kw.get("n", 0), sequential=seq)
+    rc, op = (zo.derive_sr2p if seq else zo.derive_r2p)(kw["iw"], kw["ow"], kw["xtra"], kw.get("pw", 0), kw.get("n", 0))
+    assert rc == 0
+    tail = zc.lib().zc_topolar_tail_stages(ctypes.byref(core.params))
+    assert tail >= 2, "this configuration should exercise the short form"
+    xy = _inputs(core.IW, np.random.default_rng(SEED + 91))
+    xy = xy[:(len(xy) // 4) * 4]                        # whole groups of four: all of it through the fast kernel
+    wm, wp = zo.topolar(op, xy)
+    for fl in (zc.F_DEFAULT, zc.F_NO_TAIL):
+        mag, ph = core.topolar(dev(xy), flags=fl)
+        assert np.array_equal(host(mag), wm), fl
+        assert np.array_equal(host(ph).view(np.uint32), wp), fl
+
+
 @pytest.mark.parametrize("kind,pw,ow", [("tbl", 17, 13), ("tbl", 10, 8), ("tbl", 23, 16), ("tbl", 20, 30),
                                         ("qtr", 18, 24), ("qtr", 12, 12), ("qtr", 25, 16), ("qtr", 3, 6)])
 def test_lut_modes(kind, pw, ow):

@@ -158,10 +158,11 @@ def lib():
     """Loads libzcordic.so (building it with nvcc first if it is not there). Never falls back."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("ZCORDIC_LIB") or LIB_PATH     # ZCORDIC_LIB: an experiment build (cordic_b200/build.py --out)
+        if path == LIB_PATH and not os.path.exists(LIB_PATH):
             from . import build as _build
             _build.build()
-        L = ctypes.CDLL(LIB_PATH)
+        L = ctypes.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res

@@ -19,13 +19,14 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: experiment builds (kernel variants selected by -D macros) next to the product library."""
+    if out is None and not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", out or LIB] + list(defines) + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
@@ -35,8 +36,10 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libzcordic.so")
     if verbose:
         print(r.stdout + r.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=_out,
+                defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

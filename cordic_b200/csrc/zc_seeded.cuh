@@ -38,6 +38,12 @@
 
 namespace zc {
 
+// Suffix stages whose -d is formed as d ^ ~1 (LOP3, ALU pipe) instead of a negation (IMAD.MOV/IADD3): one stage in
+// four balances the heavy FMA pipe (81 % busy with every negation on it) against the ALU pipe (70 %); measured on
+// the cfg1 sweep, 20 steps: none 456-457, 0x22 463-464, 0x88 465-467, 0xAA 461, 0xFF 460 Gsamples/s.
+#ifndef ZC_XNEG_MASK
+#define ZC_XNEG_MASK 0x8888
+#endif
 constexpr int SEED_MAX_NS = 16;
 constexpr size_t SEED_MAX_BLOCKS = 0xF0000000u;	// the table kernels count 128-sample blocks in 32 bits (2^38.9 samples)
 constexpr size_t SEED_SMEM_LIMIT = 227 * 1024 - 64;	// opt-in maximum per CTA minus the mbarrier slot
@@ -81,13 +87,16 @@ __global__ void k_seed_fill_xy(const uint32_t *__restrict__ rep_phase /* left-ju
 template <int NS, int J = 0>
 struct Suffix {
 	// directions from the table: 2 shifts + 2 multiply-adds by +-1 + one negation per stage
+	// XN: apply ZC_XNEG_MASK (word-table flavour only; the byte flavour already spends a PRMT per stage on the ALU pipe)
+	template <bool XN>
 	static __device__ __forceinline__ void run(int &x, int &y, const int (&d)[SEED_MAX_NS], const SeedConsts &s) {
-		const int nd = -d[J];
+		// -d for d = +-1: as a negation (IMAD.MOV / IADD3, ptxas' choice) or as d ^ ~1 (LOP3, ALU pipe), per stage
+		const int nd = (XN && ((ZC_XNEG_MASK >> J) & 1)) ? (d[J] ^ -2) : -d[J];
 		const int sy = y >> s.sh[J], sx = x >> s.sh[J];
 		const int x1 = imad(sy, nd, x);
 		const int y1 = imad(sx, d[J], y);
 		x = x1; y = y1;
-		Suffix<NS, J + 1>::run(x, y, d, s);
+		Suffix<NS, J + 1>::template run<XN>(x, y, d, s);
 	}
 	// directions from the phase recursion in registers (rtl/cordic.v:263-279), as in k_rotate
 	static __device__ __forceinline__ void run_reg(int &x, int &y, int &p, const CoreConsts &c, const SeedConsts &s) {
@@ -103,6 +112,7 @@ struct Suffix {
 };
 template <int NS>
 struct Suffix<NS, NS> {
+	template <bool XN>
 	static __device__ __forceinline__ void run(int &, int &, const int (&)[SEED_MAX_NS], const SeedConsts &) {}
 	static __device__ __forceinline__ void run_reg(int &, int &, int &, const CoreConsts &, const SeedConsts &) {}
 };
@@ -246,7 +256,7 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 						if (j + 2 < SEED_MAX_NS) d[j + 2] = dv.z;
 						if (j + 3 < SEED_MAX_NS) d[j + 3] = dv.w;
 					}
-					Suffix<NS>::run(x[k], y[k], d, s);
+					Suffix<NS>::template run<true>(x[k], y[k], d, s);
 				} else if (TDM == TD_PACKED) {
 					const unsigned char *row = TD + (int)row16[k];	// 8-byte (NS<=8) or 16-byte rows
 					uint32_t w[4] = {0, 0, 0, 0};
@@ -261,7 +271,7 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 #pragma unroll
 					for (int j = 0; j < NS; j++)		// sign-extend byte j&3 of word j>>2
 						d[j] = sext_byte(w[j >> 2], j & 3);
-					Suffix<NS>::run(x[k], y[k], d, s);
+					Suffix<NS>::template run<false>(x[k], y[k], d, s);
 				} else {
 					int p = imad((int)row16[k], (int)s.mul_r, s.res_bias);	// residual phase, left-justified
 					Suffix<NS>::run_reg(x[k], y[k], p, c, s);

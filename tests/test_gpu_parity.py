@@ -627,3 +627,39 @@ def test_full_size_cfg2_round_trip():
     assert abs(float(m.mean()) - 16000 * 1.16443534550574 / 2 * vcore.GAIN * 0.5) < 2.0
     del phase, xy, mag, ph, err, m
     torch.cuda.empty_cache()
+
+
+def test_more_than_2_32_samples_in_one_call():
+    """One call over 2^32 + 2^24 + 133 samples (16 GiB of phases, 32 GiB of outputs): sample and byte offsets leave 32
+    bits, the table kernels' 32-bit block counters and the NCO's modulo-2^32 sample index must not.  The phase stream is
+    257 sweeps of the 2^24 phases plus a ragged tail; every sweep must equal the first, the first must equal the
+    reference RTL's outputs (tests/golden/rtl_sweeps.json), and the NCO that generates the same phases must reproduce
+    the stream's last 2^24 + 133 samples from a starting index beyond 2^32."""
+    from . import rtl_sweeps as rs
+    free, _ = torch.cuda.mem_get_info()
+    if free < (60 << 30):
+        pytest.skip("needs 60 GB of free device memory")
+    core, op = both_p2r(**P2R_CONFIGS["cfg1"])
+    period, tail = 1 << 24, 133
+    n = (1 << 32) + period + tail
+    phase = torch.empty(n, dtype=torch.int32, device="cuda")
+    sweep = torch.arange(period, dtype=torch.int32, device="cuda")
+    for k in range(0, n, period):
+        m = min(period, n - k)
+        phase[k:k + m] = sweep[:m]
+    out = core.rotate_const(131071, 0, phase)
+    torch.cuda.synchronize()
+    del phase
+    first = out[:period]
+    w = host(first)
+    rs.check("p2r_cfg1_sweep", rs.port_words([w[:, 0], w[:, 1]], [core.OW, core.OW]))
+    for k in range(period, n, period):
+        m = min(period, n - k)
+        assert torch.equal(out[k:k + m], first[:m]), k
+    # phase32 = i << 8 for sample i: step 0x100, and n0 carries the 64-bit sample index
+    n0 = (1 << 32) - 77
+    cnt = n - n0
+    nco = core.nco(131071, 0, 0, 0x100, cnt, n0=n0)
+    assert torch.equal(nco, out[n0:])
+    del out, nco, first
+    torch.cuda.empty_cache()

@@ -202,6 +202,7 @@ def main():
     ap.add_argument("--seed-mode", default="auto", choices=["auto", "words", "packed", "regs"])
     ap.add_argument("--nco-step", type=lambda v: int(v, 0), default=NCO_STEP)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-dp2a", action="store_true", help="seeded word table: IMAD + negation instead of IDP.2A (A/B)")
     ap.add_argument("--no-tail", action="store_true", help="topolar: every stage in its full form (A/B of the short late stages)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-exchange", action="store_true", help="skip the NCCL scatter/gather-inclusive figure (N>1)")
@@ -231,6 +232,8 @@ def main():
 
     flags = zc.F_NO_SEED if args.workload.endswith("_noseed") else zc.F_DEFAULT
     flags |= {"auto": 0, "words": zc.F_SEED_WORDS, "packed": zc.F_SEED_PACKED, "regs": zc.F_SEED_REGS}[args.seed_mode]
+    if args.no_dp2a:
+        flags |= zc.F_NO_DP2A
     core = zc.Cordic(**CFG1)
     # ---- synthetic inputs, resident in HBM before the timed region (4-12 GiB: far larger than L2)
     g = torch.Generator(device=devname); g.manual_seed(20261017 + rank)
@@ -264,7 +267,7 @@ def main():
         if kind == "rotate_const":
             core.rotate_const(X0, Y0, phase, out=o_xy, flags=flags)
         elif kind == "rotate":
-            core.rotate(xy, phase, out=o_xy)
+            core.rotate(xy, phase, out=o_xy, flags=flags & zc.F_NO_DP2A)
         elif kind == "nco":
             core.nco(X0, Y0, 0, args.nco_step, nper, n0=first, out=o_xy, flags=flags)
         elif kind == "topolar":

@@ -26,6 +26,7 @@ F_SEED_PACKED = 8
 F_SEED_REGS = 16
 F_SEED_WORDS = 32
 F_NO_TAIL = 64
+F_NO_DP2A = 128
 
 MODE_P2R, MODE_R2P = 0, 1
 

@@ -84,19 +84,41 @@ __global__ void k_seed_fill_xy(const uint32_t *__restrict__ rep_phase /* left-ju
 	t2[i] = make_int2(x, y);
 }
 
+enum { MA_NEG = 0, MA_XNEG = 1, MA_DP2A = 2 };
+__device__ __forceinline__ int dp2a_lo(int a, int b, int c) {
+	int r;
+	asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+	return r;
+}
+__device__ __forceinline__ int dp2a_hi(int a, int b, int c) {
+	int r;
+	asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+	return r;
+}
+
 template <int NS, int J = 0>
 struct Suffix {
 	// directions from the table: 2 shifts + 2 multiply-adds by +-1 + one negation per stage
-	// XN: apply ZC_XNEG_MASK (word-table flavour only; the byte flavour already spends a PRMT per stage on the ALU pipe)
-	template <bool XN>
+	// MA_NEG: -d by negation; MA_XNEG: as MA_NEG with ZC_XNEG_MASK (word-table flavour; the byte flavour already spends a
+	// PRMT per stage on the ALU pipe); MA_DP2A: d[J] is the word {0, d, 0, -d} (bytes 3..0) and both updates are IDP.2A:
+	//   dp2a.lo(sy, w, x) = x + sy.h0 * (-d) + sy.h1 * 0      dp2a.hi(sx, w, y) = y + sx.h0 * d + sx.h1 * 0
+	// which is the stage exactly as long as y>>sh and x>>sh fit 16 bits (the host checks sh >= WW-16): no negation at all,
+	// 4 issue slots per stage instead of 5 (tools/ubench3.cu: IDP.2A issues at IMAD's rate, on IMAD's pipe).
+	template <int MA>
 	static __device__ __forceinline__ void run(int &x, int &y, const int (&d)[SEED_MAX_NS], const SeedConsts &s) {
-		// -d for d = +-1: as a negation (IMAD.MOV / IADD3, ptxas' choice) or as d ^ ~1 (LOP3, ALU pipe), per stage
-		const int nd = (XN && ((ZC_XNEG_MASK >> J) & 1)) ? (d[J] ^ -2) : -d[J];
 		const int sy = y >> s.sh[J], sx = x >> s.sh[J];
-		const int x1 = imad(sy, nd, x);
-		const int y1 = imad(sx, d[J], y);
+		int x1, y1;
+		if (MA == MA_DP2A) {
+			x1 = dp2a_lo(sy, d[J], x);
+			y1 = dp2a_hi(sx, d[J], y);
+		} else {
+			// -d for d = +-1: as a negation (IMAD.MOV / IADD3, ptxas' choice) or as d ^ ~1 (LOP3, ALU pipe), per stage
+			const int nd = (MA == MA_XNEG && ((ZC_XNEG_MASK >> J) & 1)) ? (d[J] ^ -2) : -d[J];
+			x1 = imad(sy, nd, x);
+			y1 = imad(sx, d[J], y);
+		}
 		x = x1; y = y1;
-		Suffix<NS, J + 1>::template run<XN>(x, y, d, s);
+		Suffix<NS, J + 1>::template run<MA>(x, y, d, s);
 	}
 	// directions from the phase recursion in registers (rtl/cordic.v:263-279), as in k_rotate
 	static __device__ __forceinline__ void run_reg(int &x, int &y, int &p, const CoreConsts &c, const SeedConsts &s) {
@@ -112,14 +134,20 @@ struct Suffix {
 };
 template <int NS>
 struct Suffix<NS, NS> {
-	template <bool XN>
+	template <int MA>
 	static __device__ __forceinline__ void run(int &, int &, const int (&)[SEED_MAX_NS], const SeedConsts &) {}
 	static __device__ __forceinline__ void run_reg(int &, int &, int &, const CoreConsts &, const SeedConsts &) {}
 };
 
-enum { TD_TABLE = 0, TD_REGS = 1, TD_PACKED = 2 };
-// plan flavours: word TD + x/y table, byte TD + x/y table, byte TD + per-interval prefix directions (no x/y table)
-enum { FL_WORDS = 0, FL_PACKED = 1, FL_DIRS = 2 };
+enum { TD_TABLE = 0, TD_REGS = 1, TD_PACKED = 2, TD_TABLE_DP = 3 };
+// plan flavours: word TD + x/y table, byte TD + x/y table, byte TD + per-interval prefix directions (no x/y table), and
+// and the IDP.2A form of the first: word TD holding the multiplier words {0, d, 0, -d}.  (The byte flavours have no
+// IDP.2A form: storing the pair (-d, d) per stage and building the multiplier word with one PRMT saves the negation but
+// doubles the rows, and their scattered reads cost more than that: 320 vs 374 Gsamples/s for the constant-vector kernel
+// on random phases, 181 vs 195 for per-sample vectors -- measured, dropped.)
+enum { FL_WORDS = 0, FL_PACKED = 1, FL_DIRS = 2, FL_WORDS_DP = 3 };
+static inline bool fl_packed(int flavour) { return flavour == FL_PACKED || flavour == FL_DIRS; }
+static inline bool fl_dirs(int flavour) { return flavour == FL_DIRS; }
 constexpr int DIRS_M = 12;	// prefix depth of the FL_DIRS flavour (its kernel unrolls the byte indices)
 
 // Sign-extends byte `b` of w with one PRMT (selector nibble 8|b replicates that byte's sign bit;
@@ -168,7 +196,7 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 	extern __shared__ __align__(128) unsigned char smem[];
 	// Auto-selection: both table flavours are enqueued behind a probe kernel that writes which one suits the
 	// data; the other returns here, before touching shared memory.
-	if (gate != nullptr && *gate != TDM) return;
+	if (gate != nullptr && *gate != (TDM == TD_TABLE_DP ? TD_TABLE : TDM)) return;
 	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
 	const uint32_t mbar = sbase + s.total_bytes;		// 8-byte slot after the tables
 
@@ -208,44 +236,37 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 	const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
 	const uint32_t nblk = (uint32_t)nblocks;
 	uint32_t blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	uint32_t pin[4] = {0, 0, 0, 0};
-	if (SRC == SRC_CONST && blk < nblk) {
+	// One block of 128 samples.  `tin` holds the block's four phases per lane; they are folded first and then, when
+	// `reload` names a block, the registers are refilled at once with that block's phases (software prefetch, one block
+	// ahead; two register sets refilled two blocks ahead measured the same in short runs and 3 % slower under the power
+	// cap).
+	auto body = [&](uint32_t (&tin)[4], const uint32_t blk, const uint32_t reload) {
+		uint32_t tq[4], tu[4];
 #pragma unroll
-		for (int k = 0; k < 4; k++) pin[k] = ldg_stream32(phase + ((size_t)blk << 7) + (k << 5) + lane);
-	}
-	for (; blk < nblk; blk += nwarps) {
-		uint32_t ph[4];
-		if (SRC == SRC_NCO) {
-			const uint32_t base = c.nco_phase0 + (c.nco_n0 + (blk << 7) + lane) * c.nco_step;
+		for (int k = 0; k < 4; k++) {
+			// octant fold (rtl/cordic.v:131-188): phase + 45 degrees; bits above PW fall off the top
+			tq[k] = (uint32_t)imad((int)tin[k], (int)s.mul_q, 0x20000000);		// [q:2][u:PW-2][0...]
+			tu[k] = (uint32_t)imad((int)tin[k], (int)s.mul_u, (int)0x80000000u);	// [u:PW-2][0...]
+		}
+		if (SRC == SRC_CONST && reload < nblk) {
 #pragma unroll
-			for (int k = 0; k < 4; k++) ph[k] = (base + (uint32_t)(k << 5) * c.nco_step) >> c.pshift;
-		} else {
-#pragma unroll
-			for (int k = 0; k < 4; k++) ph[k] = pin[k];
-			const uint32_t nb = blk + nwarps;		// software prefetch of the next block
-			if (nb < nblk) {
-#pragma unroll
-				for (int k = 0; k < 4; k++) pin[k] = ldg_stream32(phase + ((size_t)nb << 7) + (k << 5) + lane);
-			}
+			for (int k = 0; k < 4; k++) tin[k] = ldg_stream32(phase + ((size_t)reload << 7) + (k << 5) + lane);
 		}
 		int2 *const dst = xyout + ((size_t)blk << 7) + lane;
 		int x[4], y[4];
 		uint32_t row16[4];
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
-			// octant fold (rtl/cordic.v:131-188): phase + 45 degrees; bits above PW fall off the top
-			const uint32_t tq = (uint32_t)imad((int)ph[k], (int)s.mul_q, 0x20000000);	// [q:2][u:PW-2][0...]
-			const uint32_t tu = (uint32_t)imad((int)ph[k], (int)s.mul_u, (int)0x80000000u);	// [u:PW-2][0...]
-			const uint32_t u16 = tu >> s.ush;				// 16 * reduced phase
-			const uint32_t rank = (T1[tu >> s.bsh] + u16) >> s.rsh;		// carries past the step, if any
-			const int2 xy = T2[__funnelshift_l(tq, rank, 2)];		// row rank*4 + quarter turn
+			const uint32_t u16 = tu[k] >> s.ush;				// 16 * reduced phase
+			const uint32_t rank = (T1[tu[k] >> s.bsh] + u16) >> s.rsh;	// carries past the step, if any
+			const int2 xy = T2[__funnelshift_l(tq[k], rank, 2)];		// row rank*4 + quarter turn
 			x[k] = xy.x; y[k] = xy.y;
 			row16[k] = u16 - (uint32_t)TS[rank];		// residual after M stages, as the byte offset of its TD row
 		}
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			if (NS > 0) {
-				if (TDM == TD_TABLE) {
+				if (TDM == TD_TABLE || TDM == TD_TABLE_DP) {
 					int d[SEED_MAX_NS];
 #pragma unroll
 					for (int j = 0; j < NS; j += 4) {
@@ -256,7 +277,7 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 						if (j + 2 < SEED_MAX_NS) d[j + 2] = dv.z;
 						if (j + 3 < SEED_MAX_NS) d[j + 3] = dv.w;
 					}
-					Suffix<NS>::template run<true>(x[k], y[k], d, s);
+					Suffix<NS>::template run<TDM == TD_TABLE_DP ? MA_DP2A : MA_XNEG>(x[k], y[k], d, s);
 				} else if (TDM == TD_PACKED) {
 					const unsigned char *row = TD + (int)row16[k];	// 8-byte (NS<=8) or 16-byte rows
 					uint32_t w[4] = {0, 0, 0, 0};
@@ -271,7 +292,7 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 #pragma unroll
 					for (int j = 0; j < NS; j++)		// sign-extend byte j&3 of word j>>2
 						d[j] = sext_byte(w[j >> 2], j & 3);
-					Suffix<NS>::template run<false>(x[k], y[k], d, s);
+					Suffix<NS>::template run<MA_NEG>(x[k], y[k], d, s);
 				} else {
 					int p = imad((int)row16[k], (int)s.mul_r, s.res_bias);	// residual phase, left-justified
 					Suffix<NS>::run_reg(x[k], y[k], p, c, s);
@@ -281,6 +302,22 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 			const int oy = RF ? round_out_fma(y[k], s) : round_out(y[k], c);
 			stg_stream64(dst + (k << 5), make_int2(ox, oy));
 		}
+	};
+	if (SRC == SRC_NCO) {
+		for (; blk < nblk; blk += nwarps) {
+			uint32_t tin[4];
+			const uint32_t base = c.nco_phase0 + (c.nco_n0 + (blk << 7) + lane) * c.nco_step;
+#pragma unroll
+			for (int k = 0; k < 4; k++) tin[k] = (base + (uint32_t)(k << 5) * c.nco_step) >> c.pshift;
+			body(tin, blk, nblk);
+		}
+	} else {
+		uint32_t pin[4] = {0, 0, 0, 0};
+		if (blk < nblk) {
+#pragma unroll
+			for (int k = 0; k < 4; k++) pin[k] = ldg_stream32(phase + ((size_t)blk << 7) + (k << 5) + lane);
+		}
+		for (; blk < nblk; blk += nwarps) body(pin, blk, blk + nwarps);
 	}
 }
 
@@ -338,7 +375,7 @@ static void seed_intervals(const zc_params *p, int M, std::vector<Interval> &iv)
 
 static bool seed_geometry(const zc_params *p, int neff, int M, int flavour, std::vector<Interval> &iv, SeedConsts &s,
 		int &NS, int64_t &rmin, int64_t &rmax) {
-	const bool packed = (flavour != FL_WORDS);
+	const bool packed = fl_packed(flavour);
 	NS = neff - M;
 	if (NS < 0 || NS > SEED_MAX_NS) return false;
 	seed_intervals(p, M, iv);
@@ -374,7 +411,7 @@ static bool seed_geometry(const zc_params *p, int neff, int M, int flavour, std:
 	s.rsh = lgw + lgrow;
 	s.lgrow = lgrow;
 	if (LB < 1 || s.ush < 0 || ((uint64_t)R << (lgw + lgrow)) >= ((uint64_t)1 << 31)) return false;
-	if (p->pw > 28) return false;		// residual reconstruction needs 2^(28-PW)
+	if (p->pw > 28 || 32 - p->pw - lgrow < 0) return false;	// residual reconstruction needs 2^(32-PW-lgrow)
 	s.mul_r = (uint32_t)1 << (32 - p->pw - lgrow);
 	s.res_bias = (int32_t)((uint64_t)rmin << (32 - p->pw));
 	{
@@ -401,7 +438,7 @@ struct DevFree { void operator()(void *ptr) const { if (ptr) cudaFree(ptr); } };
 // Builds (or finds) the plan for (p, constant vector, device).  Called with the device current.
 static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, int flavour, cudaStream_t st,
 		SeedPlan &out) {
-	const bool packed = (flavour != FL_WORDS);
+	const bool packed = fl_packed(flavour);
 	std::lock_guard<std::mutex> lk(g_seed_mu);
 	for (SeedPlan &pl : g_seed_cache) {
 		if (pl.device == device && pl.flavour == flavour && std::memcmp(&pl.p, p, sizeof(*p)) == 0 &&
@@ -419,11 +456,13 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, in
 	int64_t rmin = 0, rmax = 0;
 	bool ok = false;
 	const int neff = c.neff;
-	if (flavour == FL_DIRS) {
+	if (fl_dirs(flavour)) {
 		if (neff >= DIRS_M) ok = seed_geometry(p, neff, DIRS_M, flavour, iv, pl.s, pl.NS, rmin, rmax);
 	} else {
 		for (int M = (neff < 13 ? neff : 13); M >= 6 && !ok; M--)
 			ok = seed_geometry(p, neff, M, flavour, iv, pl.s, pl.NS, rmin, rmax);
+		// IDP.2A multiplies the low 16 bits of x>>sh, y>>sh: exact when |x|,|y| < 2^(WW-1) and sh >= WW-16
+		if (ok && flavour == FL_WORDS_DP && pl.s.M + 1 < p->ww - 16) ok = false;
 	}
 	if (ok) {
 		const SeedConsts &s = pl.s;
@@ -462,6 +501,8 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, in
 				const bool neg = ph < 0;
 				if (packed)
 					reinterpret_cast<unsigned char *>(td)[((size_t)(res - rmin) << s.lgrow) + j] = (unsigned char)(neg ? 0xff : 0x01);
+				else if (flavour == FL_WORDS_DP)	// bytes 3..0 = {0, d, 0, -d}
+					td[((size_t)(j >> 2) * nres + (size_t)(res - rmin)) * 4 + (j & 3)] = neg ? 0x00FF0001u : 0x000100FFu;
 				else
 					td[((size_t)(j >> 2) * nres + (size_t)(res - rmin)) * 4 + (j & 3)] = (uint32_t)(neg ? -1 : 1);
 				ph += neg ? (int64_t)p->angle[s.M + j] : -(int64_t)p->angle[s.M + j];
@@ -471,7 +512,7 @@ static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, in
 			cudaError_t e = cudaMalloc(&pl.dev, host.size() * 4);
 			if (e == cudaSuccess) pl.hold = std::shared_ptr<void>(pl.dev, DevFree());
 			if (e == cudaSuccess) e = cudaMemcpyAsync(pl.dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st);
-			if (e == cudaSuccess && flavour != FL_DIRS) {
+			if (e == cudaSuccess && !fl_dirs(flavour)) {
 				const uint32_t nthreads = 4u * (uint32_t)R;
 				k_seed_fill_xy<<<(nthreads + 255) / 256, 256, 0, st>>>(
 					reinterpret_cast<const uint32_t *>(pl.dev) + s.total_bytes / 4,
@@ -538,6 +579,7 @@ struct SeedTable {
 			typedef void (*kern_t)(const uint32_t *, int2 *, size_t, const CoreConsts, const SeedConsts, const uint4 *, const int *);
 			kern_t kern;
 			if (tdm == TD_TABLE) kern = rf ? k_rotate_seeded<NS, SRC, true, TD_TABLE> : k_rotate_seeded<NS, SRC, false, TD_TABLE>;
+			else if (tdm == TD_TABLE_DP) kern = rf ? k_rotate_seeded<NS, SRC, true, TD_TABLE_DP> : k_rotate_seeded<NS, SRC, false, TD_TABLE_DP>;
 			else if (tdm == TD_REGS) kern = rf ? k_rotate_seeded<NS, SRC, true, TD_REGS> : k_rotate_seeded<NS, SRC, false, TD_REGS>;
 			else kern = rf ? k_rotate_seeded<NS, SRC, true, TD_PACKED> : k_rotate_seeded<NS, SRC, false, TD_PACKED>;
 			cudaError_t e = ensure_dynamic_smem((const void *)kern, smem);
@@ -636,8 +678,12 @@ k_rotate_dirs(const uint32_t *__restrict__ phase, const int2 *__restrict__ xyin,
 			const uint32_t tu = (uint32_t)imad((int)ph[k], (int)s.mul_u, (int)0x80000000u);
 			const uint32_t ur = tu >> s.ush;
 			const uint32_t rank = (T1[tu >> s.bsh] + ur) >> s.rsh;
-			const uint4 tpv = TP[rank];
 			const unsigned char *row = TD + (int)(ur - (uint32_t)TS[rank]);
+			// rtl/cordic.v:85-86 (extend) and :131-188 (quarter turn selected by the octant)
+			const int ex = (v[k].x << c.in_shl) >> c.in_shr, ey = (v[k].y << c.in_shl) >> c.in_shr;
+			int x, y;
+			quarter_turn((int)(tq >> 30), ex, ey, x, y);
+			const uint4 tpv = TP[rank];
 			const uint32_t tp[4] = {tpv.x, tpv.y, tpv.z, tpv.w};
 			uint32_t td[4] = {0, 0, 0, 0};
 			if (NS > 0 && NS <= 8) {
@@ -647,10 +693,6 @@ k_rotate_dirs(const uint32_t *__restrict__ phase, const int2 *__restrict__ xyin,
 				const int4 w = *reinterpret_cast<const int4 *>(row);
 				td[0] = (uint32_t)w.x; td[1] = (uint32_t)w.y; td[2] = (uint32_t)w.z; td[3] = (uint32_t)w.w;
 			}
-			// rtl/cordic.v:85-86 (extend) and :131-188 (quarter turn selected by the octant)
-			const int ex = (v[k].x << c.in_shl) >> c.in_shr, ey = (v[k].y << c.in_shl) >> c.in_shr;
-			int x, y;
-			quarter_turn((int)(tq >> 30), ex, ey, x, y);
 			DirStages<NS>::run(x, y, tp, td);
 			const int ox = RF ? round_out_fma(x, s) : round_out(x, c);
 			const int oy = RF ? round_out_fma(y, s) : round_out(y, c);
@@ -748,9 +790,15 @@ static int seeded_rotate_try(const zc_params *p, const CoreConsts &c, const uint
 		}
 	}
 	SeedPlan pl, pl2;
-	int rc = seed_plan_get(p, c, device, tdm == TD_PACKED ? FL_PACKED : FL_WORDS, st, pl);
-	if (rc != ZC_OK) return rc;
-	if (!pl.usable) return ZC_OK;
+	int rc = ZC_OK;
+	if (tdm == TD_TABLE && !(flags & ZC_F_NO_DP2A)) {	// the word table as IDP.2A multipliers, when the shifts allow
+		if ((rc = seed_plan_get(p, c, device, FL_WORDS_DP, st, pl)) != ZC_OK) return rc;
+		if (pl.usable) tdm = TD_TABLE_DP;
+	}
+	if (tdm != TD_TABLE_DP) {
+		if ((rc = seed_plan_get(p, c, device, tdm == TD_PACKED ? FL_PACKED : FL_WORDS, st, pl)) != ZC_OK) return rc;
+		if (!pl.usable) return ZC_OK;
+	}
 	int *gate = nullptr;
 	if (probe) {
 		if ((rc = seed_plan_get(p, c, device, FL_PACKED, st, pl2)) != ZC_OK) return rc;

@@ -92,6 +92,7 @@ enum {
 	ZC_F_SEED_PACKED   = 8,	/* seeded kernel: suffix directions as one byte per stage (less shared-memory traffic: the better
 				   choice when neighbouring samples have scattered phases) */
 	ZC_F_SEED_REGS     = 16,	/* seeded kernel: run the suffix phase recursion in registers (no direction table) */
+	ZC_F_NO_DP2A       = 128,	/* seeded kernel, word table: multiply-adds as IMAD with an explicit negation instead of IDP.2A */
 	ZC_F_NO_TAIL       = 64,	/* topolar: every stage in its full form (by default the late stages, where y has provably
 				   converged below the shift, run a shorter instruction sequence with identical results) */
 	ZC_F_SEED_WORDS    = 32	/* seeded kernel: suffix directions as one word per stage (fastest for phase sweeps, slow NCOs).

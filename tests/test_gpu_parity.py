@@ -53,8 +53,9 @@ P2R_CONFIGS = {
 }
 
 
-@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED,
-                                   zc.F_FORCE_SEED | zc.F_SEED_PACKED, zc.F_FORCE_SEED | zc.F_SEED_REGS])
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED, zc.F_FORCE_SEED | zc.F_NO_DP2A,
+                                   zc.F_FORCE_SEED | zc.F_SEED_PACKED, zc.F_FORCE_SEED | zc.F_SEED_PACKED | zc.F_NO_DP2A,
+                                   zc.F_FORCE_SEED | zc.F_SEED_REGS])
 @pytest.mark.parametrize("name", sorted(P2R_CONFIGS))
 def test_rotate_const_full_phase_sweep(name, flags):
     """The sweep of bench/cpp/cordic_tb.cpp:127-178: every one of the 2^PW phases, full-scale
@@ -99,7 +100,7 @@ def test_rotate_const_auto_selected_table_flavour():
 
 
 @pytest.mark.parametrize("name", sorted(P2R_CONFIGS))
-@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED, zc.F_NO_SEED])
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED, zc.F_FORCE_SEED | zc.F_NO_DP2A, zc.F_NO_SEED])
 def test_rotate_per_sample_inputs(name, flags):
     core, op = both_p2r(**P2R_CONFIGS[name])
     rng = np.random.default_rng(SEED + 1)
@@ -207,13 +208,14 @@ def test_random_configurations_differential():
         lo, hi = -(1 << (iw - 1)), (1 << (iw - 1)) - 1
         x0, y0 = int(rng.integers(lo, hi + 1)), int(rng.integers(lo, hi + 1))
         want = zo.rotate_const(op, x0, y0, phase)
-        for fl in (zc.F_DEFAULT, zc.F_FORCE_SEED | zc.F_SEED_WORDS, zc.F_FORCE_SEED | zc.F_SEED_PACKED,
+        for fl in (zc.F_DEFAULT, zc.F_FORCE_SEED | zc.F_SEED_WORDS, zc.F_FORCE_SEED | zc.F_SEED_WORDS | zc.F_NO_DP2A,
+                   zc.F_FORCE_SEED | zc.F_SEED_PACKED, zc.F_FORCE_SEED | zc.F_SEED_PACKED | zc.F_NO_DP2A,
                    zc.F_FORCE_SEED | zc.F_SEED_REGS, zc.F_FORCE_GENERIC):
             got = host(core.rotate_const(x0, y0, dev(phase), flags=fl))
             assert np.array_equal(got, want), (iw, ow, xtra, pw, ns, fl)
         xy = rng.integers(lo, hi + 1, size=(n, 2), dtype=np.int64).astype(np.int32)
         wxy = zo.rotate(op, xy, phase)
-        for fl in (zc.F_DEFAULT, zc.F_FORCE_SEED):        # plain fast kernel / table-directed kernel
+        for fl in (zc.F_DEFAULT, zc.F_FORCE_SEED, zc.F_FORCE_SEED | zc.F_NO_DP2A):        # plain fast kernel / table-directed kernels
             assert np.array_equal(host(core.rotate(dev(xy), dev(phase), flags=fl)), wxy), (iw, ow, xtra, pw, ns, fl)
         got = host(core.nco(x0, y0, 12345, 0x9E3779B1, n, n0=7, flags=zc.F_FORCE_SEED))
         assert np.array_equal(got, zo.nco(op, x0, y0, 12345, 0x9E3779B1, n, n0=7)), (iw, ow, xtra, pw, ns)
@@ -438,7 +440,8 @@ def test_quadtbl_every_phase(name):
     assert np.array_equal(out, zo.quadtbl(q, port))
 
 
-@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_SEED_PACKED, zc.F_SEED_REGS, zc.F_SEED_WORDS])
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_SEED_PACKED, zc.F_SEED_REGS, zc.F_SEED_WORDS,
+                                   zc.F_SEED_WORDS | zc.F_NO_DP2A])
 def test_nco_stream(flags):
     core, op = both_p2r(**P2R_CONFIGS["cfg1"])
     n = (1 << 20) + 5

@@ -77,8 +77,8 @@ def _host(t):
     return t.cpu().numpy()
 
 
-P2R_FLAGS = [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED | zc.F_SEED_WORDS, zc.F_FORCE_SEED | zc.F_SEED_PACKED,
-             zc.F_FORCE_SEED | zc.F_SEED_REGS]
+P2R_FLAGS = [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED | zc.F_SEED_WORDS, zc.F_FORCE_SEED | zc.F_SEED_WORDS | zc.F_NO_DP2A,
+             zc.F_FORCE_SEED | zc.F_SEED_PACKED, zc.F_FORCE_SEED | zc.F_SEED_PACKED | zc.F_NO_DP2A, zc.F_FORCE_SEED | zc.F_SEED_REGS]
 
 
 @pytest.mark.gpu
@@ -92,7 +92,7 @@ def test_gpu_rotation_sweeps_equal_the_rtl(name, flags):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED])
+@pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED, zc.F_FORCE_SEED | zc.F_NO_DP2A])
 def test_gpu_rotation_per_sample_vectors_equal_the_rtl(flags):
     name = "p2r_cfg1_xy"
     d = rs.CASES[name]["derive"]

@@ -183,7 +183,8 @@ def test_cuda_path_reproduces_the_simulated_rtl(name):
         # constant-vector entry point (seeded kernels): group the vectors by their (x, y)
         x0, y0 = int(inp[0, 0]), int(inp[0, 1])
         sel = (inp[:, 0] == x0) & (inp[:, 1] == y0)
-        for fl in (zc.F_DEFAULT, zc.F_FORCE_SEED | zc.F_SEED_WORDS, zc.F_FORCE_SEED | zc.F_SEED_PACKED):
+        for fl in (zc.F_DEFAULT, zc.F_FORCE_SEED | zc.F_SEED_WORDS, zc.F_FORCE_SEED | zc.F_SEED_WORDS | zc.F_NO_DP2A,
+                   zc.F_FORCE_SEED | zc.F_SEED_PACKED):
             got = host(core.rotate_const(x0, y0, dev(inp[sel, 2].astype(np.uint32)), flags=fl))
             assert ((got & mask(core.OW)) == want[sel]).all(), fl
     elif v["kind"] in ("r2p", "sr2p"):

@@ -407,11 +407,11 @@ static int qt_device_tables(const zc_quadtbl *q, int device, cudaStream_t st, st
 			e.stamp = ++g_qt_clock; *out = e.dev; *nowrap = e.nowrap;
 			return ZC_OK;
 		}
-	std::vector<int32_t> host(3 * (size_t)n);
+	std::vector<int32_t> host(4 * (size_t)n);		// one row {c, l, q, 0} per index
 	bool safe = true;
 	for (int k = 0; k < n; k++) {
 		const int64_t cv = sext32(q->ctbl[k], q->cbits), lv = sext32(q->ltbl[k], q->lbits), qv = sext32(q->qtbl[k], q->qbits);
-		host[k] = (int32_t)cv; host[n + k] = (int32_t)lv; host[2 * n + k] = (int32_t)qv;
+		host[4 * k] = (int32_t)cv; host[4 * k + 1] = (int32_t)lv; host[4 * k + 2] = (int32_t)qv; host[4 * k + 3] = 0;
 		const int64_t al = (lv < 0 ? -lv : lv) + (qv < 0 ? -qv : qv) + 1, ac = (cv < 0 ? -cv : cv) + al + 1;
 		if (al >= ((int64_t)1 << (q->lbits - 1)) || ac >= ((int64_t)1 << (q->cbits - 1))) safe = false;
 	}
@@ -454,10 +454,14 @@ static int launch_quadtbl(const zc_quadtbl *q, const uint32_t *phase32, int32_t 
 	const size_t groups = vec ? n / 4 : 0, tail = n - groups * 4;
 	const bool wide = (q->qbits + q->dxbits > 31) || (q->lbits + q->dxbits > 31);
 	const int grid = grid_for(groups ? groups : tail, di, 8);
-	const size_t smem = 3 * (size_t)c.ntbl * 4;
+	const size_t smem = (size_t)c.ntbl * 16;		// up to 64 KB (LGTBL = 12): beyond the 48 KB default, opt in
 #define ZC_QT_LAUNCH(W, NW)                                                                           \
-	k_quadtbl<W, NW><<<grid, 256, smem, st>>>((const int4 *)phase32, (int4 *)out, tables, groups,        \
-		phase32 + groups * 4, out + groups * 4, (int)tail, c)
+	do {                                                                                              \
+		cudaError_t qe = ensure_dynamic_smem((const void *)k_quadtbl<W, NW>, smem);                    \
+		if (qe != cudaSuccess) return set_error(ZC_ECUDA, "k_quadtbl shared memory: %s", cudaGetErrorString(qe)); \
+		k_quadtbl<W, NW><<<grid, 256, smem, st>>>((const int4 *)phase32, (int4 *)out, tables, groups,   \
+			phase32 + groups * 4, out + groups * 4, (int)tail, c);                                   \
+	} while (0)
 	if (wide) { if (nowrap) ZC_QT_LAUNCH(true, true); else ZC_QT_LAUNCH(true, false); }
 	else      { if (nowrap) ZC_QT_LAUNCH(false, true); else ZC_QT_LAUNCH(false, false); }
 #undef ZC_QT_LAUNCH

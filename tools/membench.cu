@@ -27,6 +27,30 @@ template <int MODE> __global__ void __launch_bounds__(1024) k(const int4 *__rest
 		}
 		return;
 	}
+	if (MODE == 5) {	// per warp 128 samples: lane reads 2 x 8 B (two samples), writes 2 x 16 B
+		const int2 *ph = (const int2 *)in;
+		const size_t nblk = n16 / 32, nw = stride / 32; const unsigned lane = threadIdx.x & 31;
+		for (size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / 32; b < nblk; b += nw) {
+			int2 v[2];
+#pragma unroll
+			for (int k = 0; k < 2; k++) asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(v[k].x), "=r"(v[k].y) : "l"(ph + (b << 6) + (k << 5) + lane));
+#pragma unroll
+			for (int k = 0; k < 2; k++) st128(out + (b << 6) + (k << 5) + lane, make_int4(v[k].x, ~v[k].x, v[k].y, ~v[k].y));
+		}
+		return;
+	}
+	if (MODE == 6) {	// as the kernel's shape, 8 samples per lane per iteration (256-sample blocks)
+		const uint32_t *ph = (const uint32_t *)in; int2 *xy = (int2 *)out;
+		const size_t nblk = n16 / 64, nw = stride / 32; const unsigned lane = threadIdx.x & 31;
+		for (size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / 32; b < nblk; b += nw) {
+			uint32_t v[8];
+#pragma unroll
+			for (int k = 0; k < 8; k++) v[k] = ld32(ph + (b << 8) + (k << 5) + lane);
+#pragma unroll
+			for (int k = 0; k < 8; k++) st64(xy + (b << 8) + (k << 5) + lane, make_int2((int)v[k], (int)~v[k]));
+		}
+		return;
+	}
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
 		if (MODE == 0) st128(out + i, ld128(in + i));
 		if (MODE == 1) { const int4 v = ld128(in + i); st128(out + 2 * i, make_int4(v.x, ~v.x, v.y, ~v.y)); st128(out + 2 * i + 1, make_int4(v.z, ~v.z, v.w, ~v.w)); }
@@ -55,6 +79,8 @@ int main() {
 		run<0>("copy 16 B -> 16 B", in, out, n16, 32, grid, block);
 		run<1>("4 B in + 8 B out (v4)", in, out, n16, 48, grid, block);
 		run<4>("4 B in + 8 B out (kernel's shape)", in, out, n16, 48, grid, block);
+		run<5>("4 B in + 8 B out (8 B ld, 16 B st)", in, out, n16, 48, grid, block);
+		run<6>("4 B in + 8 B out (shape, 8/lane)", in, out, n16, 48, grid, block);
 		run<2>("8 B out only", in, out, n16, 32, grid, block);
 		run<3>("8 B in + 8 B out", in, out, n16, 64, grid, block);
 	}

@@ -441,7 +441,12 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": bytes_per, "kernel_ms": 1e3 * per_step_s,
-                         "launches_per_step": launches / args.steps},
+                         "launches_per_step": launches / args.steps,
+                         # `peak` is the 1:1 copy figure; a no-arithmetic kernel moving this workload's own mix (4 B read +
+                         # 8 B written per sample, same access shape and launch geometry) measured 6100 GB/s on this pool
+                         "traffic_mix_note": ("tools/membench2.cu moves 4 B in + 8 B out per sample with this kernel's access shape "
+                                              "at 6100 GB/s (profiles/membench_r1.txt): frac of that = %.3f" % (achieved / 6100.0))
+                         if args.workload == "rotate_cfg1" else None},
             "cpu_baseline": cpu, "e2e": e2e, "scatter_gather": exchange, "gpu_launches": int(launches), "clocks": clocks,
             "parity_spot_check": ok,
         }

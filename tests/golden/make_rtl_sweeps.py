@@ -5,7 +5,7 @@ tests/golden/rtl_vectors.json pins the oracle and the CUDA path on 21,504 indivi
 every phase of the three rotation cores the benchmark cares about (rtl/cordic.v as shipped: 2^20 phases; BASELINE
 configs[0]: 2^16; configs[1], the headline core: all 2^24), every phase of the shipped sintable / quarterwav / quadtbl
 cores, and millions of seeded inputs for per-sample rotation and for the vectoring cores (rtl/topolar.v as shipped and
-BASELINE configs[2]) -- 22.8 million samples, each clocked through the reference's Verilog text by oracle/vsim.py the
+BASELINE configs[2]) -- 23.3 million samples (the two shipped sequential cores included, through their handshake), each clocked through the reference's Verilog text by oracle/vsim.py the
 way bench/cpp/cordic_tb.cpp:127-200 drives the Verilated model.  Only digests are committed: per case the SHA-256 of
 the little-endian int32 output array plus one CRC-32 per block of 2^16 samples (so a mismatch can be localised).
 The inputs are regenerated from the seeds below by tests/rtl_sweeps.py on any machine; the reference tree is needed
@@ -42,10 +42,14 @@ def _module(path):
 
 
 def _work(job):
-    path, ins, outs, cols = job
+    path, ins, outs, cols, cpo = job
     m = _module(path)
     vecs = [dict(zip(ins, row)) for row in zip(*[c.tolist() for c in cols])]
-    got = vsim.run_pipeline(m, vecs, list(outs))
+    if cpo:        # sequential core: i_stb for one clock, CLOCKS_PER_OUTPUT ticks per sample (cordic_tb.cpp:146-158)
+        got = vsim.run_handshake(m, vecs, list(outs), cpo)
+        assert got is not None, "handshake broken"
+    else:
+        got = vsim.run_pipeline(m, vecs, list(outs))
     assert len(got) == len(vecs), (path, len(got), len(vecs))
     return np.array(got, dtype=np.uint64).astype(np.uint32)
 
@@ -72,11 +76,16 @@ def main():
             n = len(cols[0])
             m = _module(path)
             params = {k: m.consts[k] for k in ("IW", "OW", "WW", "PW", "NSTAGES") if k in m.consts}
-            jobs = [(path, c["ins"], c["outs"], tuple(col[i:i + BLOCK] for col in cols)) for i in range(0, n, BLOCK)]
+            cpo = 0
+            if c.get("seq"):
+                import re
+                cpo = int(re.search(r"#define\s+CLOCKS_PER_OUTPUT\s+(\d+)", open(path[:-2] + ".h").read()).group(1))
+            step = BLOCK // 16 if cpo else BLOCK      # smaller jobs for the slow handshake (digests stay per BLOCK)
+            jobs = [(path, c["ins"], c["outs"], tuple(col[i:i + step] for col in cols), cpo) for i in range(0, n, step)]
             parts = pool.map(_work, jobs, chunksize=1)
             words = np.concatenate(parts)                 # [n, len(outs)] raw (zero-extended) port words
             h = hashlib.sha256(words.astype("<u4").tobytes()).hexdigest()
-            crcs = [zlib.crc32(p.astype("<u4").tobytes()) for p in parts]
+            crcs = [zlib.crc32(words[i:i + BLOCK].astype("<u4").tobytes()) for i in range(0, n, BLOCK)]
             out[name] = {"n": n, "params": params, "sha256": h, "crc32": crcs,
                          "first": words[:4].tolist(), "last": words[-4:].tolist()}
             print(name, n, h[:16], flush=True)

@@ -1,4 +1,4 @@
-"""Large-volume parity against the reference's RTL, executed: tests/golden/rtl_sweeps.json holds digests of 22.8 million
+"""Large-volume parity against the reference's RTL, executed: tests/golden/rtl_sweeps.json holds digests of 23.3 million
 outputs that oracle/vsim.py obtained by clocking the reference's Verilog text (every phase of rtl/cordic.v as shipped, of
 BASELINE configs[0] and of configs[1] -- the headline core; every phase of the shipped table cores; millions of seeded
 inputs for per-sample rotation and for both vectoring cores).  CPU tier: the oracle reproduces every digest.  GPU tier:
@@ -18,9 +18,15 @@ def _missing(name):
     return name not in GOLD
 
 
+def _params_match(op, want):
+    """the localparams the simulated Verilog declares (the sequential cores have no NSTAGES) against the oracle's derivation"""
+    have = {"IW": op.iw, "OW": op.ow, "WW": op.ww, "PW": op.pw, "NSTAGES": op.nstages}
+    return all(have[k] == v for k, v in want.items())
+
+
 def test_every_case_has_digests():
     assert [n for n in rs.CASES if _missing(n)] == []
-    assert sum(GOLD[n]["n"] for n in rs.CASES) == 22_806_528
+    assert sum(GOLD[n]["n"] for n in rs.CASES) == 22_806_528 + 2 * (1 << 18)
 
 
 # ---------------------------------------------------------------------------------------------- CPU tier: the oracle
@@ -31,8 +37,8 @@ def test_oracle_reproduces_the_rtl(name):
     k = c["kind"]
     if k in ("p2r_const", "p2r_xy"):
         d = c["derive"]
-        rc, op = zo.derive_p2r(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"])
-        assert rc == 0 and {"IW": op.iw, "OW": op.ow, "WW": op.ww, "PW": op.pw, "NSTAGES": op.nstages} == GOLD[name]["params"]
+        rc, op = (zo.derive_sp2r if c.get("seq") else zo.derive_p2r)(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"])
+        assert rc == 0 and _params_match(op, GOLD[name]["params"])
         if k == "p2r_const":
             out = zo.rotate_const(op, c["x0"], c["y0"], cols[2])
         else:
@@ -40,8 +46,8 @@ def test_oracle_reproduces_the_rtl(name):
         rs.check(name, rs.port_words([out[:, 0], out[:, 1]], [op.ow, op.ow]))
     elif k == "r2p":
         d = c["derive"]
-        rc, op = zo.derive_r2p(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"])
-        assert rc == 0 and {"IW": op.iw, "OW": op.ow, "WW": op.ww, "PW": op.pw, "NSTAGES": op.nstages} == GOLD[name]["params"]
+        rc, op = (zo.derive_sr2p if c.get("seq") else zo.derive_r2p)(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"])
+        assert rc == 0 and _params_match(op, GOLD[name]["params"])
         mag, ph = zo.topolar(op, np.stack([cols[0], cols[1]], 1).astype(np.int32))
         rs.check(name, rs.port_words([mag, ph], [op.ow, op.pw]))
     elif k == "tbl":
@@ -86,7 +92,7 @@ P2R_FLAGS = [zc.F_DEFAULT, zc.F_NO_SEED, zc.F_FORCE_GENERIC, zc.F_FORCE_SEED | z
 @pytest.mark.parametrize("name", [n for n in NAMES if rs.CASES[n]["kind"] == "p2r_const"])
 def test_gpu_rotation_sweeps_equal_the_rtl(name, flags):
     c, d = rs.CASES[name], rs.CASES[name]["derive"]
-    core = zc.Cordic(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"])
+    core = zc.Cordic(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"], sequential=bool(c.get("seq")))
     out = _host(core.rotate_const(c["x0"], c["y0"], _dev(rs.case_inputs(name)[2]), flags=flags))
     rs.check(name, rs.port_words([out[:, 0], out[:, 1]], [core.OW, core.OW]))
 
@@ -107,7 +113,7 @@ def test_gpu_rotation_per_sample_vectors_equal_the_rtl(flags):
 @pytest.mark.parametrize("name", [n for n in NAMES if rs.CASES[n]["kind"] == "r2p"])
 def test_gpu_vectoring_equals_the_rtl(name, flags):
     d = rs.CASES[name]["derive"]
-    core = zc.Topolar(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"])
+    core = zc.Topolar(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"], sequential=bool(rs.CASES[name].get("seq")))
     x, y = rs.case_inputs(name)
     mag, ph = core.topolar(_dev(np.stack([x, y], 1).astype(np.int32)), flags=flags)
     rs.check(name, rs.port_words([_host(mag), _host(ph)], [core.OW, core.PW]))

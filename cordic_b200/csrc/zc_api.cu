@@ -365,8 +365,33 @@ static int launch_lut(int pw, int ow, const uint32_t *tbl, const uint32_t *phase
 	size_t done = 0;
 	if (aligned16(phase32) && aligned16(out) && n >= 4) {
 		const size_t groups = n / 4;
-		k_lut<QUARTER><<<grid_for(groups, di, 32), 256, 0, st>>>((const int4 *)phase32, (int4 *)out, tbl, groups, c);
-		if ((rc = post_launch("k_lut")) != ZC_OK) return rc;
+		// Large batches of a table that fits shared memory once compressed (int16 half-wave / u16[+u8] magnitudes) go
+		// through the kernel that keeps it there: indifferent to the phase pattern.  ZCORDIC_LUT_SMEM=0 keeps the L2 path.
+		const size_t nent = QUARTER ? ((size_t)1 << (pw - 2)) : ((size_t)1 << (pw - 1));
+		const bool hi8 = QUARTER && ow > 17;
+		const size_t smem = nent * (hi8 ? 3 : 2);
+		// ZCORDIC_LUT_SMEM=0: never; =2: always (A/B); default: a probe of the phases decides on the device -- neighbouring
+		// phases (a sweep) keep the L2 kernel, which then streams at the HBM copy peak; scattered ones take shared memory.
+		static const int smem_mode = std::getenv("ZCORDIC_LUT_SMEM") ? std::atoi(std::getenv("ZCORDIC_LUT_SMEM")) : 1;
+		const bool fits = n >= ((size_t)1 << 22) && smem <= 200 * 1024 && (QUARTER ? ow <= 25 : ow <= 16);
+		int *gate = nullptr;
+		if (smem_mode == 1 && fits) {
+			if ((rc = gate_slot(device, &gate)) != ZC_OK) return rc;
+			k_seed_probe<<<1, 256, 0, st>>>(phase32, n, 0, (int)(1u << (pw < 2 ? 30 : (32 - pw > 30 ? 30 : 32 - pw))), gate);
+			if ((rc = post_launch("k_seed_probe")) != ZC_OK) return rc;
+		}
+		if (smem_mode != 2 || !fits) {
+			k_lut<QUARTER><<<grid_for(groups, di, 32), 256, 0, st>>>((const int4 *)phase32, (int4 *)out, tbl, groups, c, gate);
+			if ((rc = post_launch("k_lut")) != ZC_OK) return rc;
+		}
+		if (smem_mode != 0 && fits) {
+			typedef void (*kern_t)(const int4 *, int4 *, const uint32_t *, size_t, const LutConsts, const int *);
+			kern_t kern = hi8 ? (kern_t)k_lut_smem<QUARTER, true> : (kern_t)k_lut_smem<QUARTER, false>;
+			cudaError_t e = ensure_dynamic_smem((const void *)kern, smem);
+			if (e != cudaSuccess) return set_error(ZC_ECUDA, "k_lut_smem shared memory: %s", cudaGetErrorString(e));
+			kern<<<di.sms, 1024, smem, st>>>((const int4 *)phase32, (int4 *)out, tbl, groups, c, gate);
+			if ((rc = post_launch("k_lut_smem")) != ZC_OK) return rc;
+		}
 		done = groups * 4;
 	}
 	if (done < n) {

@@ -336,6 +336,10 @@ struct LutConsts {
 	int32_t pw;
 };
 
+// which LUT kernel a probed batch goes to (zc_seeded.cuh: k_seed_probe writes TD_TABLE = 0 for neighbouring phases,
+// TD_PACKED = 2 for scattered ones)
+enum { LUT_GATE_L2 = 0, LUT_GATE_SMEM = 2 };
+
 template <bool QUARTER>
 __device__ __forceinline__ int lut_one(uint32_t phase32, const uint32_t *__restrict__ tbl, const LutConsts &c) {
 	const uint32_t ip = phase32 >> c.pshift;
@@ -353,7 +357,8 @@ __device__ __forceinline__ int lut_one(uint32_t phase32, const uint32_t *__restr
 template <bool QUARTER>
 __global__ void __launch_bounds__(256)
 k_lut(const int4 *__restrict__ phase4, int4 *__restrict__ out4, const uint32_t *__restrict__ tbl,
-		size_t ngroups, const __grid_constant__ LutConsts c) {
+		size_t ngroups, const __grid_constant__ LutConsts c, const int *__restrict__ gate) {
+	if (gate != nullptr && *gate != LUT_GATE_L2) return;	// a probe kernel chose the shared-memory kernel for this batch
 	const size_t stride = (size_t)gridDim.x * blockDim.x;
 	for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
 		const int4 pv = ldg_stream(phase4 + g);
@@ -363,6 +368,83 @@ k_lut(const int4 *__restrict__ phase4, int4 *__restrict__ out4, const uint32_t *
 		o.z = lut_one<QUARTER>((uint32_t)pv.z, tbl, c);
 		o.w = lut_one<QUARTER>((uint32_t)pv.w, tbl, c);
 		stg_stream(out4 + g, o);
+	}
+}
+
+// ---- LUT cores with the table resident in shared memory ---------------------------------------------------
+// k_lut gathers from a table that lives in L2 (512 KB for the shipped sintable): ideal for sweeps (1.00 / 0.97 of the
+// HBM copy peak), an L2 gather per sample for scattered phases (286 / 434 Gsamples/s).  Here every CTA first stages a lossless compressed copy of the
+// table in shared memory and then looks every sample up there, whatever the phase pattern:
+//   sintable   (rtl/sintable.v:71-75)   the second half-wave is the negated first one -- IF the table really is like that;
+//              the staging loop checks tbl[i + N/2] == -tbl[i] and 16-bit range entry by entry (the generator's tables
+//              pass: C truncation toward zero is odd-symmetric, sw/sintable.cpp:156-168), and stores N/2 int16;
+//   quarterwav (rtl/quarterwav.v:92-109) the words are magnitudes below 2^16 (u16) or 2^24 (u16 + u8, HI8).
+// The table is the caller's memory and may hold anything: when a check fails the CTA (every CTA reaches the same
+// verdict, they all read the whole table) serves its samples from global memory exactly as k_lut does.
+template <bool QUARTER, bool HI8>
+__global__ void __launch_bounds__(1024, 1)
+k_lut_smem(const int4 *__restrict__ phase4, int4 *__restrict__ out4, const uint32_t *__restrict__ tbl,
+		size_t ngroups, const __grid_constant__ LutConsts c, const int *__restrict__ gate) {
+	if (gate != nullptr && *gate != LUT_GATE_SMEM) return;
+	extern __shared__ __align__(16) unsigned char lsm[];
+	const uint32_t nent = QUARTER ? (1u << (c.pw - 2)) : (1u << (c.pw - 1));
+	unsigned short *const lo = reinterpret_cast<unsigned short *>(lsm);
+	unsigned char *const hi = lsm + 2 * (size_t)nent;
+	int ok = 1;
+	for (uint32_t i = threadIdx.x; i < nent; i += blockDim.x) {
+		if (!QUARTER) {
+			const int v = (int)(tbl[i] << c.osh) >> c.osh, w = (int)(tbl[i + nent] << c.osh) >> c.osh;
+			ok &= (w == -v) & (v >= -32768) & (v <= 32767);
+			lo[i] = (unsigned short)v;
+		} else {
+			const uint32_t v = tbl[i];
+			ok &= HI8 ? (v < (1u << 24)) : (v < (1u << 16));
+			lo[i] = (unsigned short)v;
+			if (HI8) hi[i] = (unsigned char)(v >> 16);
+		}
+	}
+	ok = __syncthreads_and(ok);
+	auto one = [&](uint32_t phase32) -> int {
+		const uint32_t ip = phase32 >> c.pshift;
+		if (!QUARTER) {
+			const int neg = -(int)(ip >> (c.pw - 1));			// -1 in the second half-wave
+			const int v = (short)lo[ip & (nent - 1u)];
+			return (v ^ neg) - neg;
+		} else {
+			const uint32_t fold = 0u - ((ip >> (c.pw - 2)) & 1u);
+			const uint32_t idx = (ip ^ fold) & c.lowmask;
+			const int neg = -(int)((ip >> (c.pw - 1)) & 1u);
+			const int v = (int)(HI8 ? ((uint32_t)lo[idx] | ((uint32_t)hi[idx] << 16)) : (uint32_t)lo[idx]);
+			return (((v ^ neg) - neg) << c.osh) >> c.osh;
+		}
+	};
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (ok) {
+		// four 16-byte loads in flight per thread: one CTA of 1024 threads per SM has to cover HBM's latency alone
+		for (; g + 3 * stride < ngroups; g += 4 * stride) {
+			int4 pv[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) pv[k] = ldg_stream(phase4 + g + k * stride);
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+				stg_stream(out4 + g + k * stride, make_int4(one((uint32_t)pv[k].x), one((uint32_t)pv[k].y),
+					one((uint32_t)pv[k].z), one((uint32_t)pv[k].w)));
+		}
+		for (; g < ngroups; g += stride) {
+			const int4 pv = ldg_stream(phase4 + g);
+			stg_stream(out4 + g, make_int4(one((uint32_t)pv.x), one((uint32_t)pv.y), one((uint32_t)pv.z), one((uint32_t)pv.w)));
+		}
+	} else {
+		for (; g < ngroups; g += stride) {
+			const int4 pv = ldg_stream(phase4 + g);
+			int4 o;
+			o.x = lut_one<QUARTER>((uint32_t)pv.x, tbl, c);
+			o.y = lut_one<QUARTER>((uint32_t)pv.y, tbl, c);
+			o.z = lut_one<QUARTER>((uint32_t)pv.z, tbl, c);
+			o.w = lut_one<QUARTER>((uint32_t)pv.w, tbl, c);
+			stg_stream(out4 + g, o);
+		}
 	}
 }
 

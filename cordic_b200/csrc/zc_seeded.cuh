@@ -325,7 +325,9 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 // 8 windows of 32 consecutive samples spread over the stream; a pair counts as local when the circular phase
 // difference is at most one LSB (a sweep or a slow NCO: word rows are conflict-free), and the word flavour is
 // chosen when at least 7 pairs in 8 are.  Scattered phases get the byte-packed flavour.
-__global__ void k_seed_probe(const uint32_t *__restrict__ phase, size_t n, int pshift, int *gate) {
+// `lim`: the largest circular difference that still counts as local (1 phase LSB for the CORDIC tables; one table entry,
+// in 32-bit phase units, for the LUT cores).
+__global__ void k_seed_probe(const uint32_t *__restrict__ phase, size_t n, int pshift, int lim, int *gate) {
 	const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31u;
 	size_t off = ((n / 8) * w) & ~(size_t)31;
 	if (off + 33 > n) off = 0;
@@ -333,7 +335,7 @@ __global__ void k_seed_probe(const uint32_t *__restrict__ phase, size_t n, int p
 	if (n >= 34) {
 		const uint32_t a = phase[off + l], b = phase[off + l + 1];
 		const int d = (int)((b - a) << pshift) >> pshift;
-		local = (d >= -1 && d <= 1);
+		local = (d >= -lim && d <= lim);
 	}
 	const int votes = __syncthreads_count(local);
 	if (threadIdx.x == 0) *gate = (votes * 8 >= (int)blockDim.x * 7) ? TD_TABLE : TD_PACKED;
@@ -806,7 +808,7 @@ static int seeded_rotate_try(const zc_params *p, const CoreConsts &c, const uint
 	}
 	if (probe) {
 		if ((rc = gate_slot(device, &gate)) != ZC_OK) return rc;
-		k_seed_probe<<<1, 256, 0, st>>>(phase, n, c.pshift, gate);
+		k_seed_probe<<<1, 256, 0, st>>>(phase, n, c.pshift, 1, gate);
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess) return set_error(ZC_ECUDA, "launch of k_seed_probe failed: %s", cudaGetErrorString(e));
 		launches++;

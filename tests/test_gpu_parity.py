@@ -639,6 +639,7 @@ def test_more_than_2_32_samples_in_one_call():
     reference RTL's outputs (tests/golden/rtl_sweeps.json), and the NCO that generates the same phases must reproduce
     the stream's last 2^24 + 133 samples from a starting index beyond 2^32."""
     from . import rtl_sweeps as rs
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
     if free < (60 << 30):
         pytest.skip("needs 60 GB of free device memory")
@@ -666,3 +667,39 @@ def test_more_than_2_32_samples_in_one_call():
     assert torch.equal(nco, out[n0:])
     del out, nco, first
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("kind,pw,ow", [("tbl", 17, 13), ("tbl", 10, 8), ("tbl", 16, 16), ("qtr", 18, 24), ("qtr", 18, 13),
+                                        ("qtr", 12, 12), ("tbl", 18, 13), ("qtr", 20, 26)])
+def test_lut_large_batches_any_phase_pattern(kind, pw, ow):
+    """Batches of 4 Mi samples and more take the kernel that keeps a compressed table in shared memory (when it fits:
+    the last two cases do not, or are too wide, and stay on the L2 path).  Random, swept and ragged."""
+    lut = (zc.SinTable if kind == "tbl" else zc.QuarterWav)(phase_bits=pw, ow=ow)
+    tbl = zo.sintable(pw, ow) if kind == "tbl" else zo.quarterwav(pw, ow)
+    ref = zo.lut_sin if kind == "tbl" else zo.lut_qwav
+    rng = np.random.default_rng(SEED + 17)
+    n = (1 << 22) + 4 * 1025 + 3
+    for words in (rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32),
+                  (np.arange(n, dtype=np.uint64) * 1021 & 0xFFFFFFFF).astype(np.uint32)):
+        got = host(lut.lookup(dev(words)))
+        assert np.array_equal(got, ref(pw, ow, tbl, words))
+
+
+@pytest.mark.parametrize("kind,pw,ow", [("tbl", 12, 13), ("tbl", 14, 16), ("qtr", 14, 24), ("qtr", 14, 16), ("qtr", 13, 30)])
+def test_lut_arbitrary_table_contents(kind, pw, ow):
+    """The table is caller memory (zc_lut_sin / zc_lut_qwav take a device pointer): words that are not a sine wave at all
+    -- no half-wave symmetry, magnitudes beyond what the compressed copy can hold -- must still be looked up exactly as
+    rtl/sintable.v:71-75 / rtl/quarterwav.v:92-109 would (the shared-memory kernel detects it and reads global memory)."""
+    rng = np.random.default_rng(SEED + 18)
+    nwords = 1 << (pw if kind == "tbl" else pw - 2)
+    tbl = rng.integers(0, 1 << ow, size=nwords, dtype=np.uint64).astype(np.uint32)
+    n = (1 << 22) + 8
+    words = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+    d_tbl, d_words = dev(tbl), dev(words)
+    out = torch.empty(n, dtype=torch.int32, device="cuda")
+    fn = zc.lib().zc_lut_sin if kind == "tbl" else zc.lib().zc_lut_qwav
+    rc = fn(pw, ow, ctypes.c_void_p(d_tbl.data_ptr()), ctypes.c_void_p(d_words.data_ptr()), ctypes.c_void_p(out.data_ptr()), n, 0, None)
+    assert rc == 0, zc.lib().zc_last_error()
+    torch.cuda.synchronize()
+    want = (zo.lut_sin if kind == "tbl" else zo.lut_qwav)(pw, ow, tbl, words)
+    assert np.array_equal(host(out), want)

@@ -1,0 +1,110 @@
+// zcordic_bench.cpp -- a C++ client of the C ABI (include/zcordic.h), no Python and no torch in the process: what a
+// maintainer of the reference would write first.  It derives a core from the generator's flags, fills a phase sweep
+// the way bench/cpp/cordic_tb.cpp:127-138 does, runs it through zc_rotate_const on the device and through
+// zc_rotate_const_host end to end, and prints Gsamples/s for both.  bench.py is the driver's contract; this is the
+// same measurement from the reference's own language.
+//   zcordic_bench [-i iw] [-o ow] [-p pw] [-n stages] [-x xtra] [-l lg2(samples)] [-s steps] [-d device]
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "zcordic.h"
+
+#define CK(call)                                                                                  \
+	do {                                                                                      \
+		cudaError_t e_ = (call);                                                          \
+		if (e_ != cudaSuccess) {                                                          \
+			std::fprintf(stderr, "%s: %s\n", #call, cudaGetErrorString(e_));         \
+			return 2;                                                                 \
+		}                                                                                 \
+	} while (0)
+#define ZC(call)                                                                                  \
+	do {                                                                                      \
+		int rc_ = (call);                                                                 \
+		if (rc_ != ZC_OK) {                                                               \
+			std::fprintf(stderr, "%s: %s (%s)\n", #call, zc_strerror(rc_), zc_last_error()); \
+			return 2;                                                                 \
+		}                                                                                 \
+	} while (0)
+
+int main(int argc, char **argv) {
+	int iw = 18, ow = 18, pw = 24, ns = 20, xtra = 2, lg = 28, steps = 20, device = 0;
+	for (int k = 1; k + 1 < argc; k += 2) {
+		const int v = std::atoi(argv[k + 1]);
+		if (!std::strcmp(argv[k], "-i")) iw = v;
+		else if (!std::strcmp(argv[k], "-o")) ow = v;
+		else if (!std::strcmp(argv[k], "-p")) pw = v;
+		else if (!std::strcmp(argv[k], "-n")) ns = v;
+		else if (!std::strcmp(argv[k], "-x")) xtra = v;
+		else if (!std::strcmp(argv[k], "-l")) lg = v;
+		else if (!std::strcmp(argv[k], "-s")) steps = v;
+		else if (!std::strcmp(argv[k], "-d")) device = v;
+		else { std::fprintf(stderr, "unknown option %s\n", argv[k]); return 1; }
+	}
+	if (zc_device_count() <= 0) {
+		std::fprintf(stderr, "no CUDA device: %s (libzcordic has no CPU path)\n", zc_last_error());
+		return 3;
+	}
+	zc_params p;
+	ZC(zc_derive_p2r(iw, ow, xtra, pw, ns, &p));		// sw/main.cpp:260-279
+	std::printf("core: IW=%d OW=%d WW=%d PW=%d NSTAGES=%d GAIN=%.12f\n", p.iw, p.ow, p.ww, p.pw, p.nstages, p.gain);
+	const size_t n = (size_t)1 << lg;
+	const int32_t x0 = (1 << (p.iw - 1)) - 1, y0 = 0;	// cordic_tb.cpp:68-69
+	CK(cudaSetDevice(device));
+
+	// host buffers (pinned) holding the sweep i -> i mod 2^PW, and the device copies
+	uint32_t *h_phase = static_cast<uint32_t *>(zc_host_alloc(n * 4));
+	int32_t *h_xy = static_cast<int32_t *>(zc_host_alloc(n * 8));
+	if (!h_phase || !h_xy) { std::fprintf(stderr, "zc_host_alloc: %s\n", zc_last_error()); return 2; }
+	const uint32_t mask = p.pw >= 32 ? 0xFFFFFFFFu : ((1u << p.pw) - 1u);
+	for (size_t i = 0; i < n; i++) h_phase[i] = (uint32_t)i & mask;
+	uint32_t *d_phase = nullptr;
+	int32_t *d_xy = nullptr;
+	CK(cudaMalloc(&d_phase, n * 4));
+	CK(cudaMalloc(&d_xy, n * 8));
+	CK(cudaMemcpy(d_phase, h_phase, n * 4, cudaMemcpyHostToDevice));
+	cudaStream_t st;
+	CK(cudaStreamCreate(&st));
+	cudaEvent_t e0, e1;
+	CK(cudaEventCreate(&e0));
+	CK(cudaEventCreate(&e1));
+
+	// device-resident
+	for (int w = 0; w < 3; w++) ZC(zc_rotate_const(&p, x0, y0, d_phase, d_xy, n, device, st));
+	CK(cudaStreamSynchronize(st));
+	const uint64_t l0 = zc_launch_count();
+	CK(cudaEventRecord(e0, st));
+	for (int s = 0; s < steps; s++) ZC(zc_rotate_const(&p, x0, y0, d_phase, d_xy, n, device, st));
+	CK(cudaEventRecord(e1, st));
+	CK(cudaEventSynchronize(e1));
+	float ms = 0;
+	CK(cudaEventElapsedTime(&ms, e0, e1));
+	std::printf("device buffers: %.1f Gsamples/s  (%zu samples x %d steps, %.3f ms per step, %llu kernel launches)\n",
+		(double)n * steps / (ms * 1e-3) / 1e9, n, steps, ms / steps, (unsigned long long)(zc_launch_count() - l0));
+
+	// end to end from host memory
+	ZC(zc_rotate_const_host(&p, x0, y0, h_phase, h_xy, n, device));
+	CK(cudaEventRecord(e0, st));
+	ZC(zc_rotate_const_host(&p, x0, y0, h_phase, h_xy, n, device));
+	CK(cudaEventRecord(e1, st));
+	CK(cudaEventSynchronize(e1));
+	CK(cudaEventElapsedTime(&ms, e0, e1));
+	std::printf("host buffers  : %.2f Gsamples/s  (H2D %zu MB + D2H %zu MB per call)\n", (double)n / (ms * 1e-3) / 1e9, n * 4 >> 20, n * 8 >> 20);
+
+	// the device path and the host path must agree, and phase 0 must give the test bench's first sample
+	std::vector<int32_t> head(16);
+	CK(cudaMemcpy(head.data(), d_xy, head.size() * 4, cudaMemcpyDeviceToHost));
+	if (std::memcmp(head.data(), h_xy, head.size() * 4) != 0) { std::fprintf(stderr, "device and host paths disagree\n"); return 4; }
+	std::printf("o_xval,o_yval at phase 0..3: (%d,%d) (%d,%d) (%d,%d) (%d,%d)\n", h_xy[0], h_xy[1], h_xy[2], h_xy[3], h_xy[4], h_xy[5], h_xy[6], h_xy[7]);
+
+	zc_host_free(h_phase);
+	zc_host_free(h_xy);
+	cudaFree(d_phase);
+	cudaFree(d_xy);
+	zc_trim(device);
+	return 0;
+}

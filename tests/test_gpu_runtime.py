@@ -1,6 +1,7 @@
 """GPU tier: the library's runtime behaviour around the kernels -- stream ordering (CUDA graph capture and
 replay), the caches (`zc_trim`, eviction under concurrent use) and repeated host pipelines.  Results stay
 bit-exact against the oracle throughout.  Marked ``gpu``."""
+import os
 import threading
 
 import numpy as np
@@ -8,6 +9,7 @@ import pytest
 
 import cordic_b200 as zc
 from . import zo
+from .conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -143,3 +145,15 @@ def test_concurrent_threads_with_plan_eviction():
     for t in threads:
         t.join()
     assert not errors, errors[:5]
+
+
+def test_cpp_client():
+    """The C++ client of the C ABI (cordic_b200/csrc/zcordic_bench.cpp): device and host paths agree, phase 0 gives the
+    test bench's first sample (x0 * gain, rounded: 131071 -> 76313 for the 24-bit / 20-stage core)."""
+    import subprocess
+    exe = os.path.join(ROOT, "cordic_b200", "zcordic_bench")
+    if not os.path.exists(exe):
+        pytest.skip("zcordic_bench not built")
+    r = subprocess.run([exe, "-l", "23", "-s", "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "(76313,0)" in r.stdout and "Gsamples/s" in r.stdout

@@ -263,3 +263,21 @@ def test_hex_roundtrip_and_reference_layout(tmp_path):
     if os.path.exists("/root/reference/rtl/sintable.hex"):
         assert open(path, "rb").read() == open("/root/reference/rtl/sintable.hex", "rb").read()
         assert np.array_equal(zc.hex_read("/root/reference/rtl/quarterwav.hex"), zc.build_quarterwav(18, 24))
+
+
+def test_cpp_client_builds_and_refuses_to_run_without_a_gpu():
+    """cordic_b200/zcordic_bench: a C++ program over the C ABI (no Python in the process).  Without a CUDA device it must
+    say so and exit 3 -- there is no CPU path to fall back to."""
+    import shutil
+    import subprocess
+    exe = os.path.join(ROOT, "cordic_b200", "zcordic_bench")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "cordic_b200", "vshim"), exe])
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present: covered by tests/test_gpu_runtime.py::test_cpp_client")
+    except ImportError:
+        pass
+    r = subprocess.run([exe, "-l", "10"], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU path" in r.stderr, (r.returncode, r.stderr)

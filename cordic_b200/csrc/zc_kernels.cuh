@@ -339,6 +339,10 @@ struct LutConsts {
 // which LUT kernel a probed batch goes to (zc_seeded.cuh: k_seed_probe writes TD_TABLE = 0 for neighbouring phases,
 // TD_PACKED = 2 for scattered ones)
 enum { LUT_GATE_L2 = 0, LUT_GATE_SMEM = 2 };
+#ifndef ZC_LUT_MLP
+#define ZC_LUT_MLP 2
+#endif
+constexpr int LUT_MLP = ZC_LUT_MLP;
 
 template <bool QUARTER>
 __device__ __forceinline__ int lut_one(uint32_t phase32, const uint32_t *__restrict__ tbl, const LutConsts &c) {
@@ -421,13 +425,13 @@ k_lut_smem(const int4 *__restrict__ phase4, int4 *__restrict__ out4, const uint3
 	const size_t stride = (size_t)gridDim.x * blockDim.x;
 	size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (ok) {
-		// four 16-byte loads in flight per thread: one CTA of 1024 threads per SM has to cover HBM's latency alone
-		for (; g + 3 * stride < ngroups; g += 4 * stride) {
-			int4 pv[4];
+		// LUT_MLP 16-byte loads in flight per thread: one CTA of 1024 threads per SM has to cover HBM's latency alone
+		for (; g + (LUT_MLP - 1) * stride < ngroups; g += LUT_MLP * stride) {
+			int4 pv[LUT_MLP];
 #pragma unroll
-			for (int k = 0; k < 4; k++) pv[k] = ldg_stream(phase4 + g + k * stride);
+			for (int k = 0; k < LUT_MLP; k++) pv[k] = ldg_stream(phase4 + g + k * stride);
 #pragma unroll
-			for (int k = 0; k < 4; k++)
+			for (int k = 0; k < LUT_MLP; k++)
 				stg_stream(out4 + g + k * stride, make_int4(one((uint32_t)pv[k].x), one((uint32_t)pv[k].y),
 					one((uint32_t)pv[k].z), one((uint32_t)pv[k].w)));
 		}

@@ -183,7 +183,11 @@ int zc_nco_rotate_ex(const zc_params *p, int32_t x0, int32_t y0, uint32_t phase0
 int zc_nco_mix(const zc_params *p, const int32_t *xy_in, uint32_t phase0, uint32_t step, uint64_t n0,
 		int32_t *xy_out, size_t n, int device, void *stream);
 /* rtl/sintable.v:71-75 / rtl/quarterwav.v:92-109.  phase32 is a 32-bit NCO word; the core
- * sees i_phase = phase32 >> (32-pw).  tbl_dev: the table of zc_lut_build_* in device memory. */
+ * sees i_phase = phase32 >> (32-pw).  tbl_dev: the table of zc_lut_build_* in device memory -- or any other words:
+ * the lookup is rtl/sintable.v's / rtl/quarterwav.v's whatever the contents.  (Batches of 4 Mi samples and more with
+ * scattered phases are served from a compressed copy of the table staged in shared memory when the table allows it --
+ * half-wave odd symmetry and 16-bit range for sintable, 16/24-bit magnitudes for quarterwav, checked on the device per
+ * call; same results either way.) */
 int zc_lut_sin(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int32_t *out,
 		size_t n, int device, void *stream);
 int zc_lut_qwav(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int32_t *out,

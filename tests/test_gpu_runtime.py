@@ -76,6 +76,30 @@ def test_topolar_and_rotate_xy_cuda_graph_replay():
     assert np.array_equal(ang.cpu().numpy().view(np.uint32), wang)
 
 
+def test_lut_cuda_graph_replay():
+    """A large LUT batch is probe + L2 kernel + shared-memory kernel behind a device-side gate: captured once, the graph
+    must take the right kernel on every replay -- a sweep (L2 kernel), then scattered phases (shared-memory kernel)."""
+    lut = zc.SinTable(phase_bits=17, ow=13)
+    tbl = zo.sintable(17, 13)
+    n = (1 << 22) + 12
+    rng = np.random.default_rng(SEED + 2)
+    words = torch.zeros(n, dtype=torch.int32, device="cuda")
+    out = torch.empty(n, dtype=torch.int32, device="cuda")
+    lut.lookup(words, out=out)                              # warm-up: table upload, gate ring, function attributes
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        lut.lookup(words, out=out)
+    for rnd in range(3):
+        w = (np.arange(n, dtype=np.uint64) * 4 & 0xFFFFFFFF).astype(np.uint32) if rnd == 1 else \
+            rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+        words.copy_(torch.from_numpy(w.view(np.int32)))
+        out.fill_(-1)
+        g.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), zo.lut_sin(17, 13, tbl, w)), rnd
+
+
 def test_trim_between_calls():
     """zc_trim drops tables and staging buffers; the next call rebuilds them and the results do not change."""
     core, op = both_p2r(**CFG1)

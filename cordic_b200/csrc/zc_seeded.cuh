@@ -660,19 +660,42 @@ k_rotate_dirs(const uint32_t *__restrict__ phase, const int2 *__restrict__ xyin,
 	const unsigned char *const TD = smem + s.off_td;
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t nwarps = gridDim.x * (blockDim.x >> 5), nblk = (uint32_t)nblocks;	// see k_rotate_seeded
-	for (uint32_t blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < nblk; blk += nwarps) {
+	// software prefetch of the next block's inputs (12 registers), as in k_rotate_seeded: the loads of block b+W are in
+	// flight while block b runs its 20 stages
+	uint32_t blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	uint32_t pph[4] = {0, 0, 0, 0};
+	int2 pv[4] = {make_int2(0, 0), make_int2(0, 0), make_int2(0, 0), make_int2(0, 0)};
+	if (blk < nblk) {
+		const size_t b0 = ((size_t)blk << 7) + lane;
+#pragma unroll
+		for (int k = 0; k < 4; k++) pv[k] = ldg_stream64(xyin + b0 + (k << 5));
+		if (SRC != SRC_MIX) {
+#pragma unroll
+			for (int k = 0; k < 4; k++) pph[k] = ldg_stream32(phase + b0 + (k << 5));
+		}
+	}
+	for (; blk < nblk; blk += nwarps) {
 		const size_t base = ((size_t)blk << 7) + lane;
 		uint32_t ph[4];
 		int2 v[4];
 #pragma unroll
-		for (int k = 0; k < 4; k++) v[k] = ldg_stream64(xyin + base + (k << 5));
+		for (int k = 0; k < 4; k++) v[k] = pv[k];
 		if (SRC == SRC_MIX) {
 			const uint32_t p0 = c.nco_phase0 + (c.nco_n0 + (uint32_t)base) * c.nco_step;
 #pragma unroll
 			for (int k = 0; k < 4; k++) ph[k] = (p0 + (uint32_t)(k << 5) * c.nco_step) >> c.pshift;
 		} else {
 #pragma unroll
-			for (int k = 0; k < 4; k++) ph[k] = ldg_stream32(phase + base + (k << 5));
+			for (int k = 0; k < 4; k++) ph[k] = pph[k];
+		}
+		if (blk + nwarps < nblk) {
+			const size_t nb = ((size_t)(blk + nwarps) << 7) + lane;
+#pragma unroll
+			for (int k = 0; k < 4; k++) pv[k] = ldg_stream64(xyin + nb + (k << 5));
+			if (SRC != SRC_MIX) {
+#pragma unroll
+				for (int k = 0; k < 4; k++) pph[k] = ldg_stream32(phase + nb + (k << 5));
+			}
 		}
 #pragma unroll
 		for (int k = 0; k < 4; k++) {

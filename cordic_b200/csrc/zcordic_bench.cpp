@@ -3,11 +3,15 @@
 // the way bench/cpp/cordic_tb.cpp:127-138 does, runs it through zc_rotate_const on the device and through
 // zc_rotate_const_host end to end, and prints Gsamples/s for both.  bench.py is the driver's contract; this is the
 // same measurement from the reference's own language.
-//   zcordic_bench [-i iw] [-o ow] [-p pw] [-n stages] [-x xtra] [-l lg2(samples)] [-s steps] [-d device]
+//   zcordic_bench [-i iw] [-o ow] [-p pw] [-n stages] [-x xtra] [-l lg2(samples)] [-s steps] [-d device] [-g gpus]
+// -g G: the sample stream is sharded over devices 0..G-1 as independent chunks, one host thread per device (no collective:
+// the path has no exchange step); the figure is all samples over the slowest device's time.
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -31,8 +35,38 @@
 		}                                                                                 \
 	} while (0)
 
+// One shard on one device: n samples starting at phase index `first`; returns ms for `steps` calls (0 on failure).
+static float shard(const zc_params *p, int device, size_t n, size_t first, int steps, std::atomic<int> *ready, int gpus) {
+	const int32_t x0 = (1 << (p->iw - 1)) - 1;
+	const uint32_t mask = p->pw >= 32 ? 0xFFFFFFFFu : ((1u << p->pw) - 1u);
+	if (cudaSetDevice(device) != cudaSuccess) return 0;
+	std::vector<uint32_t> h(n);
+	for (size_t i = 0; i < n; i++) h[i] = (uint32_t)(first + i) & mask;
+	uint32_t *d_phase = nullptr;
+	int32_t *d_xy = nullptr;
+	cudaStream_t st;
+	cudaEvent_t e0, e1;
+	if (cudaMalloc(&d_phase, n * 4) != cudaSuccess || cudaMalloc(&d_xy, n * 8) != cudaSuccess) return 0;
+	cudaMemcpy(d_phase, h.data(), n * 4, cudaMemcpyHostToDevice);
+	cudaStreamCreate(&st); cudaEventCreate(&e0); cudaEventCreate(&e1);
+	for (int w = 0; w < 3; w++)
+		if (zc_rotate_const(p, x0, 0, d_phase, d_xy, n, device, st) != ZC_OK) return 0;
+	cudaStreamSynchronize(st);
+	ready->fetch_add(1);
+	while (ready->load() < gpus) std::this_thread::yield();		// all devices start their timed region together
+	cudaEventRecord(e0, st);
+	for (int s = 0; s < steps; s++)
+		if (zc_rotate_const(p, x0, 0, d_phase, d_xy, n, device, st) != ZC_OK) return 0;
+	cudaEventRecord(e1, st);
+	cudaEventSynchronize(e1);
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	cudaFree(d_phase); cudaFree(d_xy);
+	return ms;
+}
+
 int main(int argc, char **argv) {
-	int iw = 18, ow = 18, pw = 24, ns = 20, xtra = 2, lg = 28, steps = 20, device = 0;
+	int iw = 18, ow = 18, pw = 24, ns = 20, xtra = 2, lg = 28, steps = 20, device = 0, gpus = 1;
 	for (int k = 1; k + 1 < argc; k += 2) {
 		const int v = std::atoi(argv[k + 1]);
 		if (!std::strcmp(argv[k], "-i")) iw = v;
@@ -43,6 +77,7 @@ int main(int argc, char **argv) {
 		else if (!std::strcmp(argv[k], "-l")) lg = v;
 		else if (!std::strcmp(argv[k], "-s")) steps = v;
 		else if (!std::strcmp(argv[k], "-d")) device = v;
+		else if (!std::strcmp(argv[k], "-g")) gpus = v;
 		else { std::fprintf(stderr, "unknown option %s\n", argv[k]); return 1; }
 	}
 	if (zc_device_count() <= 0) {
@@ -54,6 +89,23 @@ int main(int argc, char **argv) {
 	std::printf("core: IW=%d OW=%d WW=%d PW=%d NSTAGES=%d GAIN=%.12f\n", p.iw, p.ow, p.ww, p.pw, p.nstages, p.gain);
 	const size_t n = (size_t)1 << lg;
 	const int32_t x0 = (1 << (p.iw - 1)) - 1, y0 = 0;	// cordic_tb.cpp:68-69
+	if (gpus > 1) {		// independent shards of n samples each, one host thread per device
+		if (gpus > zc_device_count()) { std::fprintf(stderr, "-g %d but %d devices\n", gpus, zc_device_count()); return 1; }
+		std::vector<float> ms(gpus, 0.f);
+		std::vector<std::thread> th;
+		std::atomic<int> ready{0};
+		for (int g = 0; g < gpus; g++)
+			th.emplace_back([&, g] { ms[g] = shard(&p, g, n, (size_t)g * n, steps, &ready, gpus); });
+		for (auto &t : th) t.join();
+		float worst = 0;
+		for (int g = 0; g < gpus; g++) {
+			if (ms[g] <= 0) { std::fprintf(stderr, "device %d failed: %s\n", g, zc_last_error()); return 2; }
+			if (ms[g] > worst) worst = ms[g];
+		}
+		std::printf("%d GPUs, device buffers: %.1f Gsamples/s  (%zu samples per GPU x %d steps, slowest device %.3f ms per step)\n",
+			gpus, (double)n * gpus * steps / (worst * 1e-3) / 1e9, n, steps, worst / steps);
+		return 0;
+	}
 	CK(cudaSetDevice(device));
 
 	// host buffers (pinned) holding the sweep i -> i mod 2^PW, and the device copies

@@ -5,7 +5,7 @@ tests/golden/rtl_vectors.json pins the oracle and the CUDA path on 21,504 indivi
 every phase of the three rotation cores the benchmark cares about (rtl/cordic.v as shipped: 2^20 phases; BASELINE
 configs[0]: 2^16; configs[1], the headline core: all 2^24), every phase of the shipped sintable / quarterwav / quadtbl
 cores, and millions of seeded inputs for per-sample rotation and for the vectoring cores (rtl/topolar.v as shipped and
-BASELINE configs[2]) -- 23.3 million samples (the two shipped sequential cores included, through their handshake), each clocked through the reference's Verilog text by oracle/vsim.py the
+BASELINE configs[2]) -- 30.2 million samples (the two shipped sequential cores included, through their handshake), each clocked through the reference's Verilog text by oracle/vsim.py the
 way bench/cpp/cordic_tb.cpp:127-200 drives the Verilated model.  Only digests are committed: per case the SHA-256 of
 the little-endian int32 output array plus one CRC-32 per block of 2^16 samples (so a mismatch can be localised).
 The inputs are regenerated from the seeds below by tests/rtl_sweeps.py on any machine; the reference tree is needed

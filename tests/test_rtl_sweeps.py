@@ -1,4 +1,4 @@
-"""Large-volume parity against the reference's RTL, executed: tests/golden/rtl_sweeps.json holds digests of 23.3 million
+"""Large-volume parity against the reference's RTL, executed: tests/golden/rtl_sweeps.json holds digests of 30.2 million
 outputs that oracle/vsim.py obtained by clocking the reference's Verilog text (every phase of rtl/cordic.v as shipped, of
 BASELINE configs[0] and of configs[1] -- the headline core; every phase of the shipped table cores; millions of seeded
 inputs for per-sample rotation and for both vectoring cores).  CPU tier: the oracle reproduces every digest.  GPU tier:
@@ -26,7 +26,7 @@ def _params_match(op, want):
 
 def test_every_case_has_digests():
     assert [n for n in rs.CASES if _missing(n)] == []
-    assert sum(GOLD[n]["n"] for n in rs.CASES) == 22_806_528 + 2 * (1 << 18)
+    assert sum(GOLD[n]["n"] for n in rs.CASES) == sum(len(rs.case_inputs(n)[0]) for n in rs.CASES) and sum(GOLD[n]["n"] for n in rs.CASES) > 30_000_000
 
 
 # ---------------------------------------------------------------------------------------------- CPU tier: the oracle
@@ -44,7 +44,7 @@ def test_oracle_reproduces_the_rtl(name):
         else:
             out = zo.rotate(op, np.stack([cols[0], cols[1]], 1).astype(np.int32), cols[2])
         rs.check(name, rs.port_words([out[:, 0], out[:, 1]], [op.ow, op.ow]))
-    elif k == "r2p":
+    elif k in ("r2p", "r2p_all"):
         d = c["derive"]
         rc, op = (zo.derive_sr2p if c.get("seq") else zo.derive_r2p)(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"])
         assert rc == 0 and _params_match(op, GOLD[name]["params"])
@@ -110,7 +110,7 @@ def test_gpu_rotation_per_sample_vectors_equal_the_rtl(flags):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("flags", [zc.F_DEFAULT, zc.F_NO_TAIL, zc.F_FORCE_GENERIC])
-@pytest.mark.parametrize("name", [n for n in NAMES if rs.CASES[n]["kind"] == "r2p"])
+@pytest.mark.parametrize("name", [n for n in NAMES if rs.CASES[n]["kind"] in ("r2p", "r2p_all")])
 def test_gpu_vectoring_equals_the_rtl(name, flags):
     d = rs.CASES[name]["derive"]
     core = zc.Topolar(d["iw"], d["ow"], d["xtra"], d["pw"], d["nstages"], sequential=bool(rs.CASES[name].get("seq")))

@@ -434,11 +434,27 @@ static int qt_device_tables(const zc_quadtbl *q, int device, cudaStream_t st, st
 		}
 	std::vector<int32_t> host(4 * (size_t)n);		// one row {c, l, q, 0} per index
 	bool safe = true;
+	// Can the LBITS-bit lsum or the CBITS-bit r_value register wrap for SOME phase?  Tables of up to 2^24 phases are
+	// simply walked: every (entry, dx) pair through the exact arithmetic of rtl/quadtbl.v:196-260 (a peak entry has
+	// |c| at full scale, so the triangle inequality alone would condemn every real table); larger ones get the bound.
+	const int dxs = q->dxbits - 1;
+	const bool walk = (q->lgtbl + dxs) <= 24;
+	const int rbits = q->cbits < q->ww ? q->cbits : q->ww;		// r must also fit OW+XTRA bits for the rounding not to wrap
+	const int64_t llim = (int64_t)1 << (q->lbits - 1), rlim = (int64_t)1 << (rbits - 1);
 	for (int k = 0; k < n; k++) {
 		const int64_t cv = sext32(q->ctbl[k], q->cbits), lv = sext32(q->ltbl[k], q->lbits), qv = sext32(q->qtbl[k], q->qbits);
 		host[4 * k] = (int32_t)cv; host[4 * k + 1] = (int32_t)lv; host[4 * k + 2] = (int32_t)qv; host[4 * k + 3] = 0;
-		const int64_t al = (lv < 0 ? -lv : lv) + (qv < 0 ? -qv : qv) + 1, ac = (cv < 0 ? -cv : cv) + al + 1;
-		if (al >= ((int64_t)1 << (q->lbits - 1)) || ac >= ((int64_t)1 << (q->cbits - 1))) safe = false;
+		if (!safe) continue;
+		if (walk) {
+			for (int64_t dx = 0; dx < ((int64_t)1 << dxs) && safe; dx++) {
+				const int64_t lsum = ((qv * dx) >> dxs) + lv;
+				const int64_t r = ((lsum * dx) >> dxs) + cv;
+				if (lsum < -llim || lsum >= llim || r < -rlim || r >= rlim) safe = false;
+			}
+		} else {
+			const int64_t al = (lv < 0 ? -lv : lv) + (qv < 0 ? -qv : qv) + 1, ac = (cv < 0 ? -cv : cv) + al + 1;
+			if (al >= llim || ac >= rlim) safe = false;
+		}
 	}
 	int32_t *dev = nullptr;
 	ZC_CUDA(cudaMalloc((void **)&dev, host.size() * 4));

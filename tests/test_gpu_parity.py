@@ -703,3 +703,24 @@ def test_lut_arbitrary_table_contents(kind, pw, ow):
     torch.cuda.synchronize()
     want = (zo.lut_sin if kind == "tbl" else zo.lut_qwav)(pw, ow, tbl, words)
     assert np.array_equal(host(out), want)
+
+
+@pytest.mark.parametrize("ow,pw", [(13, 18), (16, 20), (10, 14)])
+def test_quadtbl_tables_that_do_wrap(ow, pw):
+    """The engine drops the LBITS / CBITS register wraps of rtl/quadtbl.v:196-260 only after walking the caller's tables
+    and proving that no phase can make them wrap.  Coefficients that are not a sine wave (random words of the right
+    widths) do wrap: the kernel that models the registers must take over, and the words must still be the RTL's."""
+    core = zc.QuadTbl(ow=ow, phase_bits=pw)
+    rc, q = zo.derive_qtbl(0, ow, 2, pw)
+    assert rc == 0 and q.pw == core.PW
+    rng = np.random.default_rng(SEED + 77)
+    n = 1 << q.lgtbl
+    for name, bits in (("ctbl", q.cbits), ("ltbl", q.lbits), ("qtbl", q.qbits)):
+        words = rng.integers(0, 1 << bits, size=n, dtype=np.uint64)
+        for k in range(n):
+            getattr(q, name)[k] = int(words[k])
+            getattr(core.params, name)[k] = int(words[k])
+    port = np.arange(1 << core.PW, dtype=np.uint32) if core.PW <= 20 else rng.integers(0, 1 << core.PW, size=1 << 20, dtype=np.uint64).astype(np.uint32)
+    words32 = (port.astype(np.uint64) << (32 - core.PW)).astype(np.uint32)
+    got = host(core.lookup(dev(words32)))
+    assert np.array_equal(got, zo.quadtbl(q, port))

@@ -4,10 +4,15 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over one batch of synthetic samples.  The default workload is
+One "step" = one pass of the hot path over one batch of synthetic samples.  The headline workload is
 BASELINE.json configs[1]: rotation-mode CORDIC, 24-bit phase / 18-bit output, 20 stages, 2^30 samples
 per GPU (weak scaling: every rank owns an independent 2^30-sample shard, no data-path collective).
-Rank 0 prints ONE JSON line.
+Rank 0 prints ONE JSON line.  After the headline's timed region the same run measures, each with its own CUDA
+events and its own slice of the clock record,
+  "configs":   every other BASELINE.json configuration (random-phase cfg1, per-sample vectors, cfg2 vectoring and
+               its packed-word variant, cfg3 LUT cores at both table sizes on sweeps and random phases, cfg4 NCO
+               sharded over the ranks in closed form),
+  "sustained": the headline held for 400 steps (what the 1 kW power cap leaves of the burst figure).
 """
 import argparse
 import json
@@ -26,20 +31,34 @@ import numpy as np  # noqa: E402
 METRIC = "Gsamples/s CORDIC sin/cos (24b, 20 stages)"
 UNIT = "Gsamples/s"
 
-# name -> (kind, samples per GPU per step, algorithmic bytes per sample [SURVEY.md §8d])
+# name -> (kind, samples per GPU per step, algorithmic bytes per sample [SURVEY.md §8d], options)
 WORKLOADS = {
-    "rotate_cfg1": ("rotate_const", 1 << 30, 12),     # configs[1]  4 B phase in + 8 B (x,y) out
-    "rotate_cfg1_noseed": ("rotate_const", 1 << 30, 12),
-    "rotate_xy_cfg1": ("rotate", 1 << 29, 20),         # per-sample (x,y): 12 B in + 8 B out
-    "topolar_cfg2": ("topolar", 1 << 28, 16),          # configs[2]  8 B in + 8 B out
-    "sintable_p17": ("lut_sin", 1 << 30, 8),           # configs[3]
-    "quarterwav_p18": ("lut_qwav", 1 << 30, 8),        # configs[3]
-    "nco_cfg1": ("nco", 1 << 30, 8),                   # configs[4]  8 B out, no input stream
-    "quadtbl_p18": ("lut_quad", 1 << 30, 8),           # rtl/quadtbl.v, PW18/OW13
+    "rotate_cfg1": ("rotate_const", 1 << 30, 12, {}),     # configs[1]  4 B phase in + 8 B (x,y) out
+    "rotate_cfg1_noseed": ("rotate_const", 1 << 30, 12, {}),
+    "rotate_xy_cfg1": ("rotate", 1 << 29, 20, {}),         # per-sample (x,y): 12 B in + 8 B out
+    "topolar_cfg2": ("topolar", 1 << 28, 16, {}),          # configs[2]  8 B in + 8 B out
+    "topolar_i16_cfg2": ("topolar_i16", 1 << 28, 12, {}),  # configs[2], packed ports: int16 x 2 in, 8 B out
+    "rotate_o16_cfg0": ("rotate_const_o16", 1 << 30, 8, {}),  # packed outputs for an OW<=16 core: 4 B in + 2 x int16 out
+    "sintable_p17": ("lut_sin", 1 << 30, 8, {"pw": 17, "ow": 13}),     # configs[3], the shipped table
+    "sintable_p23": ("lut_sin", 1 << 30, 8, {"pw": 23, "ow": 16}),     # configs[3], the largest sintable (sw/sintable.cpp:62)
+    "quarterwav_p18": ("lut_qwav", 1 << 30, 8, {"pw": 18, "ow": 24}),  # configs[3], the shipped table
+    "quarterwav_p25": ("lut_qwav", 1 << 30, 8, {"pw": 25, "ow": 16}),  # configs[3], the largest quarterwav (sw/sintable.cpp:190)
+    "nco_cfg1": ("nco", 1 << 30, 8, {}),                   # configs[4]  8 B out, no input stream
+    "quadtbl_p18": ("lut_quad", 1 << 30, 8, {}),           # rtl/quadtbl.v, PW18/OW13
 }
 CFG1 = dict(iw=18, ow=18, xtra=2, phase_bits=24, nstages=20)
+CFG0 = dict(iw=16, ow=16, xtra=2, phase_bits=16, nstages=0)
 X0, Y0 = (1 << 17) - 1, 0          # full-scale input of bench/cpp/cordic_tb.cpp:68-69
 NCO_STEP = 0x01234567
+
+# (workload, phase pattern) measured after the headline, in this order (VERDICT r1 "Next" #1)
+CONFIG_PASSES = [
+    ("rotate_cfg1", "random"), ("rotate_xy_cfg1", "sweep"), ("rotate_xy_cfg1", "random"),
+    ("topolar_cfg2", "random"), ("topolar_i16_cfg2", "random"), ("rotate_o16_cfg0", "sweep"),
+    ("sintable_p17", "sweep"), ("sintable_p17", "random"), ("sintable_p23", "sweep"), ("sintable_p23", "random"),
+    ("quarterwav_p18", "sweep"), ("quarterwav_p18", "random"), ("quarterwav_p25", "sweep"), ("quarterwav_p25", "random"),
+    ("nco_cfg1", "nco"),
+]
 
 
 def peaks():
@@ -51,7 +70,8 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples nvidia-smi clocks / throttle reasons for the whole run; window(t0, t1) summarises the samples that
+    arrived inside one timed region (host clock)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -62,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -71,19 +91,23 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def window(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
         sm, mx, reasons, power = [], None, set(), []
-        for r in self.rows:
+        for ts, r in list(self.rows):
+            if ts < t0 or ts > t1 + 0.03:
+                continue
             try:
                 sm.append(float(r[0])); mx = float(r[1])
                 power.append(float(r[2]))
@@ -108,10 +132,33 @@ def cpu_threads():
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
-def cpu_run(kind, n, threads):
+def core_name(kind, opts):
+    if kind in ("rotate_const", "rotate", "nco"):
+        return "p2r IW18 OW18 WW21 PW24 NSTAGES20"
+    if kind == "rotate_const_o16":
+        return "p2r IW16 OW16 WW19 PW16 NSTAGES13 (configs[0]), outputs packed as int16 x 2"
+    if kind == "topolar":
+        return "r2p IW16 OW16 WW24 PW24 NSTAGES21"
+    if kind == "topolar_i16":
+        return "r2p IW16 OW16 WW24 PW24 NSTAGES21, inputs packed as int16 x 2"
+    if kind in ("lut_sin", "lut_qwav"):
+        return "%s PW%d OW%d" % ("sintable" if kind == "lut_sin" else "quarterwav", opts["pw"], opts["ow"])
+    return "quadtbl PW18 OW13"
+
+
+def config_for(workload, kind, opts, nper, phase, bytes_per):
+    """The workload-defining keys, identical for the `ours` and the `reference` arm."""
+    return {"workload": workload, "core": core_name(kind, opts), "samples_per_gpu_per_step": nper,
+            "phase": phase if kind != "nco" else "nco step 0x%08x" % NCO_STEP,
+            "sharding": "independent shards, no data-path collective",
+            "l2": "inputs+outputs per step are %.1f GiB per GPU, far larger than the 126 MB L2" % (bytes_per * nper / 2**30)}
+
+
+def cpu_run(kind, n, threads, opts=None):
     """One pass of the oracle (CPU port of the reference datapath) over n synthetic samples."""
     zo = oracle()
     zo.NTHREADS = threads
+    opts = opts or {}
     rng = np.random.default_rng(20261017)
     if kind in ("rotate_const", "nco"):
         rc, p = zo.derive_p2r(18, 18, 2, 24, 20)
@@ -121,13 +168,18 @@ def cpu_run(kind, n, threads):
             zo.nco(p, X0, Y0, 0, NCO_STEP, n)
         else:
             zo.rotate_const(p, X0, Y0, phase)
+    elif kind == "rotate_const_o16":
+        rc, p = zo.derive_p2r(16, 16, 2, 16, 0)
+        phase = (np.arange(n, dtype=np.uint32) & 0xFFFF)
+        t0 = time.perf_counter()
+        zo.rotate_const(p, 32767, 0, phase)
     elif kind == "rotate":
         rc, p = zo.derive_p2r(18, 18, 2, 24, 20)
         phase = (np.arange(n, dtype=np.uint32) & 0xFFFFFF)
         xy = rng.integers(-(1 << 17), 1 << 17, size=(n, 2), dtype=np.int64).astype(np.int32)
         t0 = time.perf_counter()
         zo.rotate(p, xy, phase)
-    elif kind == "topolar":
+    elif kind in ("topolar", "topolar_i16"):
         rc, p = zo.derive_r2p(16, 16, 2, 0, 0)
         xy = rng.integers(-32768, 32768, size=(n, 2), dtype=np.int64).astype(np.int32)
         t0 = time.perf_counter()
@@ -138,7 +190,7 @@ def cpu_run(kind, n, threads):
         t0 = time.perf_counter()
         zo.quadtbl(q, phase)
     else:
-        pw, ow = (17, 13) if kind == "lut_sin" else (18, 24)
+        pw, ow = opts.get("pw", 17 if kind == "lut_sin" else 18), opts.get("ow", 13 if kind == "lut_sin" else 24)
         tbl = zo.sintable(pw, ow) if kind == "lut_sin" else zo.quarterwav(pw, ow)
         phase = (np.arange(n, dtype=np.uint64) * 4).astype(np.uint32)
         t0 = time.perf_counter()
@@ -161,28 +213,37 @@ def verilator_standin():
             "passed": r.returncode == 0 and "SUCCESS" in r.stdout}
 
 
-def run_reference(args, kind, nper):
+def run_reference(args, kind, nper, bytes_per, opts):
     """--impl reference: the CPU implementation of the path on this box's host cores.  The reference's
     datapath only exists as Verilog (Verilator is not in the image), so this times the oracle port of
-    it (oracle/zc_oracle.c), all host threads, on a bounded sample of the same workload per step."""
+    it (oracle/zc_oracle.c), all host threads, over the SAME workload as the `ours` arm: every step is the
+    full samples_per_gpu_per_step, walked in slices of 2^26 samples so that the host never holds more than
+    one slice of input and output."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = cpu_threads()
-    sample = min(nper, 1 << 26)
+    piece = min(nper, 1 << 26)
+    pieces = max(1, nper // piece)
+
+    def one_step():
+        return sum(cpu_run(kind, piece, threads, opts) for _ in range(pieces))
     for _ in range(args.warmup):
-        cpu_run(kind, sample, threads)
-    times = [cpu_run(kind, sample, threads) for _ in range(args.steps)]
+        one_step()
+    times = [one_step() for _ in range(args.steps)]
     total = sum(times)
-    value = sample * args.steps / total / 1e9
+    per_step = piece * pieces
+    value = per_step * args.steps / total / 1e9
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-        "data": "synthetic", "config": {"workload": args.workload, "samples_per_step": sample,
-                                        "note": "CPU oracle port of rtl/cordic.v, bounded sample of the workload"},
+        "data": "synthetic", "config": config_for(args.workload, kind, opts, per_step, args.phase, bytes_per),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d samples/step x %d steps, pthreads over all host threads" % (sample, args.steps)},
+                         "sample": "%d samples/step (the whole workload, in %d slices of %d) x %d steps, oracle/zc_oracle.c "
+                                   "(C port of rtl/cordic.v), pthreads over all %d host threads; only the datapath is timed "
+                                   "(input synthesis is outside the clock, as it is for the GPU arm)"
+                                   % (per_step, pieces, piece, args.steps, threads)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -190,6 +251,193 @@ def run_reference(args, kind, nper):
 
 
 # ------------------------------------------------------------------------------------------------
+class Bench:
+    """Everything the `ours` arm shares between its passes."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import cordic_b200 as zc
+        self.torch, self.dist, self.zc, self.args = torch, dist, zc, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl ours needs a CUDA device: libzcordic has no CPU path")
+        torch.cuda.set_device(self.local)
+        self.dev = "cuda:%d" % self.local
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device(self.dev))
+        assert self.world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+        self.sampler = ClockSampler(self.local)
+        if self.rank == 0:
+            self.sampler.start()
+        self.peak, self.peak_src = peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- one workload: inputs resident in HBM, a step() closure, a cheap self-check ------------------------------
+    def make(self, workload, phase_mode, nper, flags=0, no_tail=False, nco_step=NCO_STEP):
+        torch, zc, devname, rank = self.torch, self.zc, self.dev, self.rank
+        kind, _, bytes_per, opts = WORKLOADS[workload]
+        g = torch.Generator(device=devname); g.manual_seed(20261017 + rank)
+        first = rank * nper                       # this rank's shard of the global sample stream
+        w = {"kind": kind, "nper": nper, "bytes_per": bytes_per, "opts": opts, "first": first}
+        pmask = 0xFFFF if kind == "rotate_const_o16" else 0xFFFFFF
+        if kind in ("rotate_const", "rotate", "rotate_const_o16"):
+            if phase_mode == "sweep":
+                phase = (torch.arange(nper, dtype=torch.int64, device=devname) + first).bitwise_and_(pmask).to(torch.int32)
+            else:
+                phase = torch.randint(0, pmask + 1, (nper,), dtype=torch.int32, device=devname, generator=g)
+            w["phase"] = phase
+        if kind in ("rotate", "topolar"):
+            lim = 1 << 17 if kind == "rotate" else 1 << 15
+            w["xy"] = torch.randint(-lim, lim, (nper, 2), dtype=torch.int32, device=devname, generator=g)
+        if kind == "topolar_i16":
+            w["iq"] = torch.randint(-(1 << 15), 1 << 15, (nper, 2), dtype=torch.int16, device=devname, generator=g)
+        if kind in ("lut_sin", "lut_qwav", "lut_quad"):
+            if phase_mode == "sweep":
+                phase = ((torch.arange(nper, dtype=torch.int64, device=devname) + first) * 4).bitwise_and_(0xFFFFFFFF).to(torch.int32)
+            else:
+                phase = torch.randint(-(1 << 31), 1 << 31, (nper,), dtype=torch.int64, device=devname, generator=g).to(torch.int32)
+            w["phase"] = phase
+            w["lut"] = (zc.SinTable(phase_bits=opts["pw"], ow=opts["ow"]) if kind == "lut_sin" else
+                        zc.QuarterWav(phase_bits=opts["pw"], ow=opts["ow"]) if kind == "lut_qwav" else zc.QuadTbl(ow=13, phase_bits=18))
+        if kind in ("topolar", "topolar_i16"):
+            w["core"] = zc.Topolar(iw=16, ow=16, xtra=2)
+            w["o_mag"] = torch.empty(nper, dtype=torch.int32, device=devname)
+            w["o_ph"] = torch.empty(nper, dtype=torch.int32, device=devname)
+        elif kind in ("lut_sin", "lut_qwav", "lut_quad"):
+            w["o_val"] = torch.empty(nper, dtype=torch.int32, device=devname)
+        elif kind == "rotate_const_o16":
+            w["core"] = zc.Cordic(**CFG0)
+            w["o_xy16"] = torch.empty((nper, 2), dtype=torch.int16, device=devname)
+        else:
+            w["core"] = zc.Cordic(**CFG1)
+            w["o_xy"] = torch.empty((nper, 2), dtype=torch.int32, device=devname)
+
+        def step():
+            if kind == "rotate_const":
+                w["core"].rotate_const(X0, Y0, w["phase"], out=w["o_xy"], flags=flags)
+            elif kind == "rotate_const_o16":
+                w["core"].rotate_const_o16(32767, 0, w["phase"], out=w["o_xy16"])
+            elif kind == "rotate":
+                w["core"].rotate(w["xy"], w["phase"], out=w["o_xy"], flags=flags & zc.F_NO_DP2A)
+            elif kind == "nco":
+                w["core"].nco(X0, Y0, 0, nco_step, nper, n0=first, out=w["o_xy"], flags=flags)
+            elif kind == "topolar":
+                w["core"].topolar(w["xy"], mag=w["o_mag"], phase=w["o_ph"], flags=zc.F_NO_TAIL if no_tail else zc.F_DEFAULT)
+            elif kind == "topolar_i16":
+                w["core"].topolar_i16(w["iq"], mag=w["o_mag"], phase=w["o_ph"])
+            else:
+                w["lut"].lookup(w["phase"], out=w["o_val"])
+        w["step"] = step
+        return w
+
+    def spot_check(self, w, phase_mode):
+        """A cheap device-side consistency check of what was just timed -- never the oracle (tests/ own parity):
+        the known full-sweep checksums, or the same samples through a different kernel family."""
+        torch, zc = self.torch, self.zc
+        kind, nper = w["kind"], w["nper"]
+        m = min(nper, 1 << 22)
+        if kind == "rotate_const" and phase_mode == "sweep" and nper >= (1 << 24):
+            return w["o_xy"][:1 << 24].sum(dim=0, dtype=torch.int64).tolist() == [-39316, -39316]
+        if kind == "rotate_const":                     # table-seeded kernel vs every stage in registers
+            ref = w["core"].rotate_const(X0, Y0, w["phase"][:m], flags=zc.F_NO_SEED)
+            return bool(torch.equal(ref, w["o_xy"][:m]))
+        if kind == "nco":                              # NCO kernel vs explicit phases through the plain kernel
+            idx = torch.arange(m, dtype=torch.int64, device=self.dev) + w["first"]
+            ph = ((idx * NCO_STEP) & 0xFFFFFFFF) >> 8
+            ref = w["core"].rotate_const(X0, Y0, ph.to(torch.int32), flags=zc.F_NO_SEED)
+            return bool(torch.equal(ref, w["o_xy"][:m])) and (w["first"] != 0 or w["o_xy"][0].tolist() == [76313, 0])
+        if kind == "rotate":                           # table-directed kernel vs plain kernel
+            ref = w["core"].rotate(w["xy"][:m], w["phase"][:m], flags=zc.F_NO_SEED)
+            return bool(torch.equal(ref, w["o_xy"][:m]))
+        if kind == "topolar_i16":                      # packed ports vs the 32-bit port words
+            mag, ph = w["core"].topolar(w["iq"][:m].to(torch.int32).contiguous())
+            return bool(torch.equal(mag, w["o_mag"][:m]) and torch.equal(ph, w["o_ph"][:m]))
+        if kind == "rotate_const_o16":
+            ref = w["core"].rotate_const(32767, 0, w["phase"][:m])
+            return bool(torch.equal(ref.to(torch.int16), w["o_xy16"][:m]))
+        if kind in ("lut_sin", "lut_qwav"):            # the lookup rule of rtl/sintable.v / rtl/quarterwav.v in torch
+            pw, ow = w["opts"]["pw"], w["opts"]["ow"]
+            tbl = torch.from_numpy(w["lut"].table.astype(np.int64)).to(self.dev)
+            ip = (w["phase"][:m].to(torch.int64) & 0xFFFFFFFF) >> (32 - pw)
+            if kind == "lut_sin":
+                v = tbl[ip]
+            else:
+                fold = (ip >> (pw - 2)) & 1
+                idx = torch.where(fold == 1, ~ip, ip) & ((1 << (pw - 2)) - 1)
+                v = tbl[idx]
+                v = torch.where(((ip >> (pw - 1)) & 1) == 1, -v, v) & ((1 << ow) - 1)
+            v = torch.where(v >= (1 << (ow - 1)), v - (1 << ow), v)
+            return bool(torch.equal(v.to(torch.int32), w["o_val"][:m]))
+        return None
+
+    def timed(self, step, steps, warmup):
+        """W untimed steps, then exactly K steps between CUDA events on the launching stream, barrier +
+        synchronize on both sides; returns (ms on this rank, ms max over ranks, host-clock window, launches)."""
+        torch, zc = self.torch, self.zc
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        stream = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = zc.launch_count()
+        self.barrier()
+        t0 = time.time()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        self.barrier()
+        t1 = time.time()
+        launches = zc.launch_count() - launches0
+        ms = e0.elapsed_time(e1)
+        return ms, self.max_over_ranks(ms), (t0, t1), launches
+
+    def roofline(self, bytes_per, nper, ms, steps):
+        per_step_s = ms * 1e-3 / steps
+        achieved = bytes_per * nper / per_step_s / 1e9
+        return {"bound": "hbm", "achieved": achieved, "peak": self.peak, "unit": "GB/s", "frac": achieved / self.peak,
+                "algorithmic_bytes_per_sample": bytes_per, "kernel_ms": 1e3 * per_step_s}
+
+    def config_pass(self, workload, phase_mode, min_seconds=0.25):
+        """One extra configuration: >= 5 steps (enough of them to cover min_seconds of device time, so that the clock
+        record has samples inside the region), own events, own clock window."""
+        torch = self.torch
+        kind, nper, bytes_per, opts = WORKLOADS[workload]
+        if self.args.samples:
+            nper = min(nper, self.args.samples)
+        w = self.make(workload, phase_mode, nper)
+        try:
+            ms3, _, _, _ = self.timed(w["step"], 3, 3)
+            steps = int(max(5, min(400, min_seconds * 1e3 / max(ms3 / 3, 1e-3))))
+            steps = int(self.max_over_ranks(steps))                 # every rank runs the same count
+            ms, ms_max, win, launches = self.timed(w["step"], steps, 0)
+            ok = self.spot_check(w, phase_mode)
+            out = {"workload": workload, "phase": phase_mode if kind != "nco" else "nco step 0x%08x, n0 = rank * samples_per_gpu" % NCO_STEP,
+                   "core": core_name(kind, opts), "samples_per_gpu_per_step": nper, "steps": steps, "warmup": 6,
+                   "value": self.world * nper * steps / (ms_max * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_max / steps,
+                   "roofline": self.roofline(bytes_per, nper, ms, steps), "launches_per_step": launches / steps,
+                   "parity_spot_check": ok}
+            if self.rank == 0:
+                out["clocks"] = self.sampler.window(*win)
+            return out
+        finally:
+            del w
+            torch.cuda.empty_cache()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,207 +449,174 @@ def main():
     ap.add_argument("--phase", default="sweep", choices=["sweep", "random"])
     ap.add_argument("--seed-mode", default="auto", choices=["auto", "words", "packed", "regs"])
     ap.add_argument("--nco-step", type=lambda v: int(v, 0), default=NCO_STEP)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="default: 2 at N=1, 5 at N>1")
     ap.add_argument("--no-dp2a", action="store_true", help="seeded word table: IMAD + negation instead of IDP.2A (A/B)")
     ap.add_argument("--no-tail", action="store_true", help="topolar: every stage in its full form (A/B of the short late stages)")
+    ap.add_argument("--no-comb", action="store_true", help="NCO: keep the block mapping for every step (A/B of the comb mapping)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-exchange", action="store_true", help="skip the NCCL scatter/gather-inclusive figure (N>1)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the extra BASELINE configurations after the headline")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--sustained-steps", type=int, default=400)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
-    kind, nper, bytes_per = WORKLOADS[args.workload]
+    kind, nper, bytes_per, opts = WORKLOADS[args.workload]
     if args.samples:
         nper = args.samples
     if args.impl == "reference":
-        return run_reference(args, kind, nper)
+        return run_reference(args, kind, nper, bytes_per, opts)
 
-    import torch
-    import torch.distributed as dist
-    import cordic_b200 as zc
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl ours needs a CUDA device: libzcordic has no CPU path")
-    torch.cuda.set_device(local)
-    devname = "cuda:%d" % local
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(devname))
-    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+    B = Bench(args)
+    torch, dist, zc = B.torch, B.dist, B.zc
+    world, rank, local, devname = B.world, B.rank, B.local, B.dev
 
     flags = zc.F_NO_SEED if args.workload.endswith("_noseed") else zc.F_DEFAULT
     flags |= {"auto": 0, "words": zc.F_SEED_WORDS, "packed": zc.F_SEED_PACKED, "regs": zc.F_SEED_REGS}[args.seed_mode]
     if args.no_dp2a:
         flags |= zc.F_NO_DP2A
-    core = zc.Cordic(**CFG1)
-    # ---- synthetic inputs, resident in HBM before the timed region (4-12 GiB: far larger than L2)
-    g = torch.Generator(device=devname); g.manual_seed(20261017 + rank)
-    first = rank * nper                       # this rank's shard of the global sample stream
-    phase = xy = None
-    if kind in ("rotate_const", "rotate"):
-        if args.phase == "sweep":
-            phase = (torch.arange(nper, dtype=torch.int64, device=devname) + first).bitwise_and_(0xFFFFFF).to(torch.int32)
-        else:
-            phase = torch.randint(0, 1 << 24, (nper,), dtype=torch.int32, device=devname, generator=g)
-    if kind in ("rotate", "topolar"):
-        lim = 1 << 17 if kind == "rotate" else 1 << 15
-        xy = torch.randint(-lim, lim, (nper, 2), dtype=torch.int32, device=devname, generator=g)
-    if kind in ("lut_sin", "lut_qwav", "lut_quad"):
-        if args.phase == "sweep":
-            phase = ((torch.arange(nper, dtype=torch.int64, device=devname) + first) * 4).bitwise_and_(0xFFFFFFFF).to(torch.int32)
-        else:
-            phase = torch.randint(-(1 << 31), 1 << 31, (nper,), dtype=torch.int64, device=devname, generator=g).to(torch.int32)
-        lut = (zc.SinTable(phase_bits=17, ow=13) if kind == "lut_sin" else zc.QuarterWav(phase_bits=18, ow=24)
-               if kind == "lut_qwav" else zc.QuadTbl(ow=13, phase_bits=18))
-    if kind == "topolar":
-        vcore = zc.Topolar(iw=16, ow=16, xtra=2)
-        o_mag = torch.empty(nper, dtype=torch.int32, device=devname)
-        o_ph = torch.empty(nper, dtype=torch.int32, device=devname)
-    elif kind in ("lut_sin", "lut_qwav", "lut_quad"):
-        o_val = torch.empty(nper, dtype=torch.int32, device=devname)
-    else:
-        o_xy = torch.empty((nper, 2), dtype=torch.int32, device=devname)
-
-    def step():
-        if kind == "rotate_const":
-            core.rotate_const(X0, Y0, phase, out=o_xy, flags=flags)
-        elif kind == "rotate":
-            core.rotate(xy, phase, out=o_xy, flags=flags & zc.F_NO_DP2A)
-        elif kind == "nco":
-            core.nco(X0, Y0, 0, args.nco_step, nper, n0=first, out=o_xy, flags=flags)
-        elif kind == "topolar":
-            vcore.topolar(xy, mag=o_mag, phase=o_ph, flags=zc.F_NO_TAIL if args.no_tail else zc.F_DEFAULT)
-        else:
-            lut.lookup(phase, out=o_val)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    stream = torch.cuda.current_stream()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = zc.launch_count()
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    launches = zc.launch_count() - launches0
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=devname)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    if args.no_comb:
+        flags |= zc.F_NO_COMB
+    # ---- headline: synthetic inputs resident in HBM before the timed region (4-12 GiB: far larger than L2) ---------
+    w = B.make(args.workload, args.phase, nper, flags=flags, no_tail=args.no_tail, nco_step=args.nco_step)
+    time.sleep(0.25)
+    ms, ms_max, win, launches = B.timed(w["step"], args.steps, args.warmup)
+    clocks = B.sampler.window(*win) if rank == 0 else None
     value = world * nper * args.steps / (ms_max * 1e-3) / 1e9
+    ok = B.spot_check(w, args.phase) if args.nco_step == NCO_STEP else None
 
-    # ---- self-check of what was just timed: the known full-sweep checksums --------
-    ok = None
-    if kind in ("rotate_const", "nco") and nper >= (1 << 24) and (kind == "nco" or args.phase == "sweep"):
-        if kind == "rotate_const":
-            sums = o_xy[:1 << 24].sum(dim=0, dtype=torch.int64).tolist()
-            ok = sums == [-39316, -39316]
-        else:   # an odd NCO step visits every 24-bit phase equally often over 2^32 samples; over 2^24 the
-                # sum is not pinned, so only check the first sample: phase 0 -> (76313, 0)
-            ok = (first != 0) or o_xy[0].tolist() == [76313, 0]
+    # ---- the headline held for 400 steps: what the board's power cap leaves of the burst figure --------------------
+    sustained = None
+    if not args.no_sustained:
+        sms, sms_max, swin, _ = B.timed(w["step"], args.sustained_steps, 0)
+        sustained = {"steps": args.sustained_steps, "value": world * nper * args.sustained_steps / (sms_max * 1e-3) / 1e9,
+                     "unit": UNIT, "ms_per_step": sms_max / args.sustained_steps,
+                     "roofline": B.roofline(bytes_per, nper, sms, args.sustained_steps),
+                     "clocks": B.sampler.window(*swin) if rank == 0 else None,
+                     "what": "the headline workload, %d back-to-back steps right after the headline's timed region" % args.sustained_steps}
 
     # ---- end to end through the host-buffer ABI (pinned host memory, H2D + D2H inside the timing) ---
+    # N=1: zc_*_host on this GPU.  N>1: rank 0 alone calls zc_*_host_multi over all N devices of the box (one host
+    # thread + pipeline per device, pinned buffers bound to each device's NUMA node), the full samples_per_gpu on each;
+    # the other ranks release their device memory and wait on the host (the rendezvous store), not on the GPU.
     e2e = None
-    if not args.no_e2e:
-        ne = nper if world == 1 else min(nper, 1 << 28)
+    host_kinds = ("rotate_const", "rotate", "nco", "topolar", "lut_sin", "lut_qwav", "lut_quad")
+    if not args.no_e2e and kind in host_kinds:
+        ne = nper
+        e2e_steps = args.e2e_steps or (2 if world == 1 else 5)
         in_words = {"rotate_const": ne, "rotate": 3 * ne, "nco": 0, "topolar": 2 * ne, "lut_sin": ne, "lut_qwav": ne, "lut_quad": ne}[kind]
         out_words = {"rotate_const": 2 * ne, "rotate": 2 * ne, "nco": 2 * ne, "topolar": 2 * ne, "lut_sin": ne, "lut_qwav": ne, "lut_quad": ne}[kind]
-        hin = zc.PinnedBuffer(max(in_words, 1), np.int32)
-        hout = zc.PinnedBuffer(out_words, np.int32)
-        if kind in ("rotate_const", "lut_sin", "lut_qwav", "lut_quad"):
-            hin.array[:ne] = phase[:ne].cpu().numpy()
-        elif kind == "rotate":
-            hin.array[:ne] = phase[:ne].cpu().numpy(); hin.array[ne:] = xy[:ne].cpu().numpy().reshape(-1)
-        elif kind == "topolar":
-            hin.array[:] = xy[:ne].cpu().numpy().reshape(-1)
-
-        def e2e_step():
-            a, o = hin.array, hout.array
-            if kind == "rotate_const":
-                core.rotate_const_host(X0, Y0, a[:ne].view(np.uint32), o, device=local)
+        if world == 1:
+            hin = zc.PinnedBuffer(max(in_words, 1), np.int32)
+            hout = zc.PinnedBuffer(out_words, np.int32)
+            if kind in ("rotate_const", "lut_sin", "lut_qwav", "lut_quad"):
+                hin.array[:ne] = w["phase"][:ne].cpu().numpy()
             elif kind == "rotate":
-                core.rotate_host(a[ne:], a[:ne].view(np.uint32), o, device=local)
-            elif kind == "nco":
-                core.nco_host(X0, Y0, 0, args.nco_step, o, n0=first, device=local)
+                hin.array[:ne] = w["phase"][:ne].cpu().numpy(); hin.array[ne:] = w["xy"][:ne].cpu().numpy().reshape(-1)
             elif kind == "topolar":
-                vcore.topolar_host(a, o[:ne], o[ne:].view(np.uint32), device=local)
-            else:
-                lut.lookup_host(a[:ne].view(np.uint32), o, device=local)
-        e2e_step()                                  # warm-up (also faults the pinned pages in)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()                              # returns when the outputs are in host memory
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=devname)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": world * ne * args.e2e_steps / dt / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": 4 * in_words, "d2h_bytes_per_step": 4 * out_words,
-               "samples_per_gpu_per_step": ne, "steps": args.e2e_steps,
-               "api": "zc_%s_host (pinned host buffers, chunked H2D->kernel->D2H pipeline)" % kind}
-        hin.free(); hout.free()
+                hin.array[:] = w["xy"][:ne].cpu().numpy().reshape(-1)
+            core, lut = w.get("core"), w.get("lut")
 
-    # ---- N>1: the same stream held by rank 0, scattered and gathered over NCCL/NVLink each step --------------
-    # north_star: "NCCL over NVLink only as a trivial scatter/gather of independent chunks".  Reported next to the
-    # shard-resident figure above; rank 0's NVLink port (8 B/sample coming back) bounds it, not the kernels.
+            def e2e_step():
+                a, o = hin.array, hout.array
+                if kind == "rotate_const":
+                    core.rotate_const_host(X0, Y0, a[:ne].view(np.uint32), o, device=local)
+                elif kind == "rotate":
+                    core.rotate_host(a[ne:], a[:ne].view(np.uint32), o, device=local)
+                elif kind == "nco":
+                    core.nco_host(X0, Y0, 0, args.nco_step, o, n0=w["first"], device=local)
+                elif kind == "topolar":
+                    core.topolar_host(a, o[:ne], o[ne:].view(np.uint32), device=local)
+                else:
+                    lut.lookup_host(a[:ne].view(np.uint32), o, device=local)
+            e2e_step()                                  # warm-up (also faults the pinned pages in)
+            B.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()                              # returns when the outputs are in host memory
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            e2e = {"value": ne * e2e_steps / dt / 1e9, "unit": UNIT,
+                   "h2d_bytes_per_step": 4 * in_words, "d2h_bytes_per_step": 4 * out_words,
+                   "samples_per_gpu_per_step": ne, "steps": e2e_steps,
+                   "api": "zc_%s_host (pinned host buffers, chunked H2D->kernel->D2H pipeline)" % kind}
+            hin.free(); hout.free()
+        elif kind == "rotate_const":
+            del w
+            w = None
+            torch.cuda.empty_cache()
+            store = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                try:
+                    devices = list(range(world))
+                    core = zc.Cordic(**CFG1)
+                    total = world * ne
+                    hin = zc.ShardedPinnedBuffer(total, devices, np.uint32)      # shard g bound to device g's NUMA node
+                    hout = zc.ShardedPinnedBuffer(2 * total, devices, np.int32)
+                    ar = hin.array
+                    for s0 in range(0, total, 1 << 26):                           # the global sweep, shard after shard
+                        ar[s0:s0 + (1 << 26)] = (np.arange(s0, min(total, s0 + (1 << 26)), dtype=np.int64) & 0xFFFFFF).astype(np.uint32)
+                    core.rotate_const_host_multi(X0, Y0, ar, hout.array, devices)   # warm-up
+                    t0 = time.perf_counter()
+                    for _ in range(e2e_steps):
+                        core.rotate_const_host_multi(X0, Y0, ar, hout.array, devices)
+                    dt = time.perf_counter() - t0
+                    sums = hout.array.reshape(-1, 2)[:1 << 24].sum(axis=0, dtype=np.int64).tolist()
+                    last = hout.array.reshape(-1, 2)[total - (1 << 24):].sum(axis=0, dtype=np.int64).tolist()
+                    e2e = {"value": total * e2e_steps / dt / 1e9, "unit": UNIT,
+                           "h2d_bytes_per_step": 4 * total, "d2h_bytes_per_step": 8 * total,
+                           "samples_per_gpu_per_step": ne, "steps": e2e_steps, "numa": hin.placement,
+                           "parity_spot_check": sums == [-39316, -39316] and last == [-39316, -39316],
+                           "api": "zc_rotate_const_host_multi: one process, one host thread + H2D->kernel->D2H pipeline per "
+                                  "device, %d devices, pinned host shards on each device's NUMA node" % world}
+                    hin.free(); hout.free()
+                except Exception as e:                              # never lose the main line over it
+                    e2e = {"error": repr(e)[:300]}
+                store.set("zc_e2e_done", "1")
+            else:
+                store.wait(["zc_e2e_done"])
+            B.barrier()
+
+    # ---- N>1: the same stream held by device 0, scattered and gathered over NCCL/NVLink each step --------------
+    # north_star: "NCCL over NVLink only as a trivial scatter/gather of independent chunks".  Product code: the C++
+    # client cordic_b200/zcordic_bench --scatter (libzcordic_nccl: ncclGroupStart/ncclSend/ncclRecv/ncclGroupEnd, chunked
+    # so that scatter(k+1), kernel(k) and gather(k-1) overlap).  Rank 0 runs it as a child process over all N devices
+    # while the other ranks wait on the host.
     exchange = None
     if world > 1 and kind == "rotate_const" and not args.no_exchange:
-        try:
-            nx = min(nper, 1 << 27)
-            chunk_in = torch.empty(nx, dtype=torch.int32, device=devname)
-            chunk_out = torch.empty((nx, 2), dtype=torch.int32, device=devname)
-            if rank == 0:
-                all_in = (torch.arange(world * nx, dtype=torch.int64, device=devname)).bitwise_and_(0xFFFFFF).to(torch.int32)
-                all_out = torch.empty((world * nx, 2), dtype=torch.int32, device=devname)
-                ins = list(all_in.split(nx)); outs = list(all_out.split(nx))
-            else:
-                ins = outs = None
+        if w is not None:
+            del w
+            w = None
+        torch.cuda.empty_cache()
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            exe = os.path.join(ROOT, "cordic_b200", "zcordic_bench")
+            try:
+                r = subprocess.run([exe, "-g", str(world), "--scatter", "-l", "28", "-s", "5", "--json"],
+                                   capture_output=True, text=True, timeout=600)
+                exchange = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+            except Exception as e:
+                exchange = {"error": repr(e)[:300]}
+            store.set("zc_xchg_done", "1")
+        else:
+            store.wait(["zc_xchg_done"])
+        B.barrier()
 
-            def xstep():
-                dist.scatter(chunk_in, ins, src=0)
-                core.rotate_const(X0, Y0, chunk_in, out=chunk_out, flags=flags)
-                dist.gather(chunk_out, outs, dst=0)
-            xstep()
-            barrier()
-            x0e, x1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            xsteps = 5
-            x0e.record(stream)
-            for _ in range(xsteps):
-                xstep()
-            x1e.record(stream)
-            barrier()
-            tx = torch.tensor([x0e.elapsed_time(x1e)], dtype=torch.float64, device=devname)
-            dist.all_reduce(tx, op=dist.ReduceOp.MAX)
-            xok = None
-            if rank == 0:
-                xok = all_out[:1 << 24].sum(dim=0, dtype=torch.int64).tolist() == [-39316, -39316] and \
-                    torch.equal(all_out[:nx], all_out[(world - 1) * nx:]) if nx % (1 << 24) == 0 else None
-            exchange = {"value": world * nx * xsteps / (float(tx.item()) * 1e-3) / 1e9, "unit": UNIT,
-                        "samples_per_gpu_per_step": nx, "steps": xsteps, "parity": xok,
-                        "what": "rank 0 owns the whole phase stream: dist.scatter -> kernel -> dist.gather (NCCL) inside the timed region"}
-            del chunk_in, chunk_out
-            if rank == 0:
-                del all_in, all_out, ins, outs
-        except Exception as e:                                   # never lose the main line over the extra figure
-            exchange = {"error": repr(e)[:200]}
+    # ---- the other BASELINE configurations, each with its own timed region ---------------------------------------
+    configs = None
+    if not args.no_configs:
+        if w is not None:
+            del w
+            w = None
+        torch.cuda.empty_cache()
+        configs = []
+        for wl, pm in CONFIG_PASSES:
+            if wl == args.workload and pm == args.phase:
+                continue
+            try:
+                configs.append(B.config_pass(wl, pm))
+            except Exception as e:                                  # noqa: BLE001 - one pass must not cost the line
+                configs.append({"workload": wl, "phase": pm, "error": repr(e)[:300]})
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) --------------------------------
     cpu = None
@@ -409,9 +624,9 @@ def main():
         threads = cpu_threads()
         sample = min(nper, 1 << 27)
         try:
-            cpu_run(kind, 1 << 22, threads)
-            dt_all = cpu_run(kind, sample, threads)
-            dt_one = cpu_run(kind, sample >> 4, 1)
+            cpu_run(kind, 1 << 22, threads, opts)
+            dt_all = cpu_run(kind, sample, threads, opts)
+            dt_one = cpu_run(kind, sample >> 4, 1, opts)
             cpu = {"value": sample / dt_all / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "%d samples of the same workload, oracle/zc_oracle.c (C port of rtl/cordic.v), %d pthreads"
                              % (sample, threads),
@@ -421,34 +636,38 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "port", "sample": "oracle not built: %s" % e}
 
     if rank == 0:
-        peak, peak_src = peaks()
-        # one dominant kernel launch per step (the seeded path adds a ~2 us probe and a launch that returns at its
-        # gate); its duration is the CUDA-event time of the timed region / steps
-        per_step_s = ms * 1e-3 / args.steps
-        achieved = bytes_per * nper / per_step_s / 1e9
+        B.sampler.stop()
+        # one dominant kernel launch per step (the auto-selected path adds a launch that returns at its probe);
+        # its duration is the CUDA-event time of the timed region / steps
+        roof = B.roofline(bytes_per, nper, ms, args.steps)
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
         except Exception:
             pass
+        roof.update({
+            "traffic": traffic,
+            "traffic_source": "profiled constant: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed "
+                              "`ncu --set full` capture of this kernel (profiles/traffic.json), not measured in this run",
+            "peak_source": B.peak_src, "launches_per_step": launches / args.steps,
+            # `peak` is the 1:1 copy figure; a no-arithmetic kernel moving this workload's own mix (4 B read +
+            # 8 B written per sample, same access shape and launch geometry) measured 6100 GB/s on this pool
+            "traffic_mix_note": ("tools/membench2.cu moves 4 B in + 8 B out per sample with this kernel's access shape "
+                                 "at 6100 GB/s (profiles/membench_r1.txt): frac of that = %.3f" % (roof["achieved"] / 6100.0))
+            if args.workload == "rotate_cfg1" else None,
+            "scope_note": ("the table-seeded kernel serves a CONSTANT input vector (the sin/cos generator of cordic_tb.cpp:61-80); "
+                           "this figure is for neighbouring phases (sweep); scattered phases, per-sample vectors and the all-"
+                           "stages-in-registers kernel are under `configs`") if args.workload == "rotate_cfg1" and args.phase == "sweep" else None})
+        cfg = config_for(args.workload, kind, opts, nper, args.phase, bytes_per)
+        if args.seed_mode != "auto":
+            cfg["seed_mode"] = args.seed_mode
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": args.workload, "core": "p2r IW18 OW18 WW21 PW24 NSTAGES20" if kind in ("rotate_const", "rotate", "nco") else kind,
-                       "samples_per_gpu_per_step": nper, "phase": args.phase, "seed_mode": args.seed_mode, "sharding": "independent shards, no data-path collective",
-                       "l2": "inputs+outputs per step are %.1f GiB per GPU, far larger than the 126 MB L2" % (bytes_per * nper / 2**30)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_sample": bytes_per, "kernel_ms": 1e3 * per_step_s,
-                         "launches_per_step": launches / args.steps,
-                         # `peak` is the 1:1 copy figure; a no-arithmetic kernel moving this workload's own mix (4 B read +
-                         # 8 B written per sample, same access shape and launch geometry) measured 6100 GB/s on this pool
-                         "traffic_mix_note": ("tools/membench2.cu moves 4 B in + 8 B out per sample with this kernel's access shape "
-                                              "at 6100 GB/s (profiles/membench_r1.txt): frac of that = %.3f" % (achieved / 6100.0))
-                         if args.workload == "rotate_cfg1" else None},
+            "config": cfg, "roofline": roof,
             "cpu_baseline": cpu, "e2e": e2e, "scatter_gather": exchange, "gpu_launches": int(launches), "clocks": clocks,
-            "parity_spot_check": ok,
+            "parity_spot_check": ok, "sustained": sustained, "configs": configs,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -27,6 +27,7 @@ F_SEED_REGS = 16
 F_SEED_WORDS = 32
 F_NO_TAIL = 64
 F_NO_DP2A = 128
+F_NO_COMB = 256
 
 MODE_P2R, MODE_R2P = 0, 1
 
@@ -96,6 +97,7 @@ _SIGNATURES = {
     "zc_iterations": (ctypes.c_int, [ctypes.POINTER(Params)]),
     "zc_clocks_per_output": (ctypes.c_int, [ctypes.POINTER(Params)]),
     "zc_topolar_tail_stages": (ctypes.c_int, [ctypes.POINTER(Params)]),
+    "zc_nco_comb_run": (ctypes.c_longlong, [ctypes.POINTER(Params), ctypes.c_uint32, ctypes.c_size_t]),
     "zc_derive_tbl": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 2),
     "zc_derive_qtr": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 2),
     "zc_lut_build_sintable": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
@@ -136,6 +138,31 @@ _SIGNATURES = {
     "zc_hex_write": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
     "zc_hex_read": (ctypes.c_long, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]),
     "zc_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
+    "zc_host_alloc_sharded": (ctypes.c_void_p, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "zc_device_numa_node": (ctypes.c_int, [ctypes.c_int]),
+    "zc_topolar_i16": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "zc_rotate_const_o16": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                           ctypes.c_void_p]),
+    "zc_topolar_i16_host": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_size_t, ctypes.c_int]),
+    "zc_rotate_const_o16_host": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32,
+                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
+    "zc_rotate_const_host_multi": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                  ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "zc_rotate_host_multi": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "zc_topolar_host_multi": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "zc_nco_rotate_host_multi": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32,
+                                                ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t,
+                                                ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "zc_lut_sin_host_multi": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "zc_lut_qwav_host_multi": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "zc_host_free": (None, [ctypes.c_void_p]),
     "zc_rotate_const_host": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32,
                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
@@ -274,15 +301,20 @@ def _is_tensor(x):
     return type(x).__module__.startswith("torch")
 
 
-def _dev_ptr(t, nwords=None):
+def _dev_ptr(t, nwords=None, itemsize=4):
     torch = _torch()
     if not (_is_tensor(t) and t.is_cuda):
         raise ZcError(-1, "expected a CUDA tensor")
-    if t.element_size() != 4 or not t.is_contiguous():
-        raise ZcError(-1, "expected a contiguous 32-bit tensor, got %s" % (t.dtype,))
+    if t.element_size() != itemsize or not t.is_contiguous():
+        raise ZcError(-1, "expected a contiguous %d-bit tensor, got %s" % (8 * itemsize, t.dtype))
     if nwords is not None and t.numel() != nwords:
         raise ZcError(-1, "tensor has %d words, expected %d" % (t.numel(), nwords))
     return ctypes.c_void_p(t.data_ptr())
+
+
+def _devices(devices):
+    arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+    return arr, len(devices)
 
 
 def _stream_ptr(device_index, stream):
@@ -291,16 +323,16 @@ def _stream_ptr(device_index, stream):
     return ctypes.c_void_p(s.cuda_stream)
 
 
-def _host_ptr(a, nwords=None):
+def _host_ptr(a, nwords=None, itemsize=4):
     """numpy array or CPU (possibly pinned) torch tensor -> pointer."""
     if _is_tensor(a):
-        if a.is_cuda or a.element_size() != 4 or not a.is_contiguous():
-            raise ZcError(-1, "expected a contiguous 32-bit CPU tensor")
+        if a.is_cuda or a.element_size() != itemsize or not a.is_contiguous():
+            raise ZcError(-1, "expected a contiguous %d-bit CPU tensor" % (8 * itemsize))
         if nwords is not None and a.numel() != nwords:
             raise ZcError(-1, "tensor has %d words, expected %d" % (a.numel(), nwords))
         return ctypes.c_void_p(a.data_ptr())
-    if not isinstance(a, np.ndarray) or a.dtype.itemsize != 4 or not a.flags["C_CONTIGUOUS"]:
-        raise ZcError(-1, "expected a C-contiguous 32-bit numpy array")
+    if not isinstance(a, np.ndarray) or a.dtype.itemsize != itemsize or not a.flags["C_CONTIGUOUS"]:
+        raise ZcError(-1, "expected a C-contiguous %d-bit numpy array" % (8 * itemsize))
     if nwords is not None and a.size != nwords:
         raise ZcError(-1, "array has %d words, expected %d" % (a.size, nwords))
     return ctypes.c_void_p(a.ctypes.data)
@@ -330,6 +362,21 @@ class PinnedBuffer:
             pass
 
 
+class ShardedPinnedBuffer(PinnedBuffer):
+    """Pinned host memory from zc_host_alloc_sharded: the g-th 1/len(devices) of the buffer lives on the NUMA node of
+    devices[g] -- the buffers the *_host_multi calls want.  ``placement`` lists (device, node) pairs."""
+
+    def __init__(self, nwords, devices, dtype=np.int32):
+        self.nbytes = int(nwords) * 4
+        arr, nd = _devices(devices)
+        self.ptr = lib().zc_host_alloc_sharded(self.nbytes, arr, nd)
+        if not self.ptr:
+            raise ZcError(-5, (lib().zc_last_error() or b"").decode())
+        buf = (ctypes.c_char * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(nwords))
+        self.placement = [(int(d), int(lib().zc_device_numa_node(int(d)))) for d in devices]
+
+
 # ---- cores ----------------------------------------------------------------------------------
 
 class Cordic:
@@ -352,6 +399,17 @@ class Cordic:
             out = torch.empty((n, 2), dtype=torch.int32, device=phase.device)
         _check(lib().zc_rotate_const_ex(ctypes.byref(self.params), int(x0), int(y0), _dev_ptr(phase),
                                         _dev_ptr(out, 2 * n), n, dev, _stream_ptr(dev, stream), flags))
+        return out
+
+    def rotate_const_o16(self, x0, y0, phase, out=None, stream=None):
+        """As rotate_const for a core with OW <= 16, outputs packed: int16 CUDA tensor [n, 2] (zc_rotate_const_o16)."""
+        torch = _torch()
+        n = phase.numel()
+        dev = phase.device.index or 0
+        if out is None:
+            out = torch.empty((n, 2), dtype=torch.int16, device=phase.device)
+        _check(lib().zc_rotate_const_o16(ctypes.byref(self.params), int(x0), int(y0), _dev_ptr(phase),
+                                         _dev_ptr(out, 2 * n, 2), n, dev, _stream_ptr(dev, stream)))
         return out
 
     def rotate(self, xy, phase, out=None, stream=None, flags=F_DEFAULT):
@@ -394,6 +452,34 @@ class Cordic:
                                           _host_ptr(out, 2 * n), n, device))
         return out
 
+    def rotate_const_o16_host(self, x0, y0, phase, out, device=0):
+        n = phase.size if isinstance(phase, np.ndarray) else phase.numel()
+        _check(lib().zc_rotate_const_o16_host(ctypes.byref(self.params), int(x0), int(y0), _host_ptr(phase),
+                                              _host_ptr(out, 2 * n, 2), n, device))
+        return out
+
+    def rotate_const_host_multi(self, x0, y0, phase, out, devices):
+        """zc_rotate_const_host_multi: the stream sharded over ``devices``, one host thread + pipeline per device."""
+        n = phase.size if isinstance(phase, np.ndarray) else phase.numel()
+        arr, nd = _devices(devices)
+        _check(lib().zc_rotate_const_host_multi(ctypes.byref(self.params), int(x0), int(y0), _host_ptr(phase),
+                                                _host_ptr(out, 2 * n), n, arr, nd))
+        return out
+
+    def rotate_host_multi(self, xy, phase, out, devices):
+        n = phase.size if isinstance(phase, np.ndarray) else phase.numel()
+        arr, nd = _devices(devices)
+        _check(lib().zc_rotate_host_multi(ctypes.byref(self.params), _host_ptr(xy, 2 * n), _host_ptr(phase),
+                                          _host_ptr(out, 2 * n), n, arr, nd))
+        return out
+
+    def nco_host_multi(self, x0, y0, phase0, step, out, devices, n0=0):
+        n = (out.size if isinstance(out, np.ndarray) else out.numel()) // 2
+        arr, nd = _devices(devices)
+        _check(lib().zc_nco_rotate_host_multi(ctypes.byref(self.params), int(x0), int(y0), int(phase0) & 0xFFFFFFFF,
+                                              int(step) & 0xFFFFFFFF, int(n0), _host_ptr(out), n, arr, nd))
+        return out
+
     def rotate_host(self, xy, phase, out, device=0):
         n = phase.size if isinstance(phase, np.ndarray) else phase.numel()
         _check(lib().zc_rotate_host(ctypes.byref(self.params), _host_ptr(xy, 2 * n), _host_ptr(phase),
@@ -426,6 +512,32 @@ class Topolar:
             phase = torch.empty(n, dtype=torch.int32, device=xy.device)
         _check(lib().zc_topolar_ex(ctypes.byref(self.params), _dev_ptr(xy, 2 * n), _dev_ptr(mag, n),
                                    _dev_ptr(phase, n), n, dev, _stream_ptr(dev, stream), flags))
+        return mag, phase
+
+    def topolar_i16(self, xy16, mag=None, phase=None, stream=None):
+        """As topolar for a core with IW <= 16, inputs packed: xy16 is an int16 CUDA tensor [n, 2] (zc_topolar_i16)."""
+        torch = _torch()
+        n = xy16.numel() // 2
+        dev = xy16.device.index or 0
+        if mag is None:
+            mag = torch.empty(n, dtype=torch.int32, device=xy16.device)
+        if phase is None:
+            phase = torch.empty(n, dtype=torch.int32, device=xy16.device)
+        _check(lib().zc_topolar_i16(ctypes.byref(self.params), _dev_ptr(xy16, 2 * n, 2), _dev_ptr(mag, n),
+                                    _dev_ptr(phase, n), n, dev, _stream_ptr(dev, stream)))
+        return mag, phase
+
+    def topolar_i16_host(self, xy16, mag, phase, device=0):
+        n = (xy16.size if isinstance(xy16, np.ndarray) else xy16.numel()) // 2
+        _check(lib().zc_topolar_i16_host(ctypes.byref(self.params), _host_ptr(xy16, 2 * n, 2), _host_ptr(mag, n),
+                                         _host_ptr(phase, n), n, device))
+        return mag, phase
+
+    def topolar_host_multi(self, xy, mag, phase, devices):
+        n = (xy.size if isinstance(xy, np.ndarray) else xy.numel()) // 2
+        arr, nd = _devices(devices)
+        _check(lib().zc_topolar_host_multi(ctypes.byref(self.params), _host_ptr(xy), _host_ptr(mag, n),
+                                           _host_ptr(phase, n), n, arr, nd))
         return mag, phase
 
     def topolar_host(self, xy, mag, phase, device=0):
@@ -468,6 +580,14 @@ class _Lut:
         n = phase32.size if isinstance(phase32, np.ndarray) else phase32.numel()
         fn = lib().zc_lut_qwav_host if self.QUARTER else lib().zc_lut_sin_host
         _check(fn(self.PW, self.OW, self.table.ctypes.data, _host_ptr(phase32), _host_ptr(out, n), n, device))
+        return out
+
+
+    def lookup_host_multi(self, phase32, out, devices):
+        n = phase32.size if isinstance(phase32, np.ndarray) else phase32.numel()
+        fn = lib().zc_lut_qwav_host_multi if self.QUARTER else lib().zc_lut_sin_host_multi
+        arr, nd = _devices(devices)
+        _check(fn(self.PW, self.OW, self.table.ctypes.data, _host_ptr(phase32), _host_ptr(out, n), n, arr, nd))
         return out
 
 

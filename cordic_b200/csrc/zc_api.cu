@@ -2,7 +2,8 @@
 // preparation, kernel selection and launch, and the host-buffer pipelines.
 #include "zc_internal.h"
 #include "zc_kernels.cuh"
-#include "zc_seeded.cuh"
+#include "zc_generic.cuh"
+#include "zc_seedplan.h"
 #include "zc_quadtbl.cuh"
 
 #include <atomic>
@@ -56,8 +57,10 @@ static int device_info(int device, DeviceInfo &out) {
 	if (!g_dev[device].ok) {
 		cudaDeviceProp prop;
 		ZC_CUDA(cudaGetDeviceProperties(&prop, device));
-		if (prop.major < 10)
-			return set_error(ZC_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only",
+		// the library is an sm_100a cubin (architecture-specific, no PTX): any other device would fail every launch
+		// later with "no kernel image"
+		if (prop.major != 10 || prop.minor != 0)
+			return set_error(ZC_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
 				device, prop.major, prop.minor);
 		g_dev[device].sms = prop.multiProcessorCount;
 		g_dev[device].ok = true;
@@ -200,50 +203,8 @@ static int post_launch(const char *what) {
 	return ZC_OK;
 }
 
-// ---- rotation-mode launcher -------------------------------------------------------------------
-template <int SRC, int N>
-struct RotTable {
-	static void launch(int neff, int grid, cudaStream_t st, const int4 *ph, const int4 *xin, int4 *out,
-			size_t groups, const CoreConsts &c) {
-		if (neff == N) k_rotate<N, SRC><<<grid, 256, 0, st>>>(ph, xin, out, groups, c);
-		else RotTable<SRC, N - 1>::launch(neff, grid, st, ph, xin, out, groups, c);
-	}
-};
-template <int SRC>
-struct RotTable<SRC, 0> {
-	static void launch(int, int, cudaStream_t, const int4 *, const int4 *, int4 *, size_t, const CoreConsts &) {}
-};
-
-// NTAIL is quantised to even counts (at most 16) to bound the number of instantiations
-template <int N, int T>
-struct VecTail {
-	static void launch(int ntail, int grid, cudaStream_t st, const int4 *xin, int4 *mag, int4 *ph,
-			size_t groups, const CoreConsts &c) {
-		if constexpr (T > N) VecTail<N, T - 2>::launch(ntail, grid, st, xin, mag, ph, groups, c);
-		else if (ntail >= T) k_topolar<N, T><<<grid, 256, 0, st>>>(xin, mag, ph, groups, c);
-		else VecTail<N, T - 2>::launch(ntail, grid, st, xin, mag, ph, groups, c);
-	}
-};
-template <int N>
-struct VecTail<N, 0> {
-	static void launch(int, int grid, cudaStream_t st, const int4 *xin, int4 *mag, int4 *ph,
-			size_t groups, const CoreConsts &c) {
-		k_topolar<N, 0><<<grid, 256, 0, st>>>(xin, mag, ph, groups, c);
-	}
-};
-
-template <int N>
-struct VecTable {
-	static void launch(int neff, int ntail, int grid, cudaStream_t st, const int4 *xin, int4 *mag, int4 *ph,
-			size_t groups, const CoreConsts &c) {
-		if (neff == N) VecTail<N, 16>::launch(ntail, grid, st, xin, mag, ph, groups, c);
-		else VecTable<N - 1>::launch(neff, ntail, grid, st, xin, mag, ph, groups, c);
-	}
-};
-template <>
-struct VecTable<0> {
-	static void launch(int, int, int, cudaStream_t, const int4 *, int4 *, int4 *, size_t, const CoreConsts &) {}
-};
+// The fully unrolled plain kernels are instantiated in zc_rot_plain.cu (k_rotate<N,SRC,OUT16>) and zc_topolar.cu
+// (k_topolar<N,NTAIL,IN16>), the table-seeded ones in zc_rot_const.cu / zc_rot_nco.cu / zc_rot_dirs.cu: see zc_seedplan.h.
 
 // First vectoring stage from which y>>>(i+1) is provably 0 or -1 for every input, so that the short stage form
 // (zc_kernels.cuh: vec_step_tail) is the same function.  After the +-45 degree turn of rtl/topolar.v:122-152,
@@ -261,9 +222,10 @@ static int vec_tail_start(const zc_params *p, int neff) {
 	return neff;
 }
 
+// out16: xy_out receives one word per sample, (int16 o_xval) | (int16 o_yval) << 16 (zc_rotate_const_o16)
 template <int SRC>
 static int launch_rotate(const zc_params *p, CoreConsts &c, const uint32_t *phase, const int32_t *xy_in,
-		int32_t *xy_out, size_t n, int device, void *stream, uint32_t flags) {
+		int32_t *xy_out, size_t n, int device, void *stream, uint32_t flags, bool out16 = false) {
 	DeviceInfo di;
 	int rc = device_info(device, di);
 	if (rc != ZC_OK) return rc;
@@ -276,15 +238,16 @@ static int launch_rotate(const zc_params *p, CoreConsts &c, const uint32_t *phas
 	// non-wrapping arithmetic must be provably exact for this configuration, else the generic kernel does it all
 	const bool math_ok = !(flags & ZC_F_FORCE_GENERIC) && fast_path_is_exact(p) && c.neff >= 1 && c.neff <= 32;
 	// the table kernels move 4-byte phases and 8-byte (x,y) pairs; the plain fast kernel moves 16-byte vectors
-	const bool pair_ok = aligned8(xy_out) && (!has_xy || aligned8(xy_in));
+	const bool pair_ok = (out16 || aligned8(xy_out)) && (!has_xy || aligned8(xy_in));
+	const size_t ow_ = out16 ? 1 : 2;		// output words per sample
 	const bool vec_ok = aligned16(xy_out) && (!has_phase || aligned16(phase)) && (!has_xy || aligned16(xy_in));
 	size_t done = 0;
 	if (math_ok && pair_ok && !(flags & ZC_F_NO_SEED) && (!p->seq || angles_all_live(p, c.neff))) {
 		int launched = 0;
-		if constexpr (SRC == SRC_XY || SRC == SRC_MIX)
-			rc = dirs_rotate_try<SRC>(p, c, phase, xy_in, xy_out, n, device, di.sms, st, flags, done, launched);
-		else
-			rc = seeded_rotate_try<SRC>(p, c, phase, xy_out, n, device, di.sms, st, flags, done, launched);
+		if constexpr (SRC == SRC_XY) rc = dirs_rotate_xy(p, c, phase, xy_in, xy_out, n, device, di.sms, st, flags, done, launched);
+		else if constexpr (SRC == SRC_MIX) rc = dirs_rotate_mix(p, c, xy_in, xy_out, n, device, di.sms, st, flags, done, launched);
+		else if constexpr (SRC == SRC_NCO) rc = seeded_rotate_nco(p, c, xy_out, n, device, di.sms, st, flags, done, launched);
+		else rc = seeded_rotate_const(p, c, phase, xy_out, out16, n, device, di.sms, st, flags, done, launched);
 		if (rc != ZC_OK) return rc;
 		g_launches.fetch_add((uint64_t)launched, std::memory_order_relaxed);
 	}
@@ -293,9 +256,9 @@ static int launch_rotate(const zc_params *p, CoreConsts &c, const uint32_t *phas
 		if (groups) {
 			CoreConsts t = c;
 			t.nco_n0 = c.nco_n0 + (uint32_t)done;
-			RotTable<SRC, 32>::launch(c.neff, grid_for(groups, di, 16), st,
+			launch_rotate_plain(SRC, out16, c.neff, grid_for(groups, di, 16), st,
 				(const int4 *)(phase ? phase + done : nullptr), (const int4 *)(xy_in ? xy_in + 2 * done : nullptr),
-				(int4 *)(xy_out + 2 * done), groups, t);
+				(int4 *)(xy_out + ow_ * done), groups, t);
 			if ((rc = post_launch("k_rotate")) != ZC_OK) return rc;
 			done += groups * 4;
 		}
@@ -306,17 +269,19 @@ static int launch_rotate(const zc_params *p, CoreConsts &c, const uint32_t *phas
 		const size_t rest = n - done;
 		k_rotate_generic<SRC><<<grid_for(rest, di, 16), 256, 0, st>>>(
 			phase ? phase + done : nullptr, xy_in ? xy_in + 2 * done : nullptr,
-			xy_out + 2 * done, rest, t);
+			xy_out + ow_ * done, rest, t, out16 ? 1 : 0);
 		if ((rc = post_launch("k_rotate_generic")) != ZC_OK) return rc;
 	}
 	return ZC_OK;
 }
 
+// in16: xy_in holds one word per sample, (int16 i_xval) | (int16 i_yval) << 16 (zc_topolar_i16)
 static int launch_topolar(const zc_params *p, const int32_t *xy_in, int32_t *mag, uint32_t *phase,
-		size_t n, int device, void *stream, uint32_t flags) {
+		size_t n, int device, void *stream, uint32_t flags, bool in16 = false) {
 	int rc = check_params(p, ZC_MODE_R2P);
 	if (rc != ZC_OK) return rc;
 	if (n && (!xy_in || !mag || !phase)) return set_error(ZC_EINVAL, "NULL buffer");
+	if (in16 && p->iw > 16) return set_error(ZC_ERANGE, "packed int16 inputs need IW <= 16 (IW=%d)", p->iw);
 	DeviceInfo di;
 	if ((rc = device_info(device, di)) != ZC_OK) return rc;
 	if (n == 0) return ZC_OK;
@@ -332,7 +297,7 @@ static int launch_topolar(const zc_params *p, const int32_t *xy_in, int32_t *mag
 		const size_t groups = n / 4;
 		if (groups) {
 			const int ntail = (flags & ZC_F_NO_TAIL) ? 0 : c.neff - vec_tail_start(p, c.neff);
-			VecTable<32>::launch(c.neff, ntail, grid_for(groups, di, 16), st, (const int4 *)xy_in, (int4 *)mag,
+			launch_topolar_plain(in16, c.neff, ntail, grid_for(groups, di, 16), st, (const int4 *)xy_in, (int4 *)mag,
 				(int4 *)phase, groups, c);
 			if ((rc = post_launch("k_topolar")) != ZC_OK) return rc;
 			done = groups * 4;
@@ -340,8 +305,8 @@ static int launch_topolar(const zc_params *p, const int32_t *xy_in, int32_t *mag
 	}
 	if (done < n) {
 		const size_t rest = n - done;
-		k_topolar_generic<<<grid_for(rest, di, 16), 256, 0, st>>>(xy_in + 2 * done, mag + done,
-			phase + done, rest, c);
+		k_topolar_generic<<<grid_for(rest, di, 16), 256, 0, st>>>(xy_in + (in16 ? 1 : 2) * done, mag + done,
+			phase + done, rest, c, in16 ? 1 : 0);
 		if ((rc = post_launch("k_topolar_generic")) != ZC_OK) return rc;
 	}
 	return ZC_OK;
@@ -374,22 +339,18 @@ static int launch_lut(int pw, int ow, const uint32_t *tbl, const uint32_t *phase
 		// phases (a sweep) keep the L2 kernel, which then streams at the HBM copy peak; scattered ones take shared memory.
 		static const int smem_mode = std::getenv("ZCORDIC_LUT_SMEM") ? std::atoi(std::getenv("ZCORDIC_LUT_SMEM")) : 1;
 		const bool fits = n >= ((size_t)1 << 22) && smem <= 200 * 1024 && (QUARTER ? ow <= 25 : ow <= 16);
-		int *gate = nullptr;
-		if (smem_mode == 1 && fits) {
-			if ((rc = gate_slot(device, &gate)) != ZC_OK) return rc;
-			k_seed_probe<<<1, 256, 0, st>>>(phase32, n, 0, (int)(1u << (pw < 2 ? 30 : (32 - pw > 30 ? 30 : 32 - pw))), gate);
-			if ((rc = post_launch("k_seed_probe")) != ZC_OK) return rc;
-		}
+		// both kernels evaluate the same probe of the same phases (zc_kernels.cuh: probe_local) and exactly one proceeds
+		const int probe_lim = (smem_mode == 1 && fits) ? (int)(1u << (pw < 2 ? 30 : (32 - pw > 30 ? 30 : 32 - pw))) : -1;
 		if (smem_mode != 2 || !fits) {
-			k_lut<QUARTER><<<grid_for(groups, di, 32), 256, 0, st>>>((const int4 *)phase32, (int4 *)out, tbl, groups, c, gate);
+			k_lut<QUARTER><<<grid_for(groups, di, 32), 256, 0, st>>>((const int4 *)phase32, (int4 *)out, tbl, groups, c, probe_lim);
 			if ((rc = post_launch("k_lut")) != ZC_OK) return rc;
 		}
 		if (smem_mode != 0 && fits) {
-			typedef void (*kern_t)(const int4 *, int4 *, const uint32_t *, size_t, const LutConsts, const int *);
+			typedef void (*kern_t)(const int4 *, int4 *, const uint32_t *, size_t, const LutConsts, int);
 			kern_t kern = hi8 ? (kern_t)k_lut_smem<QUARTER, true> : (kern_t)k_lut_smem<QUARTER, false>;
 			cudaError_t e = ensure_dynamic_smem((const void *)kern, smem);
 			if (e != cudaSuccess) return set_error(ZC_ECUDA, "k_lut_smem shared memory: %s", cudaGetErrorString(e));
-			kern<<<di.sms, 1024, smem, st>>>((const int4 *)phase32, (int4 *)out, tbl, groups, c, gate);
+			kern<<<di.sms, 1024, smem, st>>>((const int4 *)phase32, (int4 *)out, tbl, groups, c, probe_lim);
 			if ((rc = post_launch("k_lut_smem")) != ZC_OK) return rc;
 		}
 		done = groups * 4;
@@ -404,7 +365,17 @@ static int launch_lut(int pw, int ow, const uint32_t *tbl, const uint32_t *phase
 
 // ---- quadtbl ------------------------------------------------------------------------------------
 // Device copies of coefficient tables, keyed by content (the zc_quadtbl is caller memory).
-struct QtDevTable { int device; uint64_t hash; int ntbl; std::shared_ptr<void> dev; bool nowrap; uint64_t stamp; };
+// The key is the whole configuration the cached rows and the cached `nowrap` verdict depend on: the widths that decide
+// the sign extension (CBITS/LBITS/QBITS), the ones the wrap proof walks (PW via DXBITS, LBITS, CBITS, WW) and the words.
+struct QtKey {
+	int32_t pw, ww, lgtbl, dxbits, cbits, lbits, qbits;
+	std::vector<uint32_t> words;		// ctbl | ltbl | qtbl, 2^LGTBL each
+	bool operator==(const QtKey &o) const {
+		return pw == o.pw && ww == o.ww && lgtbl == o.lgtbl && dxbits == o.dxbits && cbits == o.cbits &&
+			lbits == o.lbits && qbits == o.qbits && words == o.words;
+	}
+};
+struct QtDevTable { int device; uint64_t hash; QtKey key; std::shared_ptr<void> dev; bool nowrap; uint64_t stamp; };
 static std::mutex g_qt_mu;
 static std::vector<QtDevTable> g_qt_cache;
 static uint64_t g_qt_clock = 0;
@@ -413,9 +384,20 @@ static uint64_t qt_hash(const zc_quadtbl *q) {
 	uint64_t h = 1469598103934665603ull;
 	auto mix = [&](uint32_t w) { h = (h ^ w) * 1099511628211ull; };
 	const int n = 1 << q->lgtbl;
-	mix((uint32_t)q->lgtbl);
+	mix((uint32_t)q->lgtbl); mix((uint32_t)q->pw); mix((uint32_t)q->ww); mix((uint32_t)q->dxbits);
+	mix((uint32_t)q->cbits); mix((uint32_t)q->lbits); mix((uint32_t)q->qbits);
 	for (int k = 0; k < n; k++) { mix(q->ctbl[k]); mix(q->ltbl[k]); mix(q->qtbl[k]); }
 	return h;
+}
+
+static QtKey qt_key(const zc_quadtbl *q) {
+	QtKey k{q->pw, q->ww, q->lgtbl, q->dxbits, q->cbits, q->lbits, q->qbits, {}};
+	const size_t n = (size_t)1 << q->lgtbl;
+	k.words.reserve(3 * n);
+	k.words.insert(k.words.end(), q->ctbl, q->ctbl + n);
+	k.words.insert(k.words.end(), q->ltbl, q->ltbl + n);
+	k.words.insert(k.words.end(), q->qtbl, q->qtbl + n);
+	return k;
 }
 
 static inline int32_t sext32(uint32_t w, int bits) { return (int32_t)(w << (32 - bits)) >> (32 - bits); }
@@ -426,9 +408,10 @@ static inline int32_t sext32(uint32_t w, int bits) { return (int32_t)(w << (32 -
 static int qt_device_tables(const zc_quadtbl *q, int device, cudaStream_t st, std::shared_ptr<void> *out, bool *nowrap) {
 	const uint64_t h = qt_hash(q);
 	const int n = 1 << q->lgtbl;
+	QtKey key = qt_key(q);
 	std::lock_guard<std::mutex> lk(g_qt_mu);
 	for (QtDevTable &e : g_qt_cache)
-		if (e.device == device && e.hash == h && e.ntbl == n) {
+		if (e.device == device && e.hash == h && e.key == key) {	// a hash hit is confirmed word for word
 			e.stamp = ++g_qt_clock; *out = e.dev; *nowrap = e.nowrap;
 			return ZC_OK;
 		}
@@ -466,7 +449,7 @@ static int qt_device_tables(const zc_quadtbl *q, int device, cudaStream_t st, st
 		for (size_t k = 1; k < g_qt_cache.size(); k++) if (g_qt_cache[k].stamp < g_qt_cache[victim].stamp) victim = k;
 		g_qt_cache.erase(g_qt_cache.begin() + victim);
 	}
-	g_qt_cache.push_back(QtDevTable{device, h, n, std::shared_ptr<void>(dev, DevFree()), safe, ++g_qt_clock});
+	g_qt_cache.push_back(QtDevTable{device, h, std::move(key), std::shared_ptr<void>(dev, DevFree()), safe, ++g_qt_clock});
 	*out = g_qt_cache.back().dev; *nowrap = safe;
 	return ZC_OK;
 }
@@ -605,7 +588,13 @@ static int host_pipeline(int device, size_t n, const Lane in[2], const Lane out[
 	DeviceScope scope;
 	if ((rc = scope.enter(device)) != ZC_OK) return rc;
 	constexpr int NBUF = PIPE_NBUF;
-	const size_t chunk = (n < ((size_t)4 << 20)) ? ((n + 3) & ~(size_t)3) : ((size_t)4 << 20);
+	// samples per pipeline chunk: 4 Mi by default; ZCORDIC_HOST_CHUNK_LG2 (20..28) for sweeps of it
+	static const size_t chunk_max = [] {
+		const char *e = std::getenv("ZCORDIC_HOST_CHUNK_LG2");
+		const int lg = e ? std::atoi(e) : 22;
+		return (size_t)1 << (lg < 20 ? 20 : lg > 28 ? 28 : lg);
+	}();
+	const size_t chunk = (n < chunk_max) ? ((n + 3) & ~(size_t)3) : chunk_max;
 	const size_t sizes[4] = {in[0].bytes_per_sample * chunk, in[1].bytes_per_sample * chunk,
 		out[0].bytes_per_sample * chunk, out[1].bytes_per_sample * chunk};
 	size_t per_buf = 0;
@@ -755,6 +744,11 @@ int zc_topolar_tail_stages(const zc_params *p) {
 	t &= ~1;
 	return t > 16 ? 16 : t;
 }
+long long zc_nco_comb_run(const zc_params *p, uint32_t step, size_t n) {
+	int rc = check_params(p, ZC_MODE_P2R);
+	if (rc != ZC_OK) return rc;
+	return nco_comb_run(p, step, n);
+}
 int zc_clocks_per_output(const zc_params *p) {
 	if (!p) return set_error(ZC_EINVAL, "NULL zc_params");
 	if (!p->seq) return 1;
@@ -810,6 +804,25 @@ int zc_topolar(const zc_params *p, const int32_t *xy_in, int32_t *mag, uint32_t 
 	return launch_topolar(p, xy_in, mag, phase, n, device, stream, ZC_F_DEFAULT);
 }
 
+int zc_rotate_const_o16(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int16_t *xy16,
+		size_t n, int device, void *stream) {
+	int rc = check_params(p, ZC_MODE_P2R);
+	if (rc != ZC_OK) return rc;
+	if (p->ow > 16) return set_error(ZC_ERANGE, "packed int16 outputs need OW <= 16 (OW=%d)", p->ow);
+	if (n && (!phase || !xy16)) return set_error(ZC_EINVAL, "NULL buffer");
+	if (reinterpret_cast<uintptr_t>(xy16) & 3u) return set_error(ZC_EINVAL, "xy16 must be 4-byte aligned");
+	CoreConsts c;
+	fill_consts(p, c);
+	fill_const_xy(p, x0, y0, c);
+	return launch_rotate<SRC_CONST>(p, c, phase, nullptr, reinterpret_cast<int32_t *>(xy16), n, device, stream, ZC_F_DEFAULT, true);
+}
+
+int zc_topolar_i16(const zc_params *p, const int16_t *xy16_in, int32_t *mag, uint32_t *phase, size_t n,
+		int device, void *stream) {
+	if (reinterpret_cast<uintptr_t>(xy16_in) & 3u) return set_error(ZC_EINVAL, "xy16_in must be 4-byte aligned");
+	return launch_topolar(p, reinterpret_cast<const int32_t *>(xy16_in), mag, phase, n, device, stream, ZC_F_DEFAULT, true);
+}
+
 int zc_nco_rotate_ex(const zc_params *p, int32_t x0, int32_t y0, uint32_t phase0, uint32_t step,
 		uint64_t n0, int32_t *xy, size_t n, int device, void *stream, uint32_t flags) {
 	int rc = check_params(p, ZC_MODE_P2R);
@@ -851,20 +864,6 @@ int zc_quadtbl_sin(const zc_quadtbl *q, const uint32_t *phase32, int32_t *out, s
 }
 
 // ---- host buffers --------------------------------------------------------------------------
-void *zc_host_alloc(size_t bytes) {
-	void *p = nullptr;
-	cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
-	if (e != cudaSuccess) {
-		cudaGetLastError();
-		set_error(ZC_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
-		return nullptr;
-	}
-	return p;
-}
-void zc_host_free(void *ptr) {
-	if (ptr) cudaFreeHost(ptr);
-}
-
 int zc_rotate_const_host(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int32_t *xy,
 		size_t n, int device) {
 	int rc = check_params(p, ZC_MODE_P2R);
@@ -875,6 +874,34 @@ int zc_rotate_const_host(const zc_params *p, int32_t x0, int32_t y0, const uint3
 	return host_pipeline(device, n, in, out,
 		[&](size_t, size_t cnt, char *i0, char *, char *o0, char *, cudaStream_t st) {
 			return zc_rotate_const_ex(p, x0, y0, (const uint32_t *)i0, (int32_t *)o0, cnt, device, st, ZC_F_DEFAULT);
+		});
+}
+
+int zc_rotate_const_o16_host(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int16_t *xy16,
+		size_t n, int device) {
+	int rc = check_params(p, ZC_MODE_P2R);
+	if (rc != ZC_OK) return rc;
+	if (p->ow > 16) return set_error(ZC_ERANGE, "packed int16 outputs need OW <= 16 (OW=%d)", p->ow);
+	if (n && (!phase || !xy16)) return set_error(ZC_EINVAL, "NULL buffer");
+	const Lane in[2] = {{4, (const char *)phase, nullptr}, {0, nullptr, nullptr}};
+	const Lane out[2] = {{4, nullptr, (char *)xy16}, {0, nullptr, nullptr}};
+	return host_pipeline(device, n, in, out,
+		[&](size_t, size_t cnt, char *i0, char *, char *o0, char *, cudaStream_t st) {
+			return zc_rotate_const_o16(p, x0, y0, (const uint32_t *)i0, (int16_t *)o0, cnt, device, st);
+		});
+}
+
+int zc_topolar_i16_host(const zc_params *p, const int16_t *xy16_in, int32_t *mag, uint32_t *phase, size_t n,
+		int device) {
+	int rc = check_params(p, ZC_MODE_R2P);
+	if (rc != ZC_OK) return rc;
+	if (p->iw > 16) return set_error(ZC_ERANGE, "packed int16 inputs need IW <= 16 (IW=%d)", p->iw);
+	if (n && (!xy16_in || !mag || !phase)) return set_error(ZC_EINVAL, "NULL buffer");
+	const Lane in[2] = {{4, (const char *)xy16_in, nullptr}, {0, nullptr, nullptr}};
+	const Lane out[2] = {{4, nullptr, (char *)mag}, {4, nullptr, (char *)phase}};
+	return host_pipeline(device, n, in, out,
+		[&](size_t, size_t cnt, char *i0, char *, char *o0, char *o1, cudaStream_t st) {
+			return zc_topolar_i16(p, (const int16_t *)i0, (int32_t *)o0, (uint32_t *)o1, cnt, device, st);
 		});
 }
 

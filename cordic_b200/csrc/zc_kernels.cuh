@@ -151,6 +151,8 @@ __device__ __forceinline__ void quarter_turn(int q, int ex, int ey, int &x, int 
 	y = (q & 2) ? -b : b;
 }
 
+__device__ __forceinline__ int pack16(int lo, int hi) { return (int)(((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16)); }
+
 __device__ __forceinline__ int4 ldg_stream(const int4 *p) {
 	int4 r;
 	asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
@@ -163,7 +165,8 @@ __device__ __forceinline__ void stg_stream(int4 *p, const int4 v) {
 }
 
 // ---- rotation mode, fast path: 4 samples per thread, 128-bit loads/stores ------------------
-template <int NEFF, int SRC>
+// OUT16: one output word per sample, (int16 o_xval) | (int16 o_yval) << 16 -- the packed ports of a core with OW <= 16
+template <int NEFF, int SRC, bool OUT16 = false>
 __global__ void __launch_bounds__(256)
 k_rotate(const int4 *__restrict__ phase4, const int4 *__restrict__ xyin4,
 		int4 *__restrict__ xyout4, size_t ngroups, const __grid_constant__ CoreConsts c) {
@@ -209,21 +212,34 @@ k_rotate(const int4 *__restrict__ phase4, const int4 *__restrict__ xyin4,
 			ox[s] = round_out(x[s], c);
 			oy[s] = round_out(y[s], c);
 		}
-		stg_stream(xyout4 + 2 * g, make_int4(ox[0], oy[0], ox[1], oy[1]));
-		stg_stream(xyout4 + 2 * g + 1, make_int4(ox[2], oy[2], ox[3], oy[3]));
+		if (OUT16) {
+			stg_stream(xyout4 + g, make_int4(pack16(ox[0], oy[0]), pack16(ox[1], oy[1]), pack16(ox[2], oy[2]), pack16(ox[3], oy[3])));
+		} else {
+			stg_stream(xyout4 + 2 * g, make_int4(ox[0], oy[0], ox[1], oy[1]));
+			stg_stream(xyout4 + 2 * g + 1, make_int4(ox[2], oy[2], ox[3], oy[3]));
+		}
 	}
 }
 
 // ---- vectoring mode, fast path ---------------------------------------------------------------
 // NTAIL: how many of the last stages run in the short form (vec_step_tail)
-template <int NEFF, int NTAIL>
+// IN16: one input word per sample, (int16 i_xval) | (int16 i_yval) << 16 -- the packed ports of a core with IW <= 16
+template <int NEFF, int NTAIL, bool IN16 = false>
 __global__ void __launch_bounds__(256)
 k_topolar(const int4 *__restrict__ xyin4, int4 *__restrict__ mag4, int4 *__restrict__ ph4,
 		size_t ngroups, const __grid_constant__ CoreConsts c) {
 	const size_t stride = (size_t)gridDim.x * blockDim.x;
 	for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
-		const int4 a = ldg_stream(xyin4 + 2 * g), b = ldg_stream(xyin4 + 2 * g + 1);
-		const int raw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+		int raw[8];
+		if (IN16) {
+			const int4 a = ldg_stream(xyin4 + g);
+			const int w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+			for (int s = 0; s < 4; s++) { raw[2 * s] = w[s]; raw[2 * s + 1] = w[s] >> 16; }	// bits above IW are shifted out below
+		} else {
+			const int4 a = ldg_stream(xyin4 + 2 * g), b = ldg_stream(xyin4 + 2 * g + 1);
+			raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w; raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
+		}
 		int om[4], op[4];
 #pragma unroll
 		for (int s = 0; s < 4; s++) {
@@ -249,216 +265,29 @@ k_topolar(const int4 *__restrict__ xyin4, int4 *__restrict__ mag4, int4 *__restr
 	}
 }
 
-// ---- generic kernels: any configuration, any alignment, WW-bit wrap modelled ----------------
-__device__ __forceinline__ int wrapw(int v, int wsh) { return (int)((uint32_t)v << wsh) >> wsh; }
-
-template <int SRC>
-__global__ void __launch_bounds__(256)
-k_rotate_generic(const uint32_t *__restrict__ phase, const int32_t *__restrict__ xyin,
-		int32_t *__restrict__ xyout, size_t n, const __grid_constant__ CoreConsts c) {
-	const size_t stride = (size_t)gridDim.x * blockDim.x;
-	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-		uint32_t P;
-		if (SRC == SRC_NCO || SRC == SRC_MIX) {
-			const uint32_t keep = ~((1u << c.pshift) - 1u);
-			P = (c.nco_phase0 + (c.nco_n0 + (uint32_t)i) * c.nco_step) & keep;
-		} else {
-			P = phase[i] << c.pshift;
-		}
-		int p;
-		const int q = octant(P, p);
-		int x, y;
-		if (SRC == SRC_XY || SRC == SRC_MIX) {
-			const int ex = (xyin[2 * i] << c.in_shl) >> c.in_shr;
-			const int ey = (xyin[2 * i + 1] << c.in_shl) >> c.in_shr;
-			quarter_turn(q, ex, ey, x, y);
-			x = wrapw(x, c.wsh); y = wrapw(y, c.wsh);
-		} else {
-			x = c.cx[q]; y = c.cy[q];
-		}
-		for (int k = 0; k < c.neff; k++) {
-			const int sh = (k + 1 > 31) ? 31 : (k + 1);
-			const int sy = y >> sh, sx = x >> sh;
-			const uint32_t ux = (uint32_t)x, uy = (uint32_t)y;	// unsigned: the sums may wrap (WW up to 32)
-			const uint32_t ak = (k < 32) ? c.pa[k] : 0u;		// sequential cores iterate past the last angle
-			if (p < 0) {
-				x = wrapw((int)(ux + (uint32_t)sy), c.wsh); y = wrapw((int)(uy - (uint32_t)sx), c.wsh);
-				p = (int)((uint32_t)p + ak);
-			} else {
-				x = wrapw((int)(ux - (uint32_t)sy), c.wsh); y = wrapw((int)(uy + (uint32_t)sx), c.wsh);
-				p = (int)((uint32_t)p - ak);
-			}
-		}
-		const int bx = (x >> c.D) & c.do_round, by = (y >> c.D) & c.do_round;
-		xyout[2 * i] = wrapw((int)((uint32_t)x + (uint32_t)c.rc + (uint32_t)bx), c.wsh) >> c.D;
-		xyout[2 * i + 1] = wrapw((int)((uint32_t)y + (uint32_t)c.rc + (uint32_t)by), c.wsh) >> c.D;
+enum { PROBE_LOCAL = 0, PROBE_SCATTERED = 2 };
+// ---- probe: are neighbouring samples' phases neighbours? ------------------------------------------------
+// 8 windows of 32 consecutive samples spread over the stream; a pair counts as local when the circular phase
+// difference is at most `lim` (one phase LSB for the CORDIC tables: a sweep or a slow NCO, whose word rows are
+// conflict-free; one table entry, in 32-bit phase units, for the LUT cores), and the verdict is PROBE_LOCAL when at least
+// 7 pairs in 8 are, PROBE_SCATTERED otherwise.
+// Called by EVERY thread of a CTA of at least 256 threads (it contains a barrier).  The verdict is a pure function of
+// (phase[], n, pshift, lim): the two kernels of an auto-selected call evaluate it independently, CTA by CTA, and always
+// agree -- exactly one of them processes the batch, whatever other streams or graph replays are doing.  (Round 1 passed
+// the verdict through a reused ring of device words written by a separate probe kernel; a concurrent call that was
+// handed the same slot could flip it between the two kernels' reads, and then neither ran.)
+__device__ __forceinline__ int probe_local(const uint32_t *__restrict__ phase, size_t n, int pshift, int lim) {
+	const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31u;
+	int local = 0;
+	if (threadIdx.x < 256u && n >= 34) {
+		size_t off = ((n / 8) * w) & ~(size_t)31;
+		if (off + 33 > n) off = 0;
+		const uint32_t a = phase[off + l], b = phase[off + l + 1];
+		const int d = (int)((b - a) << pshift) >> pshift;
+		local = (d >= -lim && d <= lim);
 	}
-}
-
-__global__ void __launch_bounds__(256)
-k_topolar_generic(const int32_t *__restrict__ xyin, int32_t *__restrict__ mag,
-		uint32_t *__restrict__ phout, size_t n, const __grid_constant__ CoreConsts c) {
-	const size_t stride = (size_t)gridDim.x * blockDim.x;
-	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-		const int ex = (xyin[2 * i] << c.in_shl) >> c.in_shr;
-		const int ey = (xyin[2 * i + 1] << c.in_shl) >> c.in_shr;
-		const int xn = ex < 0, yn = ey < 0;
-		int x, y;
-		const uint32_t ax = (uint32_t)ex, ay = (uint32_t)ey;
-		if (!xn && yn)      { x = (int)(ax - ay);  y = (int)(ax + ay); }
-		else if (xn && !yn) { x = (int)(ay - ax);  y = (int)(0u - ax - ay); }
-		else if (xn && yn)  { x = (int)(0u - ax - ay); y = (int)(ax - ay); }
-		else                { x = (int)(ax + ay);  y = (int)(ay - ax); }
-		x = wrapw(x, c.wsh); y = wrapw(y, c.wsh);
-		uint32_t ph = c.e_phase[(xn << 1) | yn];
-		for (int k = 0; k < c.neff; k++) {
-			const int sh = (k + 1 > 31) ? 31 : (k + 1);
-			const int sy = y >> sh, sx = x >> sh;
-			const uint32_t ux = (uint32_t)x, uy = (uint32_t)y;
-			const uint32_t ak = (k < 32) ? c.pa[k] : 0u;
-			if (y < 0) {
-				x = wrapw((int)(ux - (uint32_t)sy), c.wsh); y = wrapw((int)(uy + (uint32_t)sx), c.wsh); ph -= ak;
-			} else {
-				x = wrapw((int)(ux + (uint32_t)sy), c.wsh); y = wrapw((int)(uy - (uint32_t)sx), c.wsh); ph += ak;
-			}
-		}
-		const int b = (x >> c.D) & c.do_round;
-		mag[i] = wrapw((int)((uint32_t)x + (uint32_t)c.rc + (uint32_t)b), c.wsh) >> c.D;
-		phout[i] = ph >> c.pshift;
-	}
-}
-
-// ---- LUT cores (rtl/sintable.v:71-75, rtl/quarterwav.v:92-109) --------------------------------
-struct LutConsts {
-	int32_t pshift;		// 32-pw
-	int32_t osh;		// 32-ow : sign-extension of the OW-bit table word
-	uint32_t lowmask;	// quarterwav: 2^(pw-2)-1
-	int32_t pw;
-};
-
-// which LUT kernel a probed batch goes to (zc_seeded.cuh: k_seed_probe writes TD_TABLE = 0 for neighbouring phases,
-// TD_PACKED = 2 for scattered ones)
-enum { LUT_GATE_L2 = 0, LUT_GATE_SMEM = 2 };
-#ifndef ZC_LUT_MLP
-#define ZC_LUT_MLP 2
-#endif
-constexpr int LUT_MLP = ZC_LUT_MLP;
-
-template <bool QUARTER>
-__device__ __forceinline__ int lut_one(uint32_t phase32, const uint32_t *__restrict__ tbl, const LutConsts &c) {
-	const uint32_t ip = phase32 >> c.pshift;
-	if (!QUARTER) {
-		return (int)(__ldg(tbl + ip) << c.osh) >> c.osh;
-	} else {
-		const uint32_t fold = 0u - ((ip >> (c.pw - 2)) & 1u);	// all-ones when i_phase[PW-2]
-		const uint32_t idx = (ip ^ fold) & c.lowmask;
-		const int neg = -(int)((ip >> (c.pw - 1)) & 1u);	// -1 when i_phase[PW-1]
-		const int v = (int)__ldg(tbl + idx);
-		return (((v ^ neg) - neg) << c.osh) >> c.osh;
-	}
-}
-
-template <bool QUARTER>
-__global__ void __launch_bounds__(256)
-k_lut(const int4 *__restrict__ phase4, int4 *__restrict__ out4, const uint32_t *__restrict__ tbl,
-		size_t ngroups, const __grid_constant__ LutConsts c, const int *__restrict__ gate) {
-	if (gate != nullptr && *gate != LUT_GATE_L2) return;	// a probe kernel chose the shared-memory kernel for this batch
-	const size_t stride = (size_t)gridDim.x * blockDim.x;
-	for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
-		const int4 pv = ldg_stream(phase4 + g);
-		int4 o;
-		o.x = lut_one<QUARTER>((uint32_t)pv.x, tbl, c);
-		o.y = lut_one<QUARTER>((uint32_t)pv.y, tbl, c);
-		o.z = lut_one<QUARTER>((uint32_t)pv.z, tbl, c);
-		o.w = lut_one<QUARTER>((uint32_t)pv.w, tbl, c);
-		stg_stream(out4 + g, o);
-	}
-}
-
-// ---- LUT cores with the table resident in shared memory ---------------------------------------------------
-// k_lut gathers from a table that lives in L2 (512 KB for the shipped sintable): ideal for sweeps (1.00 / 0.97 of the
-// HBM copy peak), an L2 gather per sample for scattered phases (286 / 434 Gsamples/s).  Here every CTA first stages a lossless compressed copy of the
-// table in shared memory and then looks every sample up there, whatever the phase pattern:
-//   sintable   (rtl/sintable.v:71-75)   the second half-wave is the negated first one -- IF the table really is like that;
-//              the staging loop checks tbl[i + N/2] == -tbl[i] and 16-bit range entry by entry (the generator's tables
-//              pass: C truncation toward zero is odd-symmetric, sw/sintable.cpp:156-168), and stores N/2 int16;
-//   quarterwav (rtl/quarterwav.v:92-109) the words are magnitudes below 2^16 (u16) or 2^24 (u16 + u8, HI8).
-// The table is the caller's memory and may hold anything: when a check fails the CTA (every CTA reaches the same
-// verdict, they all read the whole table) serves its samples from global memory exactly as k_lut does.
-template <bool QUARTER, bool HI8>
-__global__ void __launch_bounds__(1024, 1)
-k_lut_smem(const int4 *__restrict__ phase4, int4 *__restrict__ out4, const uint32_t *__restrict__ tbl,
-		size_t ngroups, const __grid_constant__ LutConsts c, const int *__restrict__ gate) {
-	if (gate != nullptr && *gate != LUT_GATE_SMEM) return;
-	extern __shared__ __align__(16) unsigned char lsm[];
-	const uint32_t nent = QUARTER ? (1u << (c.pw - 2)) : (1u << (c.pw - 1));
-	unsigned short *const lo = reinterpret_cast<unsigned short *>(lsm);
-	unsigned char *const hi = lsm + 2 * (size_t)nent;
-	int ok = 1;
-	for (uint32_t i = threadIdx.x; i < nent; i += blockDim.x) {
-		if (!QUARTER) {
-			const int v = (int)(tbl[i] << c.osh) >> c.osh, w = (int)(tbl[i + nent] << c.osh) >> c.osh;
-			ok &= (w == -v) & (v >= -32768) & (v <= 32767);
-			lo[i] = (unsigned short)v;
-		} else {
-			const uint32_t v = tbl[i];
-			ok &= HI8 ? (v < (1u << 24)) : (v < (1u << 16));
-			lo[i] = (unsigned short)v;
-			if (HI8) hi[i] = (unsigned char)(v >> 16);
-		}
-	}
-	ok = __syncthreads_and(ok);
-	auto one = [&](uint32_t phase32) -> int {
-		const uint32_t ip = phase32 >> c.pshift;
-		if (!QUARTER) {
-			const int neg = -(int)(ip >> (c.pw - 1));			// -1 in the second half-wave
-			const int v = (short)lo[ip & (nent - 1u)];
-			return (v ^ neg) - neg;
-		} else {
-			const uint32_t fold = 0u - ((ip >> (c.pw - 2)) & 1u);
-			const uint32_t idx = (ip ^ fold) & c.lowmask;
-			const int neg = -(int)((ip >> (c.pw - 1)) & 1u);
-			const int v = (int)(HI8 ? ((uint32_t)lo[idx] | ((uint32_t)hi[idx] << 16)) : (uint32_t)lo[idx]);
-			return (((v ^ neg) - neg) << c.osh) >> c.osh;
-		}
-	};
-	const size_t stride = (size_t)gridDim.x * blockDim.x;
-	size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (ok) {
-		// LUT_MLP 16-byte loads in flight per thread: one CTA of 1024 threads per SM has to cover HBM's latency alone
-		for (; g + (LUT_MLP - 1) * stride < ngroups; g += LUT_MLP * stride) {
-			int4 pv[LUT_MLP];
-#pragma unroll
-			for (int k = 0; k < LUT_MLP; k++) pv[k] = ldg_stream(phase4 + g + k * stride);
-#pragma unroll
-			for (int k = 0; k < LUT_MLP; k++)
-				stg_stream(out4 + g + k * stride, make_int4(one((uint32_t)pv[k].x), one((uint32_t)pv[k].y),
-					one((uint32_t)pv[k].z), one((uint32_t)pv[k].w)));
-		}
-		for (; g < ngroups; g += stride) {
-			const int4 pv = ldg_stream(phase4 + g);
-			stg_stream(out4 + g, make_int4(one((uint32_t)pv.x), one((uint32_t)pv.y), one((uint32_t)pv.z), one((uint32_t)pv.w)));
-		}
-	} else {
-		for (; g < ngroups; g += stride) {
-			const int4 pv = ldg_stream(phase4 + g);
-			int4 o;
-			o.x = lut_one<QUARTER>((uint32_t)pv.x, tbl, c);
-			o.y = lut_one<QUARTER>((uint32_t)pv.y, tbl, c);
-			o.z = lut_one<QUARTER>((uint32_t)pv.z, tbl, c);
-			o.w = lut_one<QUARTER>((uint32_t)pv.w, tbl, c);
-			stg_stream(out4 + g, o);
-		}
-	}
-}
-
-template <bool QUARTER>
-__global__ void __launch_bounds__(256)
-k_lut_scalar(const uint32_t *__restrict__ phase, int32_t *__restrict__ out,
-		const uint32_t *__restrict__ tbl, size_t n, const __grid_constant__ LutConsts c) {
-	const size_t stride = (size_t)gridDim.x * blockDim.x;
-	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-		out[i] = lut_one<QUARTER>(phase[i], tbl, c);
+	const int votes = __syncthreads_count(local);
+	return (votes * 8 >= 256 * 7) ? PROBE_LOCAL : PROBE_SCATTERED;
 }
 
 } // namespace zc

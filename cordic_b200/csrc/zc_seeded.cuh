@@ -27,12 +27,11 @@
 #ifndef ZC_SEEDED_CUH
 #define ZC_SEEDED_CUH
 
-#include "zc_internal.h"
-#include "zc_kernels.cuh"
+#include "zc_seedplan.h"
 
+#include <cmath>
 #include <cstring>
 #include <memory>
-#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -44,46 +43,6 @@ namespace zc {
 #ifndef ZC_XNEG_MASK
 #define ZC_XNEG_MASK 0x8888
 #endif
-constexpr int SEED_MAX_NS = 16;
-constexpr size_t SEED_MAX_BLOCKS = 0xF0000000u;	// the table kernels count 128-sample blocks in 32 bits (2^38.9 samples)
-constexpr size_t SEED_SMEM_LIMIT = 227 * 1024 - 64;	// opt-in maximum per CTA minus the mbarrier slot
-
-struct SeedConsts {
-	int32_t  M;		// stages folded into the table
-	uint32_t mul_q;		// 2^(32-PW): phase*mul_q + 2^29 puts the quarter turn in bits 31:30
-	uint32_t mul_u;		// 2^(34-PW): phase*mul_u + 2^31 left-justifies the reduced phase u (PW-2 bits)
-	int32_t  bsh;		// u_left >> bsh = bucket number (32-LB)
-	int32_t  ush;		// u_left >> ush = u << lgrow, u = the reduced phase in LSBs, offset binary
-	int32_t  rsh;		// (T1 entry + (u << lgrow)) >> rsh = interval number (lgW+lgrow)
-	int32_t  lgw;
-	uint32_t mul_r;		// 2^(32-PW-lgrow): TD byte offset * mul_r + res_bias = residual phase, left-justified
-	int32_t  lgrow;		// log2(bytes per TD row slot): every T1/TS entry is scaled by it
-	int32_t  res_bias;	// rmin << (32-PW)
-	float    rscale, rbias;	// float rounding: fma(2^23*1.5 + v, 2^-D, 2^23*1.5*(1-2^-D)) rounds v/2^D to nearest even
-	uint32_t off_ts, off_t2, off_td;	// byte offsets of the tables in shared memory
-	int32_t  td_plane;	// bytes per TD plane (nres*16)
-	uint32_t total_bytes;	// multiple of 16
-	int32_t  sh[SEED_MAX_NS];	// arithmetic shift of suffix stage j: min(M+j+1, 31)
-	uint32_t R;
-};
-
-// ---- setup kernel: the x/y table, by running the real stages --------------------------------------
-__global__ void k_seed_fill_xy(const uint32_t *__restrict__ rep_phase /* left-justified, one per interval */,
-		int2 *__restrict__ t2, uint32_t R, int M, const __grid_constant__ CoreConsts c) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= 4u * R) return;
-	const uint32_t rank = i >> 2, q = i & 3u;
-	int p = (int)rep_phase[rank];
-	int x = c.cx[q], y = c.cy[q];
-	for (int k = 0; k < M; k++) {
-		const int sh = (k + 1 > 31) ? 31 : (k + 1);
-		const int sy = y >> sh, sx = x >> sh;
-		if (p < 0) { x = x + sy; y = y - sx; p += (int)c.pa[k]; }
-		else       { x = x - sy; y = y + sx; p -= (int)c.pa[k]; }
-	}
-	t2[i] = make_int2(x, y);
-}
-
 enum { MA_NEG = 0, MA_XNEG = 1, MA_DP2A = 2 };
 __device__ __forceinline__ int dp2a_lo(int a, int b, int c) {
 	int r;
@@ -139,17 +98,7 @@ struct Suffix<NS, NS> {
 	static __device__ __forceinline__ void run_reg(int &, int &, int &, const CoreConsts &, const SeedConsts &) {}
 };
 
-enum { TD_TABLE = 0, TD_REGS = 1, TD_PACKED = 2, TD_TABLE_DP = 3 };
-// plan flavours: word TD + x/y table, byte TD + x/y table, byte TD + per-interval prefix directions (no x/y table), and
-// and the IDP.2A form of the first: word TD holding the multiplier words {0, d, 0, -d}.  (The byte flavours have no
-// IDP.2A form: storing the pair (-d, d) per stage and building the multiplier word with one PRMT saves the negation but
-// doubles the rows, and their scattered reads cost more than that: 320 vs 374 Gsamples/s for the constant-vector kernel
-// on random phases, 181 vs 195 for per-sample vectors -- measured, dropped.)
-enum { FL_WORDS = 0, FL_PACKED = 1, FL_DIRS = 2, FL_WORDS_DP = 3 };
-static inline bool fl_packed(int flavour) { return flavour == FL_PACKED || flavour == FL_DIRS; }
-static inline bool fl_dirs(int flavour) { return flavour == FL_DIRS; }
-constexpr int DIRS_M = 12;	// prefix depth of the FL_DIRS flavour (its kernel unrolls the byte indices)
-
+enum { TD_TABLE = PROBE_LOCAL, TD_REGS = 1, TD_PACKED = PROBE_SCATTERED, TD_TABLE_DP = 3 };
 // Sign-extends byte `b` of w with one PRMT (selector nibble 8|b replicates that byte's sign bit;
 // __byte_perm() masks the replicate bit off, hence the PTX).
 __device__ __forceinline__ int sext_byte(uint32_t w, int b) {
@@ -188,15 +137,40 @@ __device__ __forceinline__ int4 lds128(uint32_t addr) {
 // make it bank-conflict bound for scattered phases).  TD_PACKED: one signed byte per stage (a quarter of the
 // shared-memory traffic, one PRMT per stage to unpack): the better trade for scattered phases.  TD_REGS: the phase
 // recursion in registers (3 more issue slots per stage, no table traffic).
-template <int NS, int SRC, bool RF, int TDM>
+//
+// MAP: which samples a lane takes.
+//   MAP_BLOCK  a warp owns 128 consecutive samples per iteration, lane l takes l, l+32, l+64, l+96 (see the file header).
+//   MAP_COMB   (NCO only) for a phase accumulator whose step scatters consecutive samples over the circle.  The host
+//              finds a run length K with K*step = delta (mod 2^32), |delta| about one phase LSB or less (comb_search).
+//              The stream is cut into tiles of 8K samples; lane l = (a = l & 7, b = l >> 3) works in run a of the tile,
+//              [a*K, (a+1)*K), and per iteration the warp takes one 16-sample chunk of each of the 8 runs: lane (a, b)
+//              takes samples 16m + 2b + {0, 1, 8, 9} of run a.  At every instruction the 8 lanes of a quarter-warp (the
+//              unit in which a 128-bit shared-memory read is served) then hold phases delta apart -- neighbouring or equal
+//              table rows, conflict-free like a sweep -- while the four lanes b = 0..3 of a run write 64 contiguous bytes
+//              per store (two full sectors), 128 per chunk.  Round 1's comb gave every LANE its own run and died on
+//              scattered 8/16-byte stores; here a store instruction touches 8 lines instead of 4.
+// OUT16: outputs packed as (int16 o_xval, int16 o_yval) in one word (cores with OW <= 16; zc_rotate_const_o16).
+enum { MAP_BLOCK = 0, MAP_COMB = 1 };
+struct CombConsts {
+	uint32_t K;		// run length (even)
+	uint32_t cpr;		// 16-sample chunks per run: ceil(K/16)
+	uint32_t nunits;	// tiles * cpr
+	uint32_t tile;		// 8*K samples
+	uint32_t tile_step;	// 8*K*step (mod 2^32)
+	uint32_t chunk_step;	// 16*step
+	uint32_t dt, dm;	// (number of warps in the grid) / cpr and % cpr: how (tile, chunk) advances per iteration
+};
+
+template <int NS, int SRC, bool RF, int TDM, int MAP, bool OUT16>
 __global__ void __launch_bounds__(1024, 1)
 k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, size_t nblocks,
 		const __grid_constant__ CoreConsts c, const __grid_constant__ SeedConsts s,
-		const uint4 *__restrict__ tables, const int *__restrict__ gate) {
+		const uint4 *__restrict__ tables, const int probe_lim, const __grid_constant__ CombConsts cb) {
 	extern __shared__ __align__(128) unsigned char smem[];
-	// Auto-selection: both table flavours are enqueued behind a probe kernel that writes which one suits the
-	// data; the other returns here, before touching shared memory.
-	if (gate != nullptr && *gate != (TDM == TD_TABLE_DP ? TD_TABLE : TDM)) return;
+	// Auto-selection: both table flavours are enqueued back to back and every CTA of both evaluates the same probe of
+	// the same input (probe_local: a pure function of the phase stream); the flavour the verdict does not name returns
+	// here, before touching shared memory.  No device-side state is shared between calls, streams or graph replays.
+	if (probe_lim >= 0 && probe_local(phase, nblocks << 7, c.pshift, probe_lim) != (TDM == TD_TABLE_DP ? TD_TABLE : TDM)) return;
 	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
 	const uint32_t mbar = sbase + s.total_bytes;		// 8-byte slot after the tables
 
@@ -240,7 +214,7 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 	// `reload` names a block, the registers are refilled at once with that block's phases (software prefetch, one block
 	// ahead; two register sets refilled two blocks ahead measured the same in short runs and 3 % slower under the power
 	// cap).
-	auto body = [&](uint32_t (&tin)[4], const uint32_t blk, const uint32_t reload) {
+	auto body = [&](uint32_t (&tin)[4], const uint32_t reload, auto &&store) {
 		uint32_t tq[4], tu[4];
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
@@ -252,7 +226,6 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 #pragma unroll
 			for (int k = 0; k < 4; k++) tin[k] = ldg_stream32(phase + ((size_t)reload << 7) + (k << 5) + lane);
 		}
-		int2 *const dst = xyout + ((size_t)blk << 7) + lane;
 		int x[4], y[4];
 		uint32_t row16[4];
 #pragma unroll
@@ -300,16 +273,49 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 			}
 			const int ox = RF ? round_out_fma(x[k], s) : round_out(x[k], c);
 			const int oy = RF ? round_out_fma(y[k], s) : round_out(y[k], c);
-			stg_stream64(dst + (k << 5), make_int2(ox, oy));
+			store(k, ox, oy);
 		}
 	};
-	if (SRC == SRC_NCO) {
+	// MAP_BLOCK stores: sample k of the lane goes to block*128 + 32k + lane (a coalesced 256-byte row per instruction;
+	// 128 bytes with packed outputs)
+	auto store_block = [&](const uint32_t blk) {
+		return [=](const int k, const int ox, const int oy) {
+			if (OUT16) {
+				uint32_t *const dst = reinterpret_cast<uint32_t *>(xyout) + ((size_t)blk << 7) + lane;
+				asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(dst + (k << 5)),
+					"r"(((uint32_t)ox & 0xffffu) | ((uint32_t)oy << 16)) : "memory");
+			} else {
+				stg_stream64(xyout + ((size_t)blk << 7) + lane + (k << 5), make_int2(ox, oy));
+			}
+		};
+	};
+	if (SRC == SRC_NCO && MAP == MAP_COMB) {
+		const uint32_t a = lane & 7u, b = lane >> 3;
+		const uint32_t lane_off = a * cb.K + 2u * b;		// the lane's first sample within (tile, chunk 0)
+		const uint32_t lane_phase = c.nco_phase0 + (c.nco_n0 + lane_off) * c.nco_step;
+		const uint32_t s1 = c.nco_step, s8 = 8u * s1, s9 = 9u * s1;
+		uint32_t t = blk / cb.cpr, m = blk - t * cb.cpr;	// unit = (tile t, chunk m); warp w takes units w, w+W, ...
+		for (; blk < cb.nunits; blk += nwarps) {
+			const uint32_t base = lane_phase + t * cb.tile_step + m * cb.chunk_step;
+			uint32_t tin[4] = {base >> c.pshift, (base + s1) >> c.pshift, (base + s8) >> c.pshift, (base + s9) >> c.pshift};
+			const uint32_t j0 = 16u * m + 2u * b;			// position in the run; K is even, so pairs stand or fall together
+			int2 *const dst = xyout + ((size_t)t * cb.tile + lane_off + 16u * m);
+			int hx = 0, hy = 0;
+			body(tin, 0u, [&](const int k, const int ox, const int oy) {
+				if ((k & 1) == 0) { hx = ox; hy = oy; return; }
+				if (j0 + (k == 3 ? 8u : 0u) < cb.K)
+					stg_stream(reinterpret_cast<int4 *>(dst + (k == 3 ? 8 : 0)), make_int4(hx, hy, ox, oy));
+			});
+			m += cb.dm; t += cb.dt;
+			if (m >= cb.cpr) { m -= cb.cpr; t++; }
+		}
+	} else if (SRC == SRC_NCO) {
 		for (; blk < nblk; blk += nwarps) {
 			uint32_t tin[4];
 			const uint32_t base = c.nco_phase0 + (c.nco_n0 + (blk << 7) + lane) * c.nco_step;
 #pragma unroll
 			for (int k = 0; k < 4; k++) tin[k] = (base + (uint32_t)(k << 5) * c.nco_step) >> c.pshift;
-			body(tin, blk, nblk);
+			body(tin, nblk, store_block(blk));
 		}
 	} else {
 		uint32_t pin[4] = {0, 0, 0, 0};
@@ -317,285 +323,49 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 #pragma unroll
 			for (int k = 0; k < 4; k++) pin[k] = ldg_stream32(phase + ((size_t)blk << 7) + (k << 5) + lane);
 		}
-		for (; blk < nblk; blk += nwarps) body(pin, blk, blk + nwarps);
+		for (; blk < nblk; blk += nwarps) body(pin, blk + nwarps, store_block(blk));
 	}
 }
 
-// ---- probe: are neighbouring samples' phases neighbours? ------------------------------------------------
-// 8 windows of 32 consecutive samples spread over the stream; a pair counts as local when the circular phase
-// difference is at most one LSB (a sweep or a slow NCO: word rows are conflict-free), and the word flavour is
-// chosen when at least 7 pairs in 8 are.  Scattered phases get the byte-packed flavour.
-// `lim`: the largest circular difference that still counts as local (1 phase LSB for the CORDIC tables; one table entry,
-// in 32-bit phase units, for the LUT cores).
-__global__ void k_seed_probe(const uint32_t *__restrict__ phase, size_t n, int pshift, int lim, int *gate) {
-	const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31u;
-	size_t off = ((n / 8) * w) & ~(size_t)31;
-	if (off + 33 > n) off = 0;
-	int local = 0;
-	if (n >= 34) {
-		const uint32_t a = phase[off + l], b = phase[off + l + 1];
-		const int d = (int)((b - a) << pshift) >> pshift;
-		local = (d >= -lim && d <= lim);
-	}
-	const int votes = __syncthreads_count(local);
-	if (threadIdx.x == 0) *gate = (votes * 8 >= (int)blockDim.x * 7) ? TD_TABLE : TD_PACKED;
-}
-
-// ---- host: plan construction and cache -----------------------------------------------------------
-struct SeedPlan {
-	zc_params p;
-	int32_t x0c[4], y0c[4];		// the pre-rotated constant vector (identifies x0,y0 modulo IW)
-	int device = -1;
-	int NS = 0;
-	int flavour = FL_WORDS;
-	SeedConsts s;
-	void *dev = nullptr;		// tables, laid out as in shared memory
-	std::shared_ptr<void> hold;	// owns `dev`: a copy of the plan keeps the tables alive across a cache eviction
-	bool usable = false;		// false: geometry does not fit; cached so we do not retry
-	uint64_t stamp = 0;
+struct SeedLaunch {		// what a launch needs besides the template selectors
+	int grid; size_t smem; cudaStream_t st; const uint32_t *ph; void *out; size_t nblocks;
+	const CoreConsts *c; const SeedConsts *s; const uint4 *tables; int probe_lim; const CombConsts *cb;
 };
-
-struct Interval { int64_t lo, hi, S; uint32_t neg; };	// neg: bit k set when stage k rotates clockwise (d_k = -1)
-
-// Enumerates the intervals of constant (d_0..d_{M-1}) over the reduced phase range
-// [-2^(PW-3), 2^(PW-3)), in ascending order.  Phase arithmetic only (rtl/cordic.v:265-279).
-static void seed_intervals(const zc_params *p, int M, std::vector<Interval> &iv) {
-	const int64_t half = (int64_t)1 << (p->pw - 3);
-	iv.assign(1, Interval{-half, half, 0, 0u});
-	std::vector<Interval> next;
-	for (int k = 0; k < M; k++) {
-		next.clear();
-		const int64_t a = p->angle[k];
-		for (const Interval &it : iv) {
-			// residual = phase - S ; negative residual -> rotate clockwise, S' = S - angle
-			if (it.lo < it.S) next.push_back(Interval{it.lo, it.hi < it.S ? it.hi : it.S, it.S - a, it.neg | (1u << k)});
-			if (it.hi > it.S) next.push_back(Interval{it.lo > it.S ? it.lo : it.S, it.hi, it.S + a, it.neg});
-		}
-		iv.swap(next);
-	}
-}
-
-static bool seed_geometry(const zc_params *p, int neff, int M, int flavour, std::vector<Interval> &iv, SeedConsts &s,
-		int &NS, int64_t &rmin, int64_t &rmax) {
-	const bool packed = fl_packed(flavour);
-	NS = neff - M;
-	if (NS < 0 || NS > SEED_MAX_NS) return false;
-	seed_intervals(p, M, iv);
-	int64_t wmin = INT64_MAX;
-	rmin = INT64_MAX; rmax = INT64_MIN;
-	for (const Interval &it : iv) {
-		if (it.hi - it.lo < wmin) wmin = it.hi - it.lo;
-		if (it.lo - it.S < rmin) rmin = it.lo - it.S;
-		if (it.hi - 1 - it.S > rmax) rmax = it.hi - 1 - it.S;
-	}
-	int lgw = 0;
-	while (((int64_t)2 << lgw) <= wmin) lgw++;		// largest W = 2^lgw <= wmin: at most one step per bucket
-	if (lgw < 2) return false;
-	if (lgw > 16) lgw = 16;
-	const int LB = p->pw - 2 - lgw;				// log2(number of buckets)
-	if (LB < 0 || LB > 15) return false;
-	const size_t R = iv.size();
-	const int nsp = (NS + 3) & ~3;
-	const size_t nres = (size_t)(rmax - rmin + 1);
-	// bytes per TD row slot: 16 (one int4 plane entry) or, packed, one signed byte per stage
-	const int lgrow = (packed && NS <= 8) ? 3 : 4;
-	const size_t b_t1 = (size_t)4 << LB, b_ts = (R * 4 + 15) & ~(size_t)15, b_t2 = R * (flavour == FL_DIRS ? 16 : 32),
-		     b_td = packed ? ((nres << lgrow) + 15) & ~(size_t)15 : nres * (size_t)nsp * 4;
-	const size_t total = b_t1 + b_ts + b_t2 + b_td;
-	if (total + 16 > SEED_SMEM_LIMIT) return false;
-	if ((R << lgw) >= ((uint64_t)1 << 32)) return false;
-	std::memset(&s, 0, sizeof(s));
-	s.M = M; s.lgw = lgw; s.R = (uint32_t)R;
-	s.mul_q = (uint32_t)1 << (32 - p->pw);
-	s.mul_u = (uint32_t)1 << (34 - p->pw);
-	s.bsh = 32 - LB;
-	s.ush = 34 - p->pw - lgrow;
-	s.rsh = lgw + lgrow;
-	s.lgrow = lgrow;
-	if (LB < 1 || s.ush < 0 || ((uint64_t)R << (lgw + lgrow)) >= ((uint64_t)1 << 31)) return false;
-	if (p->pw > 28 || 32 - p->pw - lgrow < 0) return false;	// residual reconstruction needs 2^(32-PW-lgrow)
-	s.mul_r = (uint32_t)1 << (32 - p->pw - lgrow);
-	s.res_bias = (int32_t)((uint64_t)rmin << (32 - p->pw));
-	{
-		const int D = p->ww - p->ow;
-		s.rscale = 1.0f / (float)((uint32_t)1 << D);
-		s.rbias = 12582912.0f - 12582912.0f / (float)((uint32_t)1 << D);
-	}
-	s.off_ts = (uint32_t)b_t1;
-	s.off_t2 = (uint32_t)(b_t1 + b_ts);
-	s.off_td = (uint32_t)(b_t1 + b_ts + b_t2);
-	s.td_plane = (int32_t)(nres * 16);
-	s.total_bytes = (uint32_t)((total + 15) & ~(size_t)15);
-	for (int j = 0; j < SEED_MAX_NS; j++) s.sh[j] = (M + j + 1 > 31) ? 31 : (M + j + 1);
-	return true;
-}
-
-static std::mutex g_seed_mu;
-static std::vector<SeedPlan> g_seed_cache;
-static uint64_t g_seed_clock = 0;
-
-// cudaFree waits for the device to go idle, so kernels already enqueued on the tables finish first.
-struct DevFree { void operator()(void *ptr) const { if (ptr) cudaFree(ptr); } };
-
-// Builds (or finds) the plan for (p, constant vector, device).  Called with the device current.
-static int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, int flavour, cudaStream_t st,
-		SeedPlan &out) {
-	const bool packed = fl_packed(flavour);
-	std::lock_guard<std::mutex> lk(g_seed_mu);
-	for (SeedPlan &pl : g_seed_cache) {
-		if (pl.device == device && pl.flavour == flavour && std::memcmp(&pl.p, p, sizeof(*p)) == 0 &&
-		    std::memcmp(pl.x0c, c.cx, sizeof(pl.x0c)) == 0 && std::memcmp(pl.y0c, c.cy, sizeof(pl.y0c)) == 0) {
-			pl.stamp = ++g_seed_clock;
-			out = pl;
-			return ZC_OK;
-		}
-	}
-	SeedPlan pl;
-	pl.p = *p; pl.device = device; pl.flavour = flavour; pl.stamp = ++g_seed_clock;
-	std::memcpy(pl.x0c, c.cx, sizeof(pl.x0c));
-	std::memcpy(pl.y0c, c.cy, sizeof(pl.y0c));
-	std::vector<Interval> iv;
-	int64_t rmin = 0, rmax = 0;
-	bool ok = false;
-	const int neff = c.neff;
-	if (fl_dirs(flavour)) {
-		if (neff >= DIRS_M) ok = seed_geometry(p, neff, DIRS_M, flavour, iv, pl.s, pl.NS, rmin, rmax);
-	} else {
-		for (int M = (neff < 13 ? neff : 13); M >= 6 && !ok; M--)
-			ok = seed_geometry(p, neff, M, flavour, iv, pl.s, pl.NS, rmin, rmax);
-		// IDP.2A multiplies the low 16 bits of x>>sh, y>>sh: exact when |x|,|y| < 2^(WW-1) and sh >= WW-16
-		if (ok && flavour == FL_WORDS_DP && pl.s.M + 1 < p->ww - 16) ok = false;
-	}
-	if (ok) {
-		const SeedConsts &s = pl.s;
-		const int pshift = c.pshift;
-		const size_t R = iv.size();
-		std::vector<uint32_t> host(s.total_bytes / 4 + R, 0u);		// tables + representative phases
-		uint32_t *t1 = host.data(), *ts = host.data() + s.off_ts / 4, *td = host.data() + s.off_td / 4;
-		uint32_t *rep = host.data() + s.total_bytes / 4;
-		const int64_t half = (int64_t)1 << (p->pw - 3), W = (int64_t)1 << s.lgw;
-		const size_t nb = (size_t)1 << (p->pw - 2 - s.lgw);
-		size_t r = 0;
-		for (size_t b = 0; b < nb && ok; b++) {
-			const int64_t b0 = -half + (int64_t)b * W;
-			while (r + 1 < R && iv[r + 1].lo <= b0) r++;
-			int64_t off = W;					// no step inside this bucket
-			if (r + 1 < R && iv[r + 1].lo < b0 + W) {
-				off = iv[r + 1].lo - b0;			// in [1, W-1]
-				if (r + 2 < R && iv[r + 2].lo < b0 + W) ok = false;	// two steps: refuse
-			}
-			t1[b] = (uint32_t)(((uint64_t)r << s.lgw) + (uint64_t)(W - off) - ((uint64_t)b << s.lgw)) << s.lgrow;
-		}
-		if (flavour == FL_DIRS) {		// per-interval prefix directions, one signed byte per stage, 16-byte rows
-			unsigned char *tp = reinterpret_cast<unsigned char *>(host.data()) + s.off_t2;
-			for (size_t k = 0; k < R; k++)
-				for (int j = 0; j < DIRS_M; j++)
-					tp[k * 16 + j] = (unsigned char)(((iv[k].neg >> j) & 1u) ? 0xff : 0x01);
-		}
-		for (size_t k = 0; k < R && ok; k++) {
-			ts[k] = (uint32_t)(int32_t)((iv[k].S + half + rmin) * ((int64_t)1 << s.lgrow));
-			rep[k] = (uint32_t)((uint64_t)iv[k].lo << pshift);
-		}
-		const size_t nres = (size_t)(rmax - rmin + 1);
-		for (int64_t res = rmin; res <= rmax && ok; res++) {
-			int64_t ph = res;
-			for (int j = 0; j < pl.NS; j++) {			// rtl/cordic.v:265-279, phase only
-				const bool neg = ph < 0;
-				if (packed)
-					reinterpret_cast<unsigned char *>(td)[((size_t)(res - rmin) << s.lgrow) + j] = (unsigned char)(neg ? 0xff : 0x01);
-				else if (flavour == FL_WORDS_DP)	// bytes 3..0 = {0, d, 0, -d}
-					td[((size_t)(j >> 2) * nres + (size_t)(res - rmin)) * 4 + (j & 3)] = neg ? 0x00FF0001u : 0x000100FFu;
-				else
-					td[((size_t)(j >> 2) * nres + (size_t)(res - rmin)) * 4 + (j & 3)] = (uint32_t)(neg ? -1 : 1);
-				ph += neg ? (int64_t)p->angle[s.M + j] : -(int64_t)p->angle[s.M + j];
-			}
-		}
-		if (ok) {
-			cudaError_t e = cudaMalloc(&pl.dev, host.size() * 4);
-			if (e == cudaSuccess) pl.hold = std::shared_ptr<void>(pl.dev, DevFree());
-			if (e == cudaSuccess) e = cudaMemcpyAsync(pl.dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st);
-			if (e == cudaSuccess && !fl_dirs(flavour)) {
-				const uint32_t nthreads = 4u * (uint32_t)R;
-				k_seed_fill_xy<<<(nthreads + 255) / 256, 256, 0, st>>>(
-					reinterpret_cast<const uint32_t *>(pl.dev) + s.total_bytes / 4,
-					reinterpret_cast<int2 *>(reinterpret_cast<char *>(pl.dev) + s.off_t2), (uint32_t)R, s.M, c);
-				e = cudaGetLastError();
-			}
-			if (e == cudaSuccess) e = cudaStreamSynchronize(st);	// tables complete before any stream uses them
-			if (e != cudaSuccess) {
-				cudaGetLastError();
-				return set_error(ZC_ECUDA, "seed table setup failed: %s", cudaGetErrorString(e));
-			}
-		}
-	}
-	pl.usable = ok;
-	if (g_seed_cache.size() >= 16) {		// evict the least recently used plan
-		size_t victim = 0;
-		for (size_t k = 1; k < g_seed_cache.size(); k++)
-			if (g_seed_cache[k].stamp < g_seed_cache[victim].stamp) victim = k;
-		g_seed_cache.erase(g_seed_cache.begin() + victim);	// the tables go when the last user's copy does
-	}
-	g_seed_cache.push_back(pl);
-	out = pl;
-	return ZC_OK;
-}
-
-// cudaFuncSetAttribute once per (device, kernel, size): launches of a configured kernel then consist of the
-// launch alone, which keeps them legal inside a stream capture.
-static cudaError_t ensure_dynamic_smem(const void *kern, size_t smem) {
-	static std::mutex mu;
-	static std::vector<std::pair<std::pair<int, const void *>, size_t>> seen;
-	int device = 0;
-	cudaError_t e = cudaGetDevice(&device);
-	if (e != cudaSuccess) return e;
-	std::lock_guard<std::mutex> lk(mu);
-	for (auto &it : seen)
-		if (it.first.first == device && it.first.second == kern) {
-			if (it.second >= smem) return cudaSuccess;
-			e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			if (e == cudaSuccess) it.second = smem;
-			return e;
-		}
-	e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if (e == cudaSuccess) seen.push_back({{device, kern}, smem});
-	return e;
-}
-
-// Drops the cached plans of `device` (all devices when negative).  The gate ring stays: 4 KB per device, and a
-// launch already enqueued may still read its slot.
-static void seed_trim(int device) {
-	std::lock_guard<std::mutex> lk(g_seed_mu);
-	for (size_t k = 0; k < g_seed_cache.size();) {
-		if (device < 0 || g_seed_cache[k].device == device) g_seed_cache.erase(g_seed_cache.begin() + k);
-		else k++;
-	}
-}
 
 template <int SRC, int NS>
 struct SeedTable {
-	static cudaError_t launch(int ns, int tdm, int grid, size_t smem, cudaStream_t st, const uint32_t *ph, int2 *out, size_t nblocks,
-			const CoreConsts &c, const SeedConsts &s, const uint4 *tables, const int *gate) {
+	// Instantiated combinations: every TDM for the block mapping with 32-bit outputs; the comb mapping only exists for
+	// the word tables, packed outputs for everything but the register-recursion flavour (an A/B switch).
+	template <int MAP, bool OUT16>
+	static cudaError_t launch(int ns, int tdm, const SeedLaunch &L) {
 		if (ns == NS) {
 			// float rounding needs every register value to fit 1.5*2^23 +- 2^22 and a rounding core (D >= 2)
-			const bool rf = c.do_round && c.wsh >= 9;
-			typedef void (*kern_t)(const uint32_t *, int2 *, size_t, const CoreConsts, const SeedConsts, const uint4 *, const int *);
-			kern_t kern;
-			if (tdm == TD_TABLE) kern = rf ? k_rotate_seeded<NS, SRC, true, TD_TABLE> : k_rotate_seeded<NS, SRC, false, TD_TABLE>;
-			else if (tdm == TD_TABLE_DP) kern = rf ? k_rotate_seeded<NS, SRC, true, TD_TABLE_DP> : k_rotate_seeded<NS, SRC, false, TD_TABLE_DP>;
-			else if (tdm == TD_REGS) kern = rf ? k_rotate_seeded<NS, SRC, true, TD_REGS> : k_rotate_seeded<NS, SRC, false, TD_REGS>;
-			else kern = rf ? k_rotate_seeded<NS, SRC, true, TD_PACKED> : k_rotate_seeded<NS, SRC, false, TD_PACKED>;
-			cudaError_t e = ensure_dynamic_smem((const void *)kern, smem);
+			const bool rf = L.c->do_round && L.c->wsh >= 9;
+			typedef void (*kern_t)(const uint32_t *, int2 *, size_t, const CoreConsts, const SeedConsts, const uint4 *, int,
+				const CombConsts);
+			kern_t kern = nullptr;
+#define ZC_PICK(T) (rf ? (kern_t)k_rotate_seeded<NS, SRC, true, T, MAP, OUT16> : (kern_t)k_rotate_seeded<NS, SRC, false, T, MAP, OUT16>)
+			if (tdm == TD_TABLE) kern = ZC_PICK(TD_TABLE);
+			else if (tdm == TD_TABLE_DP) kern = ZC_PICK(TD_TABLE_DP);
+			if constexpr (MAP == MAP_BLOCK) {
+				if (tdm == TD_PACKED) kern = ZC_PICK(TD_PACKED);
+				if constexpr (!OUT16) { if (tdm == TD_REGS) kern = ZC_PICK(TD_REGS); }
+			}
+#undef ZC_PICK
+			if (!kern) return cudaErrorInvalidValue;
+			cudaError_t e = ensure_dynamic_smem((const void *)kern, L.smem);
 			if (e != cudaSuccess) return e;
-			kern<<<grid, 1024, smem, st>>>(ph, out, nblocks, c, s, tables, gate);
+			kern<<<L.grid, 1024, L.smem, L.st>>>(L.ph, (int2 *)L.out, L.nblocks, *L.c, *L.s, L.tables, L.probe_lim,
+				L.cb ? *L.cb : CombConsts{});
 			return cudaGetLastError();
 		}
-		return SeedTable<SRC, NS - 1>::launch(ns, tdm, grid, smem, st, ph, out, nblocks, c, s, tables, gate);
+		return SeedTable<SRC, NS - 1>::template launch<MAP, OUT16>(ns, tdm, L);
 	}
 };
 template <int SRC>
 struct SeedTable<SRC, -1> {
-	static cudaError_t launch(int, int, int, size_t, cudaStream_t, const uint32_t *, int2 *, size_t, const CoreConsts &,
-			const SeedConsts &, const uint4 *, const int *) { return cudaErrorInvalidValue; }
+	template <int MAP, bool OUT16>
+	static cudaError_t launch(int, int, const SeedLaunch &) { return cudaErrorInvalidValue; }
 };
 
 // ---- per-sample input vectors: every stage in registers, every direction from a table ----------------------
@@ -772,81 +542,171 @@ static int dirs_rotate_try(const zc_params *p, const CoreConsts &c, const uint32
 	return ZC_OK;
 }
 
-// A small ring of device-side gate words per device for the auto-selected launches (stream-ordered use; a slot
-// is reused 1024 seeded calls later).
-static std::mutex g_gate_mu;
-static int *g_gate_ring[64] = {};
-static unsigned g_gate_next[64] = {};
-constexpr unsigned GATE_RING = 1024;
-
-static int gate_slot(int device, int **slot) {
-	std::lock_guard<std::mutex> lk(g_gate_mu);
-	if (!g_gate_ring[device]) {
-		cudaError_t e = cudaMalloc((void **)&g_gate_ring[device], GATE_RING * sizeof(int));
-		if (e != cudaSuccess) return set_error(ZC_ECUDA, "cudaMalloc(gate ring): %s", cudaGetErrorString(e));
+// ---- NCO comb mapping: the host side -----------------------------------------------------------------------
+// Shared-memory cost of one quarter-warp's 128-bit table reads when its 8 lanes sit `dp` phase LSBs apart: rows that
+// share (row mod 8) but differ are served one after the other.  1.0 = conflict-free (|dp| <= 8/7, or dp close to an odd
+// integer: a stride-3 walk still visits 8 different bank groups).
+static double comb_cost(double dp) {
+	double total = 0;
+	for (int f = 0; f < 4; f++) {
+		long rows[8];
+		for (int a = 0; a < 8; a++) rows[a] = (long)std::floor(0.13 + 0.25 * f + a * dp);
+		int worst = 0;
+		for (int cls = 0; cls < 8; cls++) {
+			long seen[8];
+			int cnt = 0;
+			for (int a = 0; a < 8; a++) {
+				if ((((rows[a] % 8) + 8) % 8) != cls) continue;
+				bool dup = false;
+				for (int k = 0; k < cnt; k++) dup |= (seen[k] == rows[a]);
+				if (!dup) seen[cnt++] = rows[a];
+			}
+			if (cnt > worst) worst = cnt;
+		}
+		total += worst;
 	}
-	*slot = g_gate_ring[device] + (g_gate_next[device]++ % GATE_RING);
-	return ZC_OK;
+	return total / 4;
 }
 
-// Tries the seeded path on the first floor(n/128)*128 samples.  done=0 means "not applicable here"; launches
-// reports how many kernels were enqueued.
-template <int SRC>
-static int seeded_rotate_try(const zc_params *p, const CoreConsts &c, const uint32_t *phase, int32_t *xy_out,
+// Finds a run length K (even, 64 <= K, 8K <= n) with K*step = delta (mod 2^32) and delta small enough that 8 lanes K
+// samples apart read neighbouring table rows.  Candidates: the denominators of the continued-fraction convergents of
+// step / 2^32 -- the K with record-small |K*step mod 2^32| -- and their small multiples.  Returns 0 when none qualifies.
+static uint32_t comb_search(uint32_t step, int pshift, size_t n) {
+	if (step == 0 || n < 1024) return 0;
+	const uint64_t kmax = n / 8 > 0x08000000ull ? 0x08000000ull : n / 8;		// tile = 8K <= 2^30 samples
+	uint64_t q[48];
+	int nq = 0;
+	{	// Euclid on (2^32, step): q_{i+1} = a_i * q_i + q_{i-1}
+		uint64_t r0 = (uint64_t)1 << 32, r1 = step, q0 = 0, q1 = 1;
+		while (r1 != 0 && nq < 48 && q1 <= kmax) {
+			q[nq++] = q1;
+			const uint64_t a = r0 / r1, r2 = r0 - a * r1, q2 = a * q1 + q0;
+			r0 = r1; r1 = r2; q0 = q1; q1 = q2;
+		}
+		if (r1 == 0 && nq < 48 && q1 <= kmax) q[nq++] = q1;	// the exact period: q1 * step == 0 (mod 2^32)
+	}
+	const double lsb = (double)((uint64_t)1 << pshift);
+	double best = 1e30;
+	uint32_t bestK = 0;
+	for (int i = 0; i < nq; i++)
+		for (uint64_t m = 1; m <= 64; m++) {
+			const uint64_t K = q[i] * m;
+			if (K > kmax) break;
+			if (K < 64 || (K & 1)) continue;
+			const double dp = (double)(int32_t)((uint32_t)K * step) / lsb;		// lanes of a quarter-warp: dp LSBs apart
+			if (dp > 12.0 || dp < -12.0) continue;		// stay (mostly) within one prefix interval: >= 256 LSBs wide
+			const double cost = comb_cost(dp);
+			if (cost > 1.3) continue;
+			const uint64_t cpr = (K + 15) / 16;
+			const double waste = (double)(cpr * 16 - K) / (double)(cpr * 16);	// idle lanes in the last chunk of a run
+			const uint64_t covered = (n / (8 * K)) * 8 * K;
+			const double left = (double)(n - covered) / (double)n;			// what a second pass has to take
+			const double score = cost * (1.0 + waste) * (1.0 + 0.5 * left);
+			if (score < best - 1e-9) { best = score; bestK = (uint32_t)K; }
+		}
+	return bestK;
+}
+
+// Tries the seeded path on a prefix of the n samples (a multiple of 128).  done=0 means "not applicable here"; launches
+// reports how many kernels were enqueued.  OUT16: xy_out receives (int16 x, int16 y) words.
+template <int SRC, bool OUT16>
+static int seeded_rotate_try(const zc_params *p, const CoreConsts &c, const uint32_t *phase, void *xy_out,
 		size_t n, int device, int sms, cudaStream_t st, uint32_t flags, size_t &done, int &launches) {
 	done = 0; launches = 0;
 	const size_t nblocks = n >> 7;
 	if (nblocks == 0 || nblocks > SEED_MAX_BLOCKS) return ZC_OK;
 	if (!(flags & ZC_F_FORCE_SEED) && n < ((size_t)1 << 20)) return ZC_OK;	// not worth the table load
 	if (c.neff < 6 || p->pw < 12) return ZC_OK;
-	// Which flavour of direction table.  The caller's flag wins.  For the NCO the host knows the pattern: byte rows
-	// when neighbouring lanes land more than one table row apart (|step| >= 2 phase LSBs).  For a phase stream of
-	// 4 Mi samples or more, a probe kernel decides on the device and both flavours are enqueued behind it.
+	// Which flavour of direction table.  The caller's flag wins.  For the NCO the host knows the pattern: a step of
+	// 2 phase LSBs or more scatters neighbouring samples, and then either a comb mapping exists that makes the lanes of
+	// a quarter-warp neighbours again (word tables, IDP.2A stages) or the byte rows take over.  For a phase stream of
+	// 4 Mi samples or more both flavours are enqueued and a probe inside the kernels decides.
 	const bool forced = (flags & (ZC_F_SEED_REGS | ZC_F_SEED_PACKED | ZC_F_SEED_WORDS)) != 0;
 	int tdm = (flags & ZC_F_SEED_REGS) ? TD_REGS : (flags & ZC_F_SEED_PACKED) ? TD_PACKED : TD_TABLE;
-	bool probe = false;
+	if (OUT16 && tdm == TD_REGS) tdm = TD_TABLE;
+	bool probe = false, scattered_nco = false;
 	if (!forced) {
 		if (SRC == SRC_NCO) {
 			const int32_t sstep = (int32_t)c.nco_step;
 			const uint32_t mag = (uint32_t)(sstep < 0 ? -(int64_t)sstep : (int64_t)sstep);
-			if ((mag >> c.pshift) >= 2u) tdm = TD_PACKED;
+			if ((mag >> c.pshift) >= 2u) scattered_nco = true;
 		} else if (n >= ((size_t)1 << 22)) {
 			probe = true;
 		}
 	}
 	SeedPlan pl, pl2;
 	int rc = ZC_OK;
+	bool have_words = false;
 	if (tdm == TD_TABLE && !(flags & ZC_F_NO_DP2A)) {	// the word table as IDP.2A multipliers, when the shifts allow
 		if ((rc = seed_plan_get(p, c, device, FL_WORDS_DP, st, pl)) != ZC_OK) return rc;
-		if (pl.usable) tdm = TD_TABLE_DP;
+		if (pl.usable) { tdm = TD_TABLE_DP; have_words = true; }
 	}
-	if (tdm != TD_TABLE_DP) {
+	if (tdm == TD_TABLE) {
+		if ((rc = seed_plan_get(p, c, device, FL_WORDS, st, pl)) != ZC_OK) return rc;
+		have_words = pl.usable;
+	}
+	const int grid = sms;
+	SeedLaunch L{grid, 0, st, phase, xy_out, 0, &c, nullptr, nullptr, -1, nullptr};
+	cudaError_t e = cudaSuccess;
+	size_t off = 0;
+	if constexpr (SRC == SRC_NCO && !OUT16) {
+		// ---- scattered NCO: comb passes over the largest tile-aligned prefix, again over what is left, ... -------------
+		const bool aligned = (reinterpret_cast<uintptr_t>(xy_out) & 15u) == 0;
+		while (scattered_nco && have_words && aligned && !(flags & ZC_F_NO_COMB)) {
+			const size_t rem = n - off;
+			if (rem < ((size_t)1 << 20) && !((flags & ZC_F_FORCE_SEED) && off == 0)) break;
+			const uint32_t K = comb_search(c.nco_step, c.pshift, rem);
+			if (!K) break;
+			const uint32_t nwarps = (uint32_t)grid * 32u;
+			CombConsts cb;
+			cb.K = K; cb.cpr = (K + 15u) / 16u; cb.tile = 8u * K;
+			const uint64_t tiles = rem / cb.tile, units = tiles * cb.cpr;
+			if (tiles == 0 || units + nwarps >= ((uint64_t)1 << 32)) break;
+			cb.nunits = (uint32_t)units;
+			cb.tile_step = cb.tile * c.nco_step; cb.chunk_step = 16u * c.nco_step;
+			cb.dt = nwarps / cb.cpr; cb.dm = nwarps % cb.cpr;
+			CoreConsts cc = c;
+			cc.nco_n0 = c.nco_n0 + (uint32_t)off;		// arithmetic is mod 2^32
+			L.smem = pl.s.total_bytes + 16; L.out = (int32_t *)xy_out + 2 * off; L.nblocks = 0; L.c = &cc; L.s = &pl.s;
+			L.tables = (const uint4 *)pl.dev; L.cb = &cb;
+			e = SeedTable<SRC, SEED_MAX_NS>::template launch<MAP_COMB, false>(pl.NS, tdm, L);
+			if (e != cudaSuccess) return set_error(ZC_ECUDA, "launch of k_rotate_seeded (comb) failed: %s", cudaGetErrorString(e));
+			launches++;
+			off += (size_t)tiles * cb.tile;
+		}
+		L.cb = nullptr; L.c = &c;
+	}
+	const size_t rest_blocks = (n - off) >> 7;
+	if (off && (rest_blocks << 7) < ((size_t)1 << 20)) { done = off; return ZC_OK; }	// the plain kernels take the tail
+	if (scattered_nco) { tdm = TD_PACKED; have_words = false; }
+	if (tdm == TD_PACKED || tdm == TD_REGS) {
 		if ((rc = seed_plan_get(p, c, device, tdm == TD_PACKED ? FL_PACKED : FL_WORDS, st, pl)) != ZC_OK) return rc;
-		if (!pl.usable) return ZC_OK;
+		if (!pl.usable) { done = off; return ZC_OK; }
+	} else if (!have_words) {
+		done = off; return ZC_OK;
 	}
-	int *gate = nullptr;
 	if (probe) {
 		if ((rc = seed_plan_get(p, c, device, FL_PACKED, st, pl2)) != ZC_OK) return rc;
 		if (!pl2.usable) probe = false;
 	}
-	if (probe) {
-		if ((rc = gate_slot(device, &gate)) != ZC_OK) return rc;
-		k_seed_probe<<<1, 256, 0, st>>>(phase, n, c.pshift, 1, gate);
-		cudaError_t e = cudaGetLastError();
-		if (e != cudaSuccess) return set_error(ZC_ECUDA, "launch of k_seed_probe failed: %s", cudaGetErrorString(e));
-		launches++;
-	}
-	cudaError_t e = SeedTable<SRC, SEED_MAX_NS>::launch(pl.NS, tdm, sms, pl.s.total_bytes + 16, st, phase, (int2 *)xy_out,
-		nblocks, c, pl.s, (const uint4 *)pl.dev, gate);
+	CoreConsts cc = c;
+	cc.nco_n0 = c.nco_n0 + (uint32_t)off;
+	// probe: both flavours are enqueued; each evaluates probe_local() on the same input and exactly one proceeds
+	L.probe_lim = probe ? 1 : -1;
+	L.c = &cc; L.nblocks = rest_blocks;
+	L.out = OUT16 ? (void *)((int32_t *)xy_out + off) : (void *)((int32_t *)xy_out + 2 * off);
+	L.ph = phase ? phase + off : nullptr;
+	L.smem = pl.s.total_bytes + 16; L.s = &pl.s; L.tables = (const uint4 *)pl.dev;
+	e = SeedTable<SRC, SEED_MAX_NS>::template launch<MAP_BLOCK, OUT16>(pl.NS, tdm, L);
 	if (e == cudaSuccess) launches++;
 	if (e == cudaSuccess && probe) {
-		e = SeedTable<SRC, SEED_MAX_NS>::launch(pl2.NS, TD_PACKED, sms, pl2.s.total_bytes + 16, st, phase, (int2 *)xy_out,
-			nblocks, c, pl2.s, (const uint4 *)pl2.dev, gate);
+		L.smem = pl2.s.total_bytes + 16; L.s = &pl2.s; L.tables = (const uint4 *)pl2.dev;
+		e = SeedTable<SRC, SEED_MAX_NS>::template launch<MAP_BLOCK, OUT16>(pl2.NS, TD_PACKED, L);
 		if (e == cudaSuccess) launches++;
 	}
 	if (e != cudaSuccess)
 		return set_error(ZC_ECUDA, "launch of k_rotate_seeded failed: %s", cudaGetErrorString(e));
-	done = nblocks << 7;
+	done = off + (rest_blocks << 7);
 	return ZC_OK;
 }
 

@@ -4,8 +4,13 @@
 // zc_rotate_const_host end to end, and prints Gsamples/s for both.  bench.py is the driver's contract; this is the
 // same measurement from the reference's own language.
 //   zcordic_bench [-i iw] [-o ow] [-p pw] [-n stages] [-x xtra] [-l lg2(samples)] [-s steps] [-d device] [-g gpus]
+//                 [--scatter] [--transport nccl|peer|both] [--chunks C] [--json]
 // -g G: the sample stream is sharded over devices 0..G-1 as independent chunks, one host thread per device (no collective:
 // the path has no exchange step); the figure is all samples over the slowest device's time.
+// -g G --scatter: device 0 owns the whole stream (G * 2^l samples) and every step scatters it over the G devices,
+// rotates and gathers the outputs back (libzcordic_nccl: zc_scatter_rotate_gather), over NCCL send/recv with the three
+// stages pipelined in C chunks, and with the kernels reading and writing device 0's memory directly over NVLink (peer);
+// the gathered output is compared byte for byte with device 0 computing the whole stream alone.
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +22,10 @@
 #include <cuda_runtime.h>
 
 #include "zcordic.h"
+#include "zcordic_nccl.h"
+
+#include <chrono>
+#include <string>
 
 #define CK(call)                                                                                  \
 	do {                                                                                      \
@@ -65,20 +74,102 @@ static float shard(const zc_params *p, int device, size_t n, size_t first, int s
 	return ms;
 }
 
+// Device 0 owns G * n samples; per step: scatter -> rotate on G devices -> gather.  Returns 0 and prints one JSON line.
+static int scatter_bench(const zc_params *p, int gpus, size_t n_per, int steps, int chunks, const std::string &transport, bool json) {
+	const size_t n = n_per * (size_t)gpus;
+	const int32_t x0 = (1 << (p->iw - 1)) - 1;
+	const uint32_t mask = p->pw >= 32 ? 0xFFFFFFFFu : ((1u << p->pw) - 1u);
+	std::vector<int> devices(gpus);
+	for (int g = 0; g < gpus; g++) devices[g] = g;
+	CK(cudaSetDevice(0));
+	uint32_t *d_phase = nullptr;
+	int32_t *d_xy = nullptr, *d_ref = nullptr;
+	CK(cudaMalloc(&d_phase, n * 4));
+	CK(cudaMalloc(&d_xy, n * 8));
+	CK(cudaMalloc(&d_ref, n * 8));
+	{
+		const size_t slice = (size_t)1 << 26;
+		std::vector<uint32_t> h(slice);
+		for (size_t s0 = 0; s0 < n; s0 += slice) {
+			const size_t cnt = n - s0 < slice ? n - s0 : slice;
+			for (size_t i = 0; i < cnt; i++) h[i] = (uint32_t)(s0 + i) & mask;
+			CK(cudaMemcpy(d_phase + s0, h.data(), cnt * 4, cudaMemcpyHostToDevice));
+		}
+	}
+	ZC(zc_rotate_const(p, x0, 0, d_phase, d_ref, n, 0, nullptr));		// device 0 alone: the reference result
+	CK(cudaDeviceSynchronize());
+	const size_t max_piece = ((n + chunks - 1) / chunks / gpus + 256) & ~(size_t)127;
+	double best = 0;
+	std::string best_name, detail;
+	bool parity = true;
+	for (int tr = 0; tr < 2; tr++) {
+		const char *name = tr == ZC_XCHG_NCCL ? "nccl" : "peer";
+		if (transport != "both" && transport != name) continue;
+		zc_exchange *x = nullptr;
+		int rc = zc_exchange_create(devices.data(), gpus, tr, max_piece, &x);
+		if (rc != ZC_OK) { std::fprintf(stderr, "zc_exchange_create(%s): %s\n", name, zc_strerror(rc)); return 2; }
+		CK(cudaSetDevice(0));
+		CK(cudaMemset(d_xy, 0xff, n * 8));
+		ZC(zc_scatter_rotate_gather(x, p, x0, 0, d_phase, d_xy, n, chunks));	// warm-up: tables on every device, NCCL channels
+		const auto t0 = std::chrono::steady_clock::now();
+		for (int s = 0; s < steps; s++) ZC(zc_scatter_rotate_gather(x, p, x0, 0, d_phase, d_xy, n, chunks));	// returns complete
+		const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		zc_exchange_destroy(x);
+		CK(cudaSetDevice(0));
+		// byte-for-byte against device 0 alone
+		const size_t slice = (size_t)1 << 25;
+		std::vector<int32_t> a(slice * 2), b(slice * 2);
+		bool same = true;
+		for (size_t s0 = 0; s0 < n && same; s0 += slice) {
+			const size_t cnt = n - s0 < slice ? n - s0 : slice;
+			CK(cudaMemcpy(a.data(), d_xy + 2 * s0, cnt * 8, cudaMemcpyDeviceToHost));
+			CK(cudaMemcpy(b.data(), d_ref + 2 * s0, cnt * 8, cudaMemcpyDeviceToHost));
+			same = std::memcmp(a.data(), b.data(), cnt * 8) == 0;
+		}
+		parity = parity && same;
+		const double gs = (double)n * steps / dt / 1e9;
+		// what crosses device 0's NVLink port per sample: 4 B out + 8 B back for the (G-1)/G of the stream that leaves
+		const double link = gs * 8.0 * (gpus - 1) / gpus;
+		char buf[256];
+		std::snprintf(buf, sizeof(buf), "%s\"%s\": {\"value\": %.2f, \"ms_per_step\": %.3f, \"dev0_ingress_gbs\": %.1f, \"parity\": %s}",
+			detail.empty() ? "" : ", ", name, gs, 1e3 * dt / steps, link, same ? "true" : "false");
+		detail += buf;
+		if (!json) std::printf("%d GPUs, scatter->rotate->gather over %s: %.1f Gsamples/s (%.1f GB/s into device 0), output %s device 0 alone\n",
+			gpus, name, gs, link, same ? "==" : "!=");
+		if (gs > best) { best = gs; best_name = name; }
+	}
+	if (json)
+		std::printf("{\"value\": %.2f, \"unit\": \"Gsamples/s\", \"transport\": \"%s\", \"n_gpus\": %d, \"samples_per_gpu_per_step\": %zu, "
+			"\"steps\": %d, \"chunks\": %d, \"parity\": %s, %s, \"what\": \"device 0 owns the whole phase stream; per step it is scattered over "
+			"the devices, rotated and gathered back (libzcordic_nccl: ncclSend/ncclRecv groups, 3-stage pipeline | kernels on peer "
+			"memory over NVLink); host wall clock around complete calls; parity = output byte-identical to device 0 alone\"}\n",
+			best, best_name.c_str(), gpus, n_per, steps, chunks, parity ? "true" : "false", detail.c_str());
+	cudaFree(d_phase); cudaFree(d_xy); cudaFree(d_ref);
+	return parity ? 0 : 4;
+}
+
 int main(int argc, char **argv) {
-	int iw = 18, ow = 18, pw = 24, ns = 20, xtra = 2, lg = 28, steps = 20, device = 0, gpus = 1;
-	for (int k = 1; k + 1 < argc; k += 2) {
+	int iw = 18, ow = 18, pw = 24, ns = 20, xtra = 2, lg = 28, steps = 20, device = 0, gpus = 1, chunks = 8;
+	bool scatter = false, json = false;
+	std::string transport = "both";
+	for (int k = 1; k < argc; k++) {
+		if (!std::strcmp(argv[k], "--scatter")) { scatter = true; continue; }
+		if (!std::strcmp(argv[k], "--json")) { json = true; continue; }
+		if (k + 1 >= argc) { std::fprintf(stderr, "option %s needs a value\n", argv[k]); return 1; }
+		if (!std::strcmp(argv[k], "--transport")) { transport = argv[++k]; continue; }
 		const int v = std::atoi(argv[k + 1]);
-		if (!std::strcmp(argv[k], "-i")) iw = v;
-		else if (!std::strcmp(argv[k], "-o")) ow = v;
-		else if (!std::strcmp(argv[k], "-p")) pw = v;
-		else if (!std::strcmp(argv[k], "-n")) ns = v;
-		else if (!std::strcmp(argv[k], "-x")) xtra = v;
-		else if (!std::strcmp(argv[k], "-l")) lg = v;
-		else if (!std::strcmp(argv[k], "-s")) steps = v;
-		else if (!std::strcmp(argv[k], "-d")) device = v;
-		else if (!std::strcmp(argv[k], "-g")) gpus = v;
-		else { std::fprintf(stderr, "unknown option %s\n", argv[k]); return 1; }
+		k++;
+		if (!std::strcmp(argv[k - 1], "--chunks")) chunks = v;
+		else if (!std::strcmp(argv[k - 1], "-i")) iw = v;
+		else if (!std::strcmp(argv[k - 1], "-o")) ow = v;
+		else if (!std::strcmp(argv[k - 1], "-p")) pw = v;
+		else if (!std::strcmp(argv[k - 1], "-n")) ns = v;
+		else if (!std::strcmp(argv[k - 1], "-x")) xtra = v;
+		else if (!std::strcmp(argv[k - 1], "-l")) lg = v;
+		else if (!std::strcmp(argv[k - 1], "-s")) steps = v;
+		else if (!std::strcmp(argv[k - 1], "-d")) device = v;
+		else if (!std::strcmp(argv[k - 1], "-g")) gpus = v;
+		else { std::fprintf(stderr, "unknown option %s\n", argv[k - 1]); return 1; }
 	}
 	if (zc_device_count() <= 0) {
 		std::fprintf(stderr, "no CUDA device: %s (libzcordic has no CPU path)\n", zc_last_error());
@@ -86,8 +177,12 @@ int main(int argc, char **argv) {
 	}
 	zc_params p;
 	ZC(zc_derive_p2r(iw, ow, xtra, pw, ns, &p));		// sw/main.cpp:260-279
-	std::printf("core: IW=%d OW=%d WW=%d PW=%d NSTAGES=%d GAIN=%.12f\n", p.iw, p.ow, p.ww, p.pw, p.nstages, p.gain);
+	if (!json) std::printf("core: IW=%d OW=%d WW=%d PW=%d NSTAGES=%d GAIN=%.12f\n", p.iw, p.ow, p.ww, p.pw, p.nstages, p.gain);
 	const size_t n = (size_t)1 << lg;
+	if (scatter) {
+		if (gpus > zc_device_count()) { std::fprintf(stderr, "-g %d but %d devices\n", gpus, zc_device_count()); return 1; }
+		return scatter_bench(&p, gpus, n, steps, chunks < 1 ? 1 : chunks, transport, json);
+	}
 	const int32_t x0 = (1 << (p.iw - 1)) - 1, y0 = 0;	// cordic_tb.cpp:68-69
 	if (gpus > 1) {		// independent shards of n samples each, one host thread per device
 		if (gpus > zc_device_count()) { std::fprintf(stderr, "-g %d but %d devices\n", gpus, zc_device_count()); return 1; }

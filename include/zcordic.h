@@ -95,9 +95,14 @@ enum {
 	ZC_F_NO_DP2A       = 128,	/* seeded kernel, word table: multiply-adds as IMAD with an explicit negation instead of IDP.2A */
 	ZC_F_NO_TAIL       = 64,	/* topolar: every stage in its full form (by default the late stages, where y has provably
 				   converged below the shift, run a shorter instruction sequence with identical results) */
+	ZC_F_NO_COMB       = 256,	/* NCO with a scattering step: keep the block sample mapping + byte table (by default the
+				   engine looks for a comb mapping -- runs K samples apart with K*step ~ 0 mod 2^32 share a
+				   quarter-warp -- under which the word table is conflict-free again; same results) */
 	ZC_F_SEED_WORDS    = 32	/* seeded kernel: suffix directions as one word per stage (fastest for phase sweeps, slow NCOs).
 				   With none of the three: NCO picks by step size on the host; phase streams of >= 4 Mi
-				   samples are probed on the device (one extra tiny launch + one skipped launch per call). */
+				   samples are probed on the device: both flavours are enqueued, every CTA of both evaluates
+				   the same pure function of the phase stream and exactly one flavour proceeds (one skipped
+				   launch per call; no device-side state is shared between calls, streams or graph replays). */
 };
 
 int         zc_version(void);				/* major*1000 + minor */
@@ -135,6 +140,11 @@ int zc_clocks_per_output(const zc_params *p);
  * stage i on the engine has proved -2^(i+1) <= y < 2^(i+1) for every input, so rtl/topolar.v:227-243's
  * y>>>(i+1) is the sign word and x' = x - sign: identical results, six instructions instead of eight. */
 int zc_topolar_tail_stages(const zc_params *p);
+/* Diagnostic: the run length K of the comb sample mapping zc_nco_rotate would use for a phase accumulator advancing by
+ * `step` over n samples (0: the block mapping is used -- a slow NCO, or no suitable K; negative: zc_status).  K*step is
+ * within about one phase LSB of a multiple of 2^32, so samples K apart read neighbouring table rows; lane (a, b) of a
+ * warp takes samples a*K + 16m + 2b + {0,1,8,9} of every 8K-sample tile.  Same results as the block mapping. */
+long long zc_nco_comb_run(const zc_params *p, uint32_t step, size_t n);
 /* gencordic -t tbl [-i n] [-p pw] [-o ow]   sw/main.cpp:358-379 ; limit sw/sintable.cpp:62 */
 int zc_derive_tbl(int iw, int pw, int ow, int *pw_out, int *ow_out);
 /* gencordic -t qtr ...                       sw/main.cpp:401-422 ; limit sw/sintable.cpp:190 */
@@ -193,6 +203,20 @@ int zc_lut_sin(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32,
 int zc_lut_qwav(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int32_t *out,
 		size_t n, int device, void *stream);
 
+/* ---- packed port words ("report separately") ----------------------------------------------
+ * The ports of the generated cores are IW / OW bits wide (rtl/cordic.v:58-63, rtl/topolar.v:59-64); the entry points
+ * above carry each port in a 32-bit word.  For cores with IW <= 16 / OW <= 16 these variants carry a pair of ports
+ * in ONE 32-bit word -- half the bytes on the PCIe-bound host path -- with bit-identical values:
+ *   zc_topolar_i16       xy16_in[2i] = i_xval, xy16_in[2i+1] = i_yval as int16 (the low IW bits are the port);
+ *                        mag / phase as in zc_topolar.  12 algorithmic bytes per sample instead of 16.
+ *   zc_rotate_const_o16  xy16[2i] = o_xval, xy16[2i+1] = o_yval as int16 (OW <= 16: the sign-extended port value
+ *                        fits).  8 algorithmic bytes per sample instead of 12.
+ * Buffers must be 4-byte aligned. */
+int zc_topolar_i16(const zc_params *p, const int16_t *xy16_in, int32_t *mag, uint32_t *phase, size_t n,
+		int device, void *stream);
+int zc_rotate_const_o16(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int16_t *xy16,
+		size_t n, int device, void *stream);
+
 /* rtl/quadtbl.v:143-291: table lookup + quadratic interpolation + overflow-safe convergent rounding.
  * phase32 is a 32-bit NCO word; the core sees i_phase = phase32 >> (32-PW).  out[i] = o_sin. */
 int zc_quadtbl_sin(const zc_quadtbl *q, const uint32_t *phase32, int32_t *out, size_t n, int device, void *stream);
@@ -200,7 +224,12 @@ int zc_quadtbl_sin(const zc_quadtbl *q, const uint32_t *phase32, int32_t *out, s
 /* ---- the data path, host buffers (end-to-end) ---------------------------------------- */
 
 void *zc_host_alloc(size_t bytes);		/* pinned; NULL on failure */
-void  zc_host_free(void *ptr);
+void  zc_host_free(void *ptr);			/* memory of zc_host_alloc or zc_host_alloc_sharded */
+/* Pinned memory for the *_host_multi entry points: the g-th 1/ndev of the buffer is placed on the NUMA node of
+ * devices[g] (read from sysfs; mbind(2) before first touch, best effort), so that each device's shard is copied over
+ * its own socket's memory controllers.  NULL on failure. */
+void *zc_host_alloc_sharded(size_t bytes, const int *devices, int ndev);
+int   zc_device_numa_node(int device);		/* NUMA node the device's PCIe slot hangs off; -1 when unknown */
 
 int zc_rotate_const_host(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase,
 		int32_t *xy, size_t n, int device);
@@ -218,6 +247,30 @@ int zc_quadtbl_sin_host(const zc_quadtbl *q, const uint32_t *phase32, int32_t *o
 int zc_nco_mix_host(const zc_params *p, const int32_t *xy_in, uint32_t phase0, uint32_t step, uint64_t n0,
 		int32_t *xy_out, size_t n, int device);
 
+int zc_topolar_i16_host(const zc_params *p, const int16_t *xy16_in, int32_t *mag, uint32_t *phase, size_t n,
+		int device);
+int zc_rotate_const_o16_host(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int16_t *xy16,
+		size_t n, int device);
+
+/* ---- the data path, host buffers, several devices of one box -----------------------------------------------------
+ * The sample stream is cut into ndev contiguous shards (boundaries at multiples of 4 samples; samples are independent
+ * units -- SURVEY.md section 8e -- so there is no exchange step); shard g runs through the H2D -> kernel -> D2H
+ * pipeline of the matching zc_*_host call on devices[g], one host thread per device, concurrently.  Returns when every
+ * output word is in host memory.  Concatenated output == single-device output, byte for byte.  The NCO derives every
+ * shard's start phase in closed form (phase0 + (n0 + first)*step), the truncation of bench/cpp/cordic_tb.cpp:128-138. */
+int zc_rotate_const_host_multi(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int32_t *xy, size_t n,
+		const int *devices, int ndev);
+int zc_rotate_host_multi(const zc_params *p, const int32_t *xy_in, const uint32_t *phase, int32_t *xy_out, size_t n,
+		const int *devices, int ndev);
+int zc_topolar_host_multi(const zc_params *p, const int32_t *xy_in, int32_t *mag, uint32_t *phase, size_t n,
+		const int *devices, int ndev);
+int zc_nco_rotate_host_multi(const zc_params *p, int32_t x0, int32_t y0, uint32_t phase0, uint32_t step, uint64_t n0,
+		int32_t *xy, size_t n, const int *devices, int ndev);
+int zc_lut_sin_host_multi(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int32_t *out, size_t n,
+		const int *devices, int ndev);
+int zc_lut_qwav_host_multi(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int32_t *out, size_t n,
+		const int *devices, int ndev);
+
 /* $readmemh files in the layout hextable() writes (sw/hexfile.cpp:78-89): exchange LUTs with FPGA flows.
  * zc_hex_read returns the number of words read (>= 0) or a negative zc_status. */
 int  zc_hex_write(const char *path, const uint32_t *words, size_t nwords, int bits);
@@ -232,7 +285,12 @@ uint64_t zc_launch_count(void);
  * (the model the reference's test bench `new`s once and clocks many times, bench/cpp/testb.h:56-63).
  * zc_trim releases those of `device` (every device when negative); work already enqueued finishes first.
  * The first call for a new configuration uploads its tables and synchronises the stream -- warm up before
- * capturing calls into a CUDA graph. */
+ * capturing calls into a CUDA graph.
+ * A captured graph holds raw pointers to the tables of the configurations it uses and thereby PINS them: between
+ * capture and the last replay do not call zc_trim for that device and do not cycle more than 15 other
+ * (configuration, input vector) pairs through the engine (the table caches keep the 16 most recently used and free an
+ * evicted entry once its last in-flight user returns -- a replay is not a user the library can see).  Nothing else is
+ * shared between calls: a graph may replay concurrently with any other call on any other stream. */
 int zc_trim(int device);
 
 #ifdef __cplusplus

@@ -77,15 +77,15 @@ def test_topolar_and_rotate_xy_cuda_graph_replay():
 
 
 def test_lut_cuda_graph_replay():
-    """A large LUT batch is probe + L2 kernel + shared-memory kernel behind a device-side gate: captured once, the graph
-    must take the right kernel on every replay -- a sweep (L2 kernel), then scattered phases (shared-memory kernel)."""
+    """A large LUT batch is the L2 kernel + the shared-memory kernel, each evaluating the same probe of the phases: captured
+    once, the graph must take the right kernel on every replay -- a sweep (L2 kernel), then scattered phases (shared-memory kernel)."""
     lut = zc.SinTable(phase_bits=17, ow=13)
     tbl = zo.sintable(17, 13)
     n = (1 << 22) + 12
     rng = np.random.default_rng(SEED + 2)
     words = torch.zeros(n, dtype=torch.int32, device="cuda")
     out = torch.empty(n, dtype=torch.int32, device="cuda")
-    lut.lookup(words, out=out)                              # warm-up: table upload, gate ring, function attributes
+    lut.lookup(words, out=out)                              # warm-up: table upload, function attributes
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
@@ -98,6 +98,60 @@ def test_lut_cuda_graph_replay():
         g.replay()
         torch.cuda.synchronize()
         assert np.array_equal(out.cpu().numpy(), zo.lut_sin(17, 13, tbl, w)), rnd
+
+
+def test_graph_replay_concurrent_with_probed_calls():
+    """an auto-selected call is two launches that must agree on which of them runs.  Round 1 passed
+    the verdict through a reused 1024-slot ring of device words, so a graph replaying on stream A while stream B cycled
+    more than 1024 probed calls could see its slot flip between the two reads and write nothing.  Now both launches
+    evaluate the same pure function of the input: replay a captured sweep call and a captured scattered call on one
+    stream while another stream issues > 1024 probed calls of the opposite kind, and check every replay word for word."""
+    core, op = both_p2r(**CFG1)
+    lut = zc.SinTable(phase_bits=17, ow=13)
+    tbl = zo.sintable(17, 13)
+    n = (1 << 22) + 128
+    rng = np.random.default_rng(SEED + 7)
+    sweep = (np.arange(n, dtype=np.uint32) + 12345) & 0xFFFFFF
+    scat = rng.integers(0, 1 << 24, size=n, dtype=np.uint64).astype(np.uint32)
+    want = {"sweep": zo.rotate_const(op, 131071, 0, sweep), "scat": zo.rotate_const(op, 131071, 0, scat)}
+    lwant = {"sweep": zo.lut_sin(17, 13, tbl, sweep << 8), "scat": zo.lut_sin(17, 13, tbl, scat << 8)}
+    d = {"sweep": torch.from_numpy(sweep.view(np.int32)).cuda(), "scat": torch.from_numpy(scat.view(np.int32)).cuda()}
+    d32 = {k: (v << 8) for k, v in d.items()}
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = {k: torch.empty((n, 2), dtype=torch.int32, device="cuda") for k in d}
+    louts = {k: torch.empty(n, dtype=torch.int32, device="cuda") for k in d}
+    scratch = torch.empty((n, 2), dtype=torch.int32, device="cuda")
+    lscratch = torch.empty(n, dtype=torch.int32, device="cuda")
+    for k in d:                                             # warm-up: tables of both flavours exist before capture
+        core.rotate_const(131071, 0, d[k], out=outs[k])
+        lut.lookup(d32[k], out=louts[k])
+    torch.cuda.synchronize()
+    graphs = {}
+    for k in d:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=sa):
+            core.rotate_const(131071, 0, d[k], out=outs[k])
+            lut.lookup(d32[k], out=louts[k])
+        graphs[k] = g
+    torch.cuda.synchronize()
+    calls = 0
+    for rnd in range(6):
+        key, other = ("sweep", "scat") if rnd % 2 == 0 else ("scat", "sweep")
+        outs[key].fill_(-1); louts[key].fill_(-1)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(sa):
+            for _ in range(8):
+                graphs[key].replay()
+        for _ in range(200):                                # stream B: probed calls of the other kind, concurrently
+            core.rotate_const(131071, 0, d[other], out=scratch, stream=sb)
+            lut.lookup(d32[other], out=lscratch, stream=sb)
+            calls += 2
+        torch.cuda.synchronize()
+        assert np.array_equal(outs[key].cpu().numpy(), want[key]), (rnd, key)
+        assert np.array_equal(louts[key].cpu().numpy(), lwant[key]), (rnd, key)
+        assert np.array_equal(scratch.cpu().numpy(), want[other]), (rnd, other)
+        assert np.array_equal(lscratch.cpu().numpy(), lwant[other]), (rnd, other)
+    assert calls > 1024
 
 
 def test_trim_between_calls():

@@ -30,6 +30,7 @@
 #include "zc_seedplan.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <utility>
@@ -125,6 +126,12 @@ __device__ __forceinline__ int round_out_fma(int v, const SeedConsts &s) {
 	return __float_as_int(r) - 0x4B400000;
 }
 
+// 256-bit store (sm_100: STG.256), 32-byte aligned
+__device__ __forceinline__ void stg256(int2 *p, int a, int b, int c, int d, int e, int f, int g, int h) {
+	asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d),
+		"r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
+
 __device__ __forceinline__ int4 lds128(uint32_t addr) {
 	int4 r;
 	asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -141,18 +148,18 @@ __device__ __forceinline__ int4 lds128(uint32_t addr) {
 // MAP: which samples a lane takes.
 //   MAP_BLOCK  a warp owns 128 consecutive samples per iteration, lane l takes l, l+32, l+64, l+96 (see the file header).
 //   MAP_COMB   (NCO only) for a phase accumulator whose step scatters consecutive samples over the circle.  The host
-//              finds a run length K with K*step = delta (mod 2^32), |delta| about one phase LSB or less (comb_search).
+//              finds a run length K with K*step = delta (mod 2^32), |delta| a fraction of a phase LSB (comb_search).
 //              The stream is cut into tiles of 8K samples; lane l = (a = l & 7, b = l >> 3) works in run a of the tile,
 //              [a*K, (a+1)*K), and per iteration the warp takes one 16-sample chunk of each of the 8 runs: lane (a, b)
-//              takes samples 16m + 2b + {0, 1, 8, 9} of run a.  At every instruction the 8 lanes of a quarter-warp (the
-//              unit in which a 128-bit shared-memory read is served) then hold phases delta apart -- neighbouring or equal
-//              table rows, conflict-free like a sweep -- while the four lanes b = 0..3 of a run write 64 contiguous bytes
-//              per store (two full sectors), 128 per chunk.  Round 1's comb gave every LANE its own run and died on
-//              scattered 8/16-byte stores; here a store instruction touches 8 lines instead of 4.
+//              computes samples 16m + 4b + {0, 1, 2, 3} of run a.  At every instruction the 8 lanes of a quarter-warp (the
+//              unit in which a 128-bit shared-memory read is served) then hold phases delta apart -- mostly the SAME
+//              table rows, which the LSU serves once.  Before storing, the results are transposed with warp shuffles so
+//              that a quarter-warp holds two whole 128-byte lines (runs 2h and 2h+1) and writes them with one 256-bit
+//              store per lane.  Round 1's comb gave every LANE its own run and died on scattered 8/16-byte stores.
 // OUT16: outputs packed as (int16 o_xval, int16 o_yval) in one word (cores with OW <= 16; zc_rotate_const_o16).
 enum { MAP_BLOCK = 0, MAP_COMB = 1 };
 struct CombConsts {
-	uint32_t K;		// run length (even)
+	uint32_t K;		// run length, a multiple of 4: every run starts on a 32-byte boundary (one 256-bit store per lane)
 	uint32_t cpr;		// 16-sample chunks per run: ceil(K/16)
 	uint32_t nunits;	// tiles * cpr
 	uint32_t tile;		// 8*K samples
@@ -290,22 +297,29 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 		};
 	};
 	if (SRC == SRC_NCO && MAP == MAP_COMB) {
+		// compute layout: lane (a = l & 7, b = l >> 3) takes samples 16m + 4b + {0,1,2,3} of run a -- the 8 lanes of a
+		// quarter-warp sit in 8 different runs, delta apart in phase.  store layout: lane (a' = l >> 2, b' = l & 3) holds the
+		// 32 bytes of run a', samples 16m + 4b' .. +3 -- a quarter-warp writes two full 128-byte lines with one 256-bit
+		// store per lane.  Eight shuffles per 128 samples move the results from one layout to the other (stored straight
+		// from the compute layout, every lane of a quarter-warp hit a different line: 32 LSU wavefronts per store
+		// instruction, profiles/r2_ncu_comb_untransposed.md -- the data pipe was 95 % busy, 54 % of it those stores).
 		const uint32_t a = lane & 7u, b = lane >> 3;
-		const uint32_t lane_off = a * cb.K + 2u * b;		// the lane's first sample within (tile, chunk 0)
+		const uint32_t lane_off = a * cb.K + 4u * b;		// the lane's first sample within (tile, chunk 0)
 		const uint32_t lane_phase = c.nco_phase0 + (c.nco_n0 + lane_off) * c.nco_step;
-		const uint32_t s1 = c.nco_step, s8 = 8u * s1, s9 = 9u * s1;
+		const uint32_t s1 = c.nco_step, s2 = 2u * s1, s3 = 3u * s1;
+		const uint32_t src_lane = (lane >> 2) + 8u * (lane & 3u);	// who computed what this lane stores
+		const uint32_t st_off = (lane >> 2) * cb.K + 4u * (lane & 3u);
 		uint32_t t = blk / cb.cpr, m = blk - t * cb.cpr;	// unit = (tile t, chunk m); warp w takes units w, w+W, ...
 		for (; blk < cb.nunits; blk += nwarps) {
 			const uint32_t base = lane_phase + t * cb.tile_step + m * cb.chunk_step;
-			uint32_t tin[4] = {base >> c.pshift, (base + s1) >> c.pshift, (base + s8) >> c.pshift, (base + s9) >> c.pshift};
-			const uint32_t j0 = 16u * m + 2u * b;			// position in the run; K is even, so pairs stand or fall together
-			int2 *const dst = xyout + ((size_t)t * cb.tile + lane_off + 16u * m);
-			int hx = 0, hy = 0;
-			body(tin, 0u, [&](const int k, const int ox, const int oy) {
-				if ((k & 1) == 0) { hx = ox; hy = oy; return; }
-				if (j0 + (k == 3 ? 8u : 0u) < cb.K)
-					stg_stream(reinterpret_cast<int4 *>(dst + (k == 3 ? 8 : 0)), make_int4(hx, hy, ox, oy));
-			});
+			uint32_t tin[4] = {base >> c.pshift, (base + s1) >> c.pshift, (base + s2) >> c.pshift, (base + s3) >> c.pshift};
+			int r[8];
+			body(tin, 0u, [&](const int k, const int ox, const int oy) { r[2 * k] = ox; r[2 * k + 1] = oy; });
+#pragma unroll
+			for (int i = 0; i < 8; i++) r[i] = __shfl_sync(0xffffffffu, r[i], (int)src_lane);
+			const uint32_t j0 = 16u * m + 4u * (lane & 3u);
+			int2 *const dst = xyout + ((size_t)t * cb.tile + st_off + 16u * m);
+			if (j0 < cb.K) stg256(dst, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);	// K % 4 == 0: all four or none, 32-byte aligned
 			m += cb.dm; t += cb.dt;
 			if (m >= cb.cpr) { m -= cb.cpr; t++; }
 		}
@@ -543,36 +557,22 @@ static int dirs_rotate_try(const zc_params *p, const CoreConsts &c, const uint32
 }
 
 // ---- NCO comb mapping: the host side -----------------------------------------------------------------------
-// Shared-memory cost of one quarter-warp's 128-bit table reads when its 8 lanes sit `dp` phase LSBs apart: rows that
-// share (row mod 8) but differ are served one after the other.  1.0 = conflict-free (|dp| <= 8/7, or dp close to an odd
-// integer: a stride-3 walk still visits 8 different bank groups).
-static double comb_cost(double dp) {
-	double total = 0;
-	for (int f = 0; f < 4; f++) {
-		long rows[8];
-		for (int a = 0; a < 8; a++) rows[a] = (long)std::floor(0.13 + 0.25 * f + a * dp);
-		int worst = 0;
-		for (int cls = 0; cls < 8; cls++) {
-			long seen[8];
-			int cnt = 0;
-			for (int a = 0; a < 8; a++) {
-				if ((((rows[a] % 8) + 8) % 8) != cls) continue;
-				bool dup = false;
-				for (int k = 0; k < cnt; k++) dup |= (seen[k] == rows[a]);
-				if (!dup) seen[cnt++] = rows[a];
-			}
-			if (cnt > worst) worst = cnt;
-		}
-		total += worst;
-	}
-	return total / 4;
-}
+// What the mapping buys is ROW SHARING: with the 8 lanes of a quarter-warp `dp` phase LSBs apart, a 128-bit read of the
+// direction table touches about 1 + 7|dp| distinct 16-byte rows per quarter-warp instead of 8, and the LSU serves
+// identical rows once.  Measured on B200 (profiles/r2_comb_ab.txt): |dp| = 0 .. 0.3 -> 460-510 Gsamples/s; |dp| = 0.95
+// (eight distinct rows again, plus 8 shuffles and the transposed stores) -> 245-280, below the 380 of the byte table
+// under the block mapping.  Hence the acceptance bound.
+constexpr double COMB_MAX_DP = 0.35;
 
-// Finds a run length K (even, 64 <= K, 8K <= n) with K*step = delta (mod 2^32) and delta small enough that 8 lanes K
-// samples apart read neighbouring table rows.  Candidates: the denominators of the continued-fraction convergents of
+// Finds a run length K (a multiple of 4, 64 <= K, 8K <= n) with K*step = delta (mod 2^32) and |delta| at most
+// COMB_MAX_DP phase LSBs, so that 8 lanes K samples apart mostly read the SAME table rows.  Candidates: the denominators of the continued-fraction convergents of
 // step / 2^32 -- the K with record-small |K*step mod 2^32| -- and their small multiples.  Returns 0 when none qualifies.
 static uint32_t comb_search(uint32_t step, int pshift, size_t n) {
 	if (step == 0 || n < 1024) return 0;
+	if (const char *force = std::getenv("ZCORDIC_COMB_K")) {	// experiments: any even K is correct, only the bank conflicts change
+		const uint64_t K = std::strtoull(force, nullptr, 0);
+		return (K >= 16 && !(K & 3) && 8 * K <= n) ? (uint32_t)K : 0;
+	}
 	const uint64_t kmax = n / 8 > 0x08000000ull ? 0x08000000ull : n / 8;		// tile = 8K <= 2^30 samples
 	uint64_t q[48];
 	int nq = 0;
@@ -592,11 +592,10 @@ static uint32_t comb_search(uint32_t step, int pshift, size_t n) {
 		for (uint64_t m = 1; m <= 64; m++) {
 			const uint64_t K = q[i] * m;
 			if (K > kmax) break;
-			if (K < 64 || (K & 1)) continue;
+			if (K < 64 || (K & 3)) continue;
 			const double dp = (double)(int32_t)((uint32_t)K * step) / lsb;		// lanes of a quarter-warp: dp LSBs apart
-			if (dp > 12.0 || dp < -12.0) continue;		// stay (mostly) within one prefix interval: >= 256 LSBs wide
-			const double cost = comb_cost(dp);
-			if (cost > 1.3) continue;
+			if (dp > COMB_MAX_DP || dp < -COMB_MAX_DP) continue;
+			const double cost = 1.0 + 7.0 * std::fabs(dp);				// distinct rows per quarter-warp read
 			const uint64_t cpr = (K + 15) / 16;
 			const double waste = (double)(cpr * 16 - K) / (double)(cpr * 16);	// idle lanes in the last chunk of a run
 			const uint64_t covered = (n / (8 * K)) * 8 * K;
@@ -651,7 +650,7 @@ static int seeded_rotate_try(const zc_params *p, const CoreConsts &c, const uint
 	size_t off = 0;
 	if constexpr (SRC == SRC_NCO && !OUT16) {
 		// ---- scattered NCO: comb passes over the largest tile-aligned prefix, again over what is left, ... -------------
-		const bool aligned = (reinterpret_cast<uintptr_t>(xy_out) & 15u) == 0;
+		const bool aligned = (reinterpret_cast<uintptr_t>(xy_out) & 31u) == 0;	// 256-bit stores
 		while (scattered_nco && have_words && aligned && !(flags & ZC_F_NO_COMB)) {
 			const size_t rem = n - off;
 			if (rem < ((size_t)1 << 20) && !((flags & ZC_F_FORCE_SEED) && off == 0)) break;

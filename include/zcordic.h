@@ -97,7 +97,7 @@ enum {
 				   converged below the shift, run a shorter instruction sequence with identical results) */
 	ZC_F_NO_COMB       = 256,	/* NCO with a scattering step: keep the block sample mapping + byte table (by default the
 				   engine looks for a comb mapping -- runs K samples apart with K*step ~ 0 mod 2^32 share a
-				   quarter-warp -- under which the word table is conflict-free again; same results) */
+				   quarter-warp -- under which the lanes of a quarter-warp share word-table rows; same results) */
 	ZC_F_SEED_WORDS    = 32	/* seeded kernel: suffix directions as one word per stage (fastest for phase sweeps, slow NCOs).
 				   With none of the three: NCO picks by step size on the host; phase streams of >= 4 Mi
 				   samples are probed on the device: both flavours are enqueued, every CTA of both evaluates
@@ -142,8 +142,8 @@ int zc_clocks_per_output(const zc_params *p);
 int zc_topolar_tail_stages(const zc_params *p);
 /* Diagnostic: the run length K of the comb sample mapping zc_nco_rotate would use for a phase accumulator advancing by
  * `step` over n samples (0: the block mapping is used -- a slow NCO, or no suitable K; negative: zc_status).  K*step is
- * within about one phase LSB of a multiple of 2^32, so samples K apart read neighbouring table rows; lane (a, b) of a
- * warp takes samples a*K + 16m + 2b + {0,1,8,9} of every 8K-sample tile.  Same results as the block mapping. */
+ * within a third of a phase LSB of a multiple of 2^32, so samples K apart mostly read the same table rows; lane (a, b)
+ * of a warp computes samples a*K + 16m + 4b + {0,1,2,3} of every 8K-sample tile.  Same results as the block mapping. */
 long long zc_nco_comb_run(const zc_params *p, uint32_t step, size_t n);
 /* gencordic -t tbl [-i n] [-p pw] [-o ow]   sw/main.cpp:358-379 ; limit sw/sintable.cpp:62 */
 int zc_derive_tbl(int iw, int pw, int ow, int *pw_out, int *ow_out);

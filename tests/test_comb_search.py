@@ -20,15 +20,19 @@ def signed_delta(K, step):
 
 def test_comb_search_known_steps():
     p = zc.derive_p2r(18, 18, 2, 24, 20)
-    assert comb_run(p, 0x01234567, 1 << 30) == 450               # BASELINE configs[4]: 225 steps ~ one turn
+    # BASELINE configs[4]: 225 steps are one turn minus 0.47 phase LSB, but K must be a multiple of 4 and 900 steps are
+    # 1.9 LSB off -- eight distinct table rows per quarter-warp again: no comb (measured: slower than the byte table)
+    assert comb_run(p, 0x01234567, 1 << 30) == 0
     assert comb_run(p, 0x00300000, 1 << 24) == 4096              # an exact period: every lane of a quarter-warp on one row
+    assert comb_run(p, 0x80000001, 1 << 24) == 64                # 64 steps: a quarter of a phase LSB
     assert comb_run(p, 1, 1 << 30) == 0 and comb_run(p, 0x1FF, 1 << 30) == 0   # below 2 phase LSBs: block mapping
     assert comb_run(p, 0x01234567, 2000) == 0                    # a tile (8K samples) does not fit
 
 
 @pytest.mark.parametrize("pw", [16, 20, 24])
 def test_comb_search_properties(pw):
-    """Whatever it returns is even, at least 64, fits n, and keeps the lanes of a quarter-warp within a dozen phase LSBs."""
+    """Whatever it returns is a multiple of 4, at least 64, fits n, and keeps neighbouring lanes of a quarter-warp within
+    0.35 phase LSB."""
     p = zc.derive_p2r(16, 16, 2, pw, 0)
     rng = np.random.default_rng(20261017 + pw)
     found = 0
@@ -38,15 +42,16 @@ def test_comb_search_properties(pw):
             if K == 0:
                 continue
             found += 1
-            assert K % 2 == 0 and K >= 64 and 8 * K <= n
-            assert abs(signed_delta(K, step)) <= 12 * (1 << (32 - pw)), (hex(step), K)
+            assert K % 4 == 0 and K >= 64 and 8 * K <= n
+            assert abs(signed_delta(K, step)) <= 0.35 * (1 << (32 - pw)) + 1, (hex(step), K)
     assert found > 100               # 2^30 samples: Dirichlet guarantees a run with |delta| <= 32 below n/8
 
 
 def test_comb_lane_arithmetic_covers_every_sample_once():
-    """Mirror of the index arithmetic in k_rotate_seeded<.., MAP_COMB, ..>: unit (t, m) -> lane (a, b) -> samples
-    t*8K + a*K + 16m + 2b + {0, 1, 8, 9}, stored when 16m + 2b (+8) < K; warps stride over the units with (dt, dm)."""
-    for K, n, nwarps in [(450, 50000, 7), (64, 4096, 5), (66, 9000, 300), (450, 450 * 8 * 3 + 17, 148 * 32)]:
+    """Mirror of the index arithmetic in k_rotate_seeded<.., MAP_COMB, ..>: unit (t, m) -> store lane (a', b') -> samples
+    t*8K + a'*K + 16m + 4b' + {0, 1, 2, 3}, pairs stored when 16m + 4b' (+2) < K; warps stride over the units with
+    (dt, dm).  The compute lane (a, b) = (l & 7, l >> 3) hands its four results to store lane 4a + b."""
+    for K, n, nwarps in [(452, 50000, 7), (64, 4096, 5), (68, 9000, 300), (452, 452 * 8 * 3 + 17, 148 * 32)]:
         cpr, tile = (K + 15) // 16, 8 * K
         tiles = n // tile
         nunits = tiles * cpr
@@ -58,13 +63,13 @@ def test_comb_lane_arithmetic_covers_every_sample_once():
             m = blk - t * cpr
             while blk < nunits:
                 for lane in range(32):
-                    a, b = lane & 7, lane >> 3
-                    base = t * tile + a * K + 2 * b + 16 * m
-                    j0 = 16 * m + 2 * b
-                    if j0 < K:
-                        seen[base] += 1; seen[base + 1] += 1
-                    if j0 + 8 < K:
-                        seen[base + 8] += 1; seen[base + 9] += 1
+                    a, b = lane >> 2, lane & 3                      # store layout
+                    src = (lane >> 2) + 8 * (lane & 3)              # the compute lane that produced these four samples
+                    assert (src & 7, src >> 3) == (a, b)
+                    base = t * tile + a * K + 4 * b + 16 * m
+                    j0 = 16 * m + 4 * b
+                    if j0 < K:                                      # K % 4 == 0: all four or none
+                        seen[base:base + 4] += 1
                 m += dm; t += dt
                 if m >= cpr:
                     m -= cpr; t += 1

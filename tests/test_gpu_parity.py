@@ -83,8 +83,8 @@ def test_rotate_const_other_vectors_and_random_phase(flags):
 
 def test_rotate_const_auto_selected_table_flavour():
     """Streams of >= 4 Mi phases are probed on the device: a sweep must take the word-table kernel, scattered
-    phases the byte-table kernel; either way the result is the oracle's, and three launches are enqueued
-    (probe + the chosen kernel + the one that returns at its gate)."""
+    phases the byte-table kernel; either way the result is the oracle's, and two table launches are enqueued
+    (the chosen kernel + the one that returns at its probe)."""
     core, op = both_p2r(**P2R_CONFIGS["cfg1"])
     rng = np.random.default_rng(SEED + 31)
     n = (1 << 22) + 5
@@ -93,9 +93,9 @@ def test_rotate_const_auto_selected_table_flavour():
                   ((np.arange(n, dtype=np.uint64) * 3) & 0xFFFFFF).astype(np.uint32)):
         before = zc.launch_count()
         got = host(core.rotate_const(131071, 0, dev(phase)))
-        # probe + 2 seeded launches (one returns at its gate) + the 5-sample rest: one group of 4 on the plain
+        # 2 seeded launches (one returns at its probe) + the 5-sample rest: one group of 4 on the plain
         # fast kernel and one sample on the generic kernel
-        assert zc.launch_count() - before == 5
+        assert zc.launch_count() - before == 4
         assert np.array_equal(got, zo.rotate_const(op, 131071, 0, phase))
 
 

@@ -34,22 +34,21 @@ def test_nco_comb_mapping_is_bit_exact(step):
         assert np.array_equal(blk, want), (hex(step), n, "block mapping")
 
 
-def test_nco_comb_is_taken_for_the_cfg4_step():
-    """The BASELINE configs[4] step 0x01234567: 225 steps are one turn minus 121/2^32, so K = 450 puts the lanes of a
-    quarter-warp 0.95 phase LSB apart.  The diagnostic says so, and the launch count shows the comb pass + one tail."""
+def test_nco_comb_is_taken_when_a_near_period_exists():
+    """Step 0x80000001: 64 steps are 32 turns plus 64/2^32, a quarter of a phase LSB -- the lanes of a quarter-warp share
+    table rows under K = 64.  The diagnostic says so, and the launch count shows one comb pass covering all of n.  The
+    BASELINE configs[4] step has no such K below n/8 (its near-period 225 is odd, 900 is 1.9 LSB off) and keeps the block
+    mapping with the byte table; slow NCOs keep the block mapping with the word table."""
     core, op = both_p2r(**P2R_CONFIGS["cfg1"])
     n = 1 << 22
-    K = comb_run(core, 0x01234567, n)
-    assert K == 450
-    d = (K * 0x01234567) & 0xFFFFFFFF
-    d = d - (1 << 32) if d >= (1 << 31) else d
-    assert abs(d) <= 256
-    assert comb_run(core, 0x100, n) == 0 and comb_run(core, 0xFFFFFF00, n) == 0      # slow NCOs keep the block mapping
+    assert comb_run(core, 0x80000001, n) == 64
+    assert comb_run(core, 0x01234567, n) == 0
+    assert comb_run(core, 0x100, n) == 0 and comb_run(core, 0xFFFFFF00, n) == 0
     l0 = zc.launch_count()
-    out = core.nco(131071, 0, 0, 0x01234567, n)
+    out = core.nco(131071, 0, 0, 0x80000001, n)
     torch.cuda.synchronize()
-    assert zc.launch_count() - l0 == 2          # comb pass over floor(n / 3600) tiles + the plain kernel on the rest
-    assert np.array_equal(host(out), zo.nco(op, 131071, 0, 0, 0x01234567, n))
+    assert zc.launch_count() - l0 == 1          # n is a multiple of the 512-sample tile: the comb pass is all there is
+    assert np.array_equal(host(out), zo.nco(op, 131071, 0, 0, 0x80000001, n))
 
 
 def test_nco_comb_misaligned_output_and_other_cores():

@@ -547,31 +547,41 @@ def main():
             torch.cuda.empty_cache()
             store = dist.distributed_c10d._get_default_store()
             if rank == 0:
-                try:
+                def run_multi(ne_):
                     devices = list(range(world))
                     core = zc.Cordic(**CFG1)
-                    total = world * ne
+                    total = world * ne_
                     hin = zc.ShardedPinnedBuffer(total, devices, np.uint32)      # shard g bound to device g's NUMA node
                     hout = zc.ShardedPinnedBuffer(2 * total, devices, np.int32)
                     ar = hin.array
-                    for s0 in range(0, total, 1 << 26):                           # the global sweep, shard after shard
-                        ar[s0:s0 + (1 << 26)] = (np.arange(s0, min(total, s0 + (1 << 26)), dtype=np.int64) & 0xFFFFFF).astype(np.uint32)
+                    period = 1 << 24                                              # the global sweep: i & 0xFFFFFF
+                    ar[:min(period, total)] = np.arange(min(period, total), dtype=np.uint32)
+                    for s0 in range(period, total, period):
+                        ar[s0:s0 + period] = ar[:min(period, total - s0)]
                     core.rotate_const_host_multi(X0, Y0, ar, hout.array, devices)   # warm-up
                     t0 = time.perf_counter()
                     for _ in range(e2e_steps):
                         core.rotate_const_host_multi(X0, Y0, ar, hout.array, devices)
                     dt = time.perf_counter() - t0
-                    sums = hout.array.reshape(-1, 2)[:1 << 24].sum(axis=0, dtype=np.int64).tolist()
-                    last = hout.array.reshape(-1, 2)[total - (1 << 24):].sum(axis=0, dtype=np.int64).tolist()
-                    e2e = {"value": total * e2e_steps / dt / 1e9, "unit": UNIT,
-                           "h2d_bytes_per_step": 4 * total, "d2h_bytes_per_step": 8 * total,
-                           "samples_per_gpu_per_step": ne, "steps": e2e_steps, "numa": hin.placement,
-                           "parity_spot_check": sums == [-39316, -39316] and last == [-39316, -39316],
-                           "api": "zc_rotate_const_host_multi: one process, one host thread + H2D->kernel->D2H pipeline per "
-                                  "device, %d devices, pinned host shards on each device's NUMA node" % world}
+                    o = hout.array.reshape(-1, 2)
+                    sums = o[:period].sum(axis=0, dtype=np.int64).tolist()
+                    last = o[total - period:].sum(axis=0, dtype=np.int64).tolist()
+                    r = {"value": total * e2e_steps / dt / 1e9, "unit": UNIT,
+                         "h2d_bytes_per_step": 4 * total, "d2h_bytes_per_step": 8 * total,
+                         "samples_per_gpu_per_step": ne_, "steps": e2e_steps, "numa": hin.placement,
+                         "parity_spot_check": sums == [-39316, -39316] and last == [-39316, -39316],
+                         "api": "zc_rotate_const_host_multi: one process, one host thread + H2D->kernel->D2H pipeline per "
+                                "device, %d devices, pinned host shards on each device's NUMA node" % world}
                     hin.free(); hout.free()
-                except Exception as e:                              # never lose the main line over it
-                    e2e = {"error": repr(e)[:300]}
+                    return r
+                try:
+                    e2e = run_multi(ne)
+                except Exception as e:                              # e.g. the host cannot pin 12 GiB per GPU: a quarter each
+                    try:
+                        e2e = run_multi(ne >> 2)
+                        e2e["note"] = "full size failed (%s); ran a quarter of samples_per_gpu_per_step" % repr(e)[:120]
+                    except Exception as e2:                         # never lose the main line over it
+                        e2e = {"error": repr(e2)[:300]}
                 store.set("zc_e2e_done", "1")
             else:
                 store.wait(["zc_e2e_done"])

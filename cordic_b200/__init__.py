@@ -140,6 +140,8 @@ _SIGNATURES = {
     "zc_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "zc_host_alloc_sharded": (ctypes.c_void_p, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "zc_device_numa_node": (ctypes.c_int, [ctypes.c_int]),
+    "zc_shard_range": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t),
+                                      ctypes.POINTER(ctypes.c_size_t)]),
     "zc_topolar_i16": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
     "zc_rotate_const_o16": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32,
@@ -211,6 +213,13 @@ def launch_count():
 def trim(device=-1):
     """Releases the library's cached device allocations (tables, staging buffers) -- zc_trim."""
     _check(lib().zc_trim(int(device)))
+
+
+def shard_range(n, ndev, g):
+    """(first, count) of shard g of ndev over n samples -- zc_shard_range, the rule the *_host_multi calls apply."""
+    a, b = ctypes.c_size_t(), ctypes.c_size_t()
+    _check(lib().zc_shard_range(int(n), int(ndev), int(g), ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
 
 
 # ---- configuration ------------------------------------------------------------------------

@@ -158,6 +158,13 @@ void *zc_host_alloc_sharded(size_t bytes, const int *devices, int ndev) { return
 void zc_host_free(void *ptr) { host_free(ptr); }
 int zc_device_numa_node(int device) { return device_numa_node(device); }
 
+int zc_shard_range(size_t n, int ndev, int g, size_t *first, size_t *count) {
+	if (ndev < 1 || g < 0 || g >= ndev || !first || !count) return set_error(ZC_EINVAL, "bad shard arguments");
+	*first = shard_first(n, g, ndev);
+	*count = shard_first(n, g + 1, ndev) - *first;
+	return ZC_OK;
+}
+
 int zc_rotate_const_host_multi(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int32_t *xy, size_t n,
 		const int *devices, int ndev) {
 	if (n && (!phase || !xy)) return set_error(ZC_EINVAL, "NULL buffer");

@@ -4,7 +4,7 @@
 // zc_rotate_const_host end to end, and prints Gsamples/s for both.  bench.py is the driver's contract; this is the
 // same measurement from the reference's own language.
 //   zcordic_bench [-i iw] [-o ow] [-p pw] [-n stages] [-x xtra] [-l lg2(samples)] [-s steps] [-d device] [-g gpus]
-//                 [--scatter] [--transport nccl|peer|both] [--chunks C] [--json]
+//                 [--scatter] [--transport nccl|peer|both] [--chunks C] [--json] [--pcie-probe]
 // -g G: the sample stream is sharded over devices 0..G-1 as independent chunks, one host thread per device (no collective:
 // the path has no exchange step); the figure is all samples over the slowest device's time.
 // -g G --scatter: device 0 owns the whole stream (G * 2^l samples) and every step scatters it over the G devices,
@@ -72,6 +72,62 @@ static float shard(const zc_params *p, int device, size_t n, size_t first, int s
 	cudaEventElapsedTime(&ms, e0, e1);
 	cudaFree(d_phase); cudaFree(d_xy);
 	return ms;
+}
+
+// Copy-only probe: what the host links of this box deliver when G devices move 4 B/sample in and 8 B/sample out
+// concurrently (the traffic of zc_rotate_const_host), each from its own pinned buffers -- plain cudaHostAlloc memory, then
+// zc_host_alloc_sharded memory (each device's shard on its own NUMA node).  The ceiling of the end-to-end figure.
+static int pcie_probe(int gpus, size_t n, bool json) {
+	std::vector<int> devices(gpus);
+	for (int g = 0; g < gpus; g++) devices[g] = g;
+	std::string out = "{\"what\": \"copy-only probe: every device moves 4 B/sample H2D and 8 B/sample D2H concurrently on two streams, "
+		"pinned host memory, all devices at once; Gsamples/s = the ceiling of zc_rotate_const_host_multi\", \"n_gpus\": " + std::to_string(gpus) +
+		", \"samples_per_gpu\": " + std::to_string(n);
+	for (int mode = 0; mode < 2; mode++) {
+		char *hin = nullptr, *hout = nullptr;
+		if (mode == 0) { hin = (char *)zc_host_alloc(n * 4 * gpus); hout = (char *)zc_host_alloc(n * 8 * gpus); }
+		else { hin = (char *)zc_host_alloc_sharded(n * 4 * gpus, devices.data(), gpus); hout = (char *)zc_host_alloc_sharded(n * 8 * gpus, devices.data(), gpus); }
+		if (!hin || !hout) { std::fprintf(stderr, "host alloc: %s\n", zc_last_error()); return 2; }
+		std::memset(hin, 1, n * 4 * gpus);
+		std::vector<double> secs(gpus, 0.0);
+		std::vector<std::thread> th;
+		std::atomic<int> ready{0};
+		for (int g = 0; g < gpus; g++)
+			th.emplace_back([&, g] {
+				cudaSetDevice(g);
+				char *din = nullptr, *dout = nullptr;
+				cudaStream_t s1, s2;
+				cudaMalloc(&din, n * 4); cudaMalloc(&dout, n * 8);
+				cudaStreamCreate(&s1); cudaStreamCreate(&s2);
+				auto pass = [&] {
+					cudaMemcpyAsync(din, hin + (size_t)g * n * 4, n * 4, cudaMemcpyHostToDevice, s1);
+					cudaMemcpyAsync(hout + (size_t)g * n * 8, dout, n * 8, cudaMemcpyDeviceToHost, s2);
+					cudaStreamSynchronize(s1); cudaStreamSynchronize(s2);
+				};
+				pass();
+				ready.fetch_add(1);
+				while (ready.load() < gpus) std::this_thread::yield();
+				const auto t0 = std::chrono::steady_clock::now();
+				for (int r = 0; r < 3; r++) pass();
+				secs[g] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / 3;
+				cudaFree(din); cudaFree(dout);
+			});
+		for (auto &t : th) t.join();
+		double worst = 0;
+		for (double v : secs) worst = v > worst ? v : worst;
+		const double gs = (double)n * gpus / worst / 1e9;
+		char buf[256];
+		std::snprintf(buf, sizeof(buf), ", \"%s\": {\"gsamples_per_s\": %.2f, \"h2d_gbs\": %.1f, \"d2h_gbs\": %.1f}", mode ? "numa_sharded_pinned" : "plain_pinned",
+			gs, gs * 4, gs * 8);
+		out += buf;
+		if (!json) std::printf("%d GPUs, %s: %.2f Gsamples/s (%.1f GB/s in + %.1f GB/s out)\n", gpus, mode ? "NUMA-sharded pinned" : "plain pinned", gs, gs * 4, gs * 8);
+		zc_host_free(hin); zc_host_free(hout);
+	}
+	out += ", \"numa_nodes\": [";
+	for (int g = 0; g < gpus; g++) out += (g ? ", " : "") + std::to_string(zc_device_numa_node(g));
+	out += "]}";
+	if (json) std::printf("%s\n", out.c_str());
+	return 0;
 }
 
 // Device 0 owns G * n samples; per step: scatter -> rotate on G devices -> gather.  Returns 0 and prints one JSON line.
@@ -150,11 +206,12 @@ static int scatter_bench(const zc_params *p, int gpus, size_t n_per, int steps, 
 
 int main(int argc, char **argv) {
 	int iw = 18, ow = 18, pw = 24, ns = 20, xtra = 2, lg = 28, steps = 20, device = 0, gpus = 1, chunks = 8;
-	bool scatter = false, json = false;
+	bool scatter = false, json = false, probe = false;
 	std::string transport = "both";
 	for (int k = 1; k < argc; k++) {
 		if (!std::strcmp(argv[k], "--scatter")) { scatter = true; continue; }
 		if (!std::strcmp(argv[k], "--json")) { json = true; continue; }
+		if (!std::strcmp(argv[k], "--pcie-probe")) { probe = true; continue; }
 		if (k + 1 >= argc) { std::fprintf(stderr, "option %s needs a value\n", argv[k]); return 1; }
 		if (!std::strcmp(argv[k], "--transport")) { transport = argv[++k]; continue; }
 		const int v = std::atoi(argv[k + 1]);
@@ -179,6 +236,10 @@ int main(int argc, char **argv) {
 	ZC(zc_derive_p2r(iw, ow, xtra, pw, ns, &p));		// sw/main.cpp:260-279
 	if (!json) std::printf("core: IW=%d OW=%d WW=%d PW=%d NSTAGES=%d GAIN=%.12f\n", p.iw, p.ow, p.ww, p.pw, p.nstages, p.gain);
 	const size_t n = (size_t)1 << lg;
+	if (probe) {
+		if (gpus > zc_device_count()) { std::fprintf(stderr, "-g %d but %d devices\n", gpus, zc_device_count()); return 1; }
+		return pcie_probe(gpus, n, json);
+	}
 	if (scatter) {
 		if (gpus > zc_device_count()) { std::fprintf(stderr, "-g %d but %d devices\n", gpus, zc_device_count()); return 1; }
 		return scatter_bench(&p, gpus, n, steps, chunks < 1 ? 1 : chunks, transport, json);

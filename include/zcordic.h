@@ -258,6 +258,11 @@ int zc_rotate_const_o16_host(const zc_params *p, int32_t x0, int32_t y0, const u
  * pipeline of the matching zc_*_host call on devices[g], one host thread per device, concurrently.  Returns when every
  * output word is in host memory.  Concatenated output == single-device output, byte for byte.  The NCO derives every
  * shard's start phase in closed form (phase0 + (n0 + first)*step), the truncation of bench/cpp/cordic_tb.cpp:128-138. */
+/* The sharding rule itself: shard g of ndev over n samples is [first, first + count), boundaries at multiples of 4
+ * samples (every shard keeps the 16-byte alignment of the whole), the last shard takes the ragged tail.  A caller that
+ * keeps device-resident shards (one process per GPU under torchrun/MPI) uses the same rule, and for the NCO passes
+ * n0 + first as the shard's start index. */
+int zc_shard_range(size_t n, int ndev, int g, size_t *first, size_t *count);
 int zc_rotate_const_host_multi(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int32_t *xy, size_t n,
 		const int *devices, int ndev);
 int zc_rotate_host_multi(const zc_params *p, const int32_t *xy_in, const uint32_t *phase, int32_t *xy_out, size_t n,

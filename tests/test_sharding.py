@@ -1,13 +1,21 @@
-"""CPU tier: the N>1 path.  Two gloo ranks each take their shard (cordic_b200.shard), compute it -- with the
-oracle standing in for the GPU, since this tier has none -- and rank 0 gathers; the concatenation must equal the
-single-rank result byte for byte.  Also pins shard_range's alignment/coverage contract."""
+"""CPU tier: the host logic of the N>1 path -- NOT multi-GPU parity (that is tests/test_gpu_round2.py::
+test_multi_device_parity_through_the_c_abi, which runs the kernels on every device of the box).  Here: the product's
+sharding rule (zc_shard_range, the one zc_*_host_multi applies) tiles any stream with aligned boundaries, the NCO's
+closed-form shard start equals the running accumulator, and a two-rank gloo scatter -> compute -> gather flow -- the
+oracle standing in for the device, since this tier has none -- concatenates to the single-rank result."""
 import os
 import socket
 
 import numpy as np
 import pytest
 
-from cordic_b200.shard import nco_start_phase, shard_range
+from cordic_b200 import shard_range
+
+
+def nco_start_phase(phase0, step, start):
+    """32-bit accumulator value at sample index `start`: phase0 + start*step (mod 2^32) -- what zc_nco_rotate computes
+    from n0 (include/zcordic.h)."""
+    return (phase0 + start * step) & 0xFFFFFFFF
 
 
 @pytest.mark.parametrize("n", [0, 1, 127, 128, 129, 1000, 4096, (1 << 20) + 77])
@@ -17,9 +25,8 @@ def test_shard_ranges_tile_the_stream(n, world):
     for r in range(world):
         start, count = shard_range(n, world, r)
         assert count >= 0
-        if count:
-            assert start == pos and start % 128 == 0
-            pos += count
+        assert start == pos and start % 4 == 0
+        pos += count
     assert pos == n
 
 

@@ -387,22 +387,32 @@ struct SeedTable<SRC, -1> {
 // DIRS_M prefix directions come from the sample's interval (16-byte row of signed bytes), the rest from the
 // residual row as in the byte flavour above.  A stage is then PRMT + IMAD.MOV + 2 SHF + 2 IMAD (6 issue slots
 // instead of 8), and the phase recursion is gone altogether.
-template <int NS, int J = 0>
+// TDW: the suffix stages (J >= DIRS_M) take their directions as IDP.2A multiplier words {0, d, 0, -d} from word planes
+// (as k_rotate_seeded's TD_TABLE_DP: 4 issue slots instead of 6; conflict-free when neighbouring samples have
+// neighbouring phases, which a probe of the phase stream establishes per call).
+template <int NS, bool TDW, int J = 0>
 struct DirStages {
-	static __device__ __forceinline__ void run(int &x, int &y, const uint32_t (&tp)[4], const uint32_t (&td)[4]) {
+	static __device__ __forceinline__ void run(int &x, int &y, const uint32_t (&tp)[4], const uint32_t (&td)[4],
+			const int (&wd)[SEED_MAX_NS]) {
 		constexpr int S = (J + 1 > 31) ? 31 : (J + 1);
-		const int d = (J < DIRS_M) ? sext_byte(tp[J >> 2], J & 3) : sext_byte(td[(J - DIRS_M) >> 2], (J - DIRS_M) & 3);
-		const int nd = ineg(d);
 		const int sy = y >> S, sx = x >> S;
-		const int x1 = imad(sy, nd, x);
-		const int y1 = imad(sx, d, y);
+		int x1, y1;
+		if (TDW && J >= DIRS_M) {
+			x1 = dp2a_lo(sy, wd[J - DIRS_M], x);
+			y1 = dp2a_hi(sx, wd[J - DIRS_M], y);
+		} else {
+			const int d = (J < DIRS_M) ? sext_byte(tp[J >> 2], J & 3) : sext_byte(td[(J - DIRS_M) >> 2], (J - DIRS_M) & 3);
+			const int nd = ineg(d);
+			x1 = imad(sy, nd, x);
+			y1 = imad(sx, d, y);
+		}
 		x = x1; y = y1;
-		DirStages<NS, J + 1>::run(x, y, tp, td);
+		DirStages<NS, TDW, J + 1>::run(x, y, tp, td, wd);
 	}
 };
-template <int NS>
-struct DirStages<NS, DIRS_M + NS> {
-	static __device__ __forceinline__ void run(int &, int &, const uint32_t (&)[4], const uint32_t (&)[4]) {}
+template <int NS, bool TDW>
+struct DirStages<NS, TDW, DIRS_M + NS> {
+	static __device__ __forceinline__ void run(int &, int &, const uint32_t (&)[4], const uint32_t (&)[4], const int (&)[SEED_MAX_NS]) {}
 };
 
 __device__ __forceinline__ int2 ldg_stream64(const int2 *p) {
@@ -411,12 +421,15 @@ __device__ __forceinline__ int2 ldg_stream64(const int2 *p) {
 	return r;
 }
 
-template <int NS, int SRC, bool RF>
+template <int NS, int SRC, bool RF, bool TDW>
 __global__ void __launch_bounds__(1024, 1)
 k_rotate_dirs(const uint32_t *__restrict__ phase, const int2 *__restrict__ xyin, int2 *__restrict__ xyout,
 		size_t nblocks, const __grid_constant__ CoreConsts c, const __grid_constant__ SeedConsts s,
-		const uint4 *__restrict__ tables) {
+		const uint4 *__restrict__ tables, const int probe_lim) {
 	extern __shared__ __align__(128) unsigned char smem[];
+	// auto-selection as in k_rotate_seeded: the word-suffix and the byte-suffix kernels are both enqueued, both evaluate
+	// the same probe of the same phase stream, one proceeds
+	if (probe_lim >= 0 && probe_local(phase, nblocks << 7, c.pshift, probe_lim) != (TDW ? PROBE_LOCAL : PROBE_SCATTERED)) return;
 	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
 	const uint32_t mbar = sbase + s.total_bytes;
 	if (threadIdx.x == 0) {
@@ -443,6 +456,10 @@ k_rotate_dirs(const uint32_t *__restrict__ phase, const int2 *__restrict__ xyin,
 	const uint4 *const TP = reinterpret_cast<const uint4 *>(smem + s.off_t2);
 	const unsigned char *const TD = smem + s.off_td;
 	const uint32_t lane = threadIdx.x & 31u;
+	uint32_t tdbase[SEED_MAX_NS / 4];		// one uniform shared-window base per word plane (see k_rotate_seeded)
+#pragma unroll
+	for (int j = 0; j < SEED_MAX_NS / 4; j++)
+		asm("mov.b32 %0, %1;" : "=r"(tdbase[j]) : "r"(sbase + s.off_td + (uint32_t)(j * s.td_plane)));
 	const uint32_t nwarps = gridDim.x * (blockDim.x >> 5), nblk = (uint32_t)nblocks;	// see k_rotate_seeded
 	// software prefetch of the next block's inputs (12 registers), as in k_rotate_seeded: the loads of block b+W are in
 	// flight while block b runs its 20 stages
@@ -487,7 +504,8 @@ k_rotate_dirs(const uint32_t *__restrict__ phase, const int2 *__restrict__ xyin,
 			const uint32_t tu = (uint32_t)imad((int)ph[k], (int)s.mul_u, (int)0x80000000u);
 			const uint32_t ur = tu >> s.ush;
 			const uint32_t rank = (T1[tu >> s.bsh] + ur) >> s.rsh;
-			const unsigned char *row = TD + (int)(ur - (uint32_t)TS[rank]);
+			const uint32_t row16 = ur - (uint32_t)TS[rank];		// byte offset of the residual's row (or 16-byte plane slot)
+			const unsigned char *row = TD + (int)row16;
 			// rtl/cordic.v:85-86 (extend) and :131-188 (quarter turn selected by the octant)
 			const int ex = (v[k].x << c.in_shl) >> c.in_shr, ey = (v[k].y << c.in_shl) >> c.in_shr;
 			int x, y;
@@ -495,14 +513,24 @@ k_rotate_dirs(const uint32_t *__restrict__ phase, const int2 *__restrict__ xyin,
 			const uint4 tpv = TP[rank];
 			const uint32_t tp[4] = {tpv.x, tpv.y, tpv.z, tpv.w};
 			uint32_t td[4] = {0, 0, 0, 0};
-			if (NS > 0 && NS <= 8) {
+			int wd[SEED_MAX_NS];
+			if (TDW) {
+#pragma unroll
+				for (int j = 0; j < NS; j += 4) {
+					const int4 dv = lds128(row16 + tdbase[j >> 2]);
+					wd[j] = dv.x;
+					if (j + 1 < SEED_MAX_NS) wd[j + 1] = dv.y;
+					if (j + 2 < SEED_MAX_NS) wd[j + 2] = dv.z;
+					if (j + 3 < SEED_MAX_NS) wd[j + 3] = dv.w;
+				}
+			} else if (NS > 0 && NS <= 8) {
 				const int2 w = *reinterpret_cast<const int2 *>(row);
 				td[0] = (uint32_t)w.x; td[1] = (uint32_t)w.y;
 			} else if (NS > 8) {
 				const int4 w = *reinterpret_cast<const int4 *>(row);
 				td[0] = (uint32_t)w.x; td[1] = (uint32_t)w.y; td[2] = (uint32_t)w.z; td[3] = (uint32_t)w.w;
 			}
-			DirStages<NS>::run(x, y, tp, td);
+			DirStages<NS, TDW>::run(x, y, tp, td, wd);
 			const int ox = RF ? round_out_fma(x, s) : round_out(x, c);
 			const int oy = RF ? round_out_fma(y, s) : round_out(y, c);
 			stg_stream64(xyout + base + (k << 5), make_int2(ox, oy));
@@ -512,27 +540,31 @@ k_rotate_dirs(const uint32_t *__restrict__ phase, const int2 *__restrict__ xyin,
 
 template <int SRC, int NS>
 struct DirsTable {
-	static cudaError_t launch(int ns, int grid, size_t smem, cudaStream_t st, const uint32_t *ph, const int2 *xin, int2 *out,
-			size_t nblocks, const CoreConsts &c, const SeedConsts &s, const uint4 *tables) {
+	static cudaError_t launch(int ns, bool tdw, int grid, size_t smem, cudaStream_t st, const uint32_t *ph, const int2 *xin, int2 *out,
+			size_t nblocks, const CoreConsts &c, const SeedConsts &s, const uint4 *tables, int probe_lim) {
 		if (ns == NS) {
 			const bool rf = c.do_round && c.wsh >= 9;
-			typedef void (*kern_t)(const uint32_t *, const int2 *, int2 *, size_t, const CoreConsts, const SeedConsts, const uint4 *);
-			kern_t kern = rf ? (kern_t)k_rotate_dirs<NS, SRC, true> : (kern_t)k_rotate_dirs<NS, SRC, false>;
+			typedef void (*kern_t)(const uint32_t *, const int2 *, int2 *, size_t, const CoreConsts, const SeedConsts, const uint4 *, int);
+			kern_t kern = tdw ? (rf ? (kern_t)k_rotate_dirs<NS, SRC, true, true> : (kern_t)k_rotate_dirs<NS, SRC, false, true>)
+					  : (rf ? (kern_t)k_rotate_dirs<NS, SRC, true, false> : (kern_t)k_rotate_dirs<NS, SRC, false, false>);
 			cudaError_t e = ensure_dynamic_smem((const void *)kern, smem);
 			if (e != cudaSuccess) return e;
-			kern<<<grid, 1024, smem, st>>>(ph, xin, out, nblocks, c, s, tables);
+			kern<<<grid, 1024, smem, st>>>(ph, xin, out, nblocks, c, s, tables, probe_lim);
 			return cudaGetLastError();
 		}
-		return DirsTable<SRC, NS - 1>::launch(ns, grid, smem, st, ph, xin, out, nblocks, c, s, tables);
+		return DirsTable<SRC, NS - 1>::launch(ns, tdw, grid, smem, st, ph, xin, out, nblocks, c, s, tables, probe_lim);
 	}
 };
 template <int SRC>
 struct DirsTable<SRC, -1> {
-	static cudaError_t launch(int, int, size_t, cudaStream_t, const uint32_t *, const int2 *, int2 *, size_t, const CoreConsts &,
-			const SeedConsts &, const uint4 *) { return cudaErrorInvalidValue; }
+	static cudaError_t launch(int, bool, int, size_t, cudaStream_t, const uint32_t *, const int2 *, int2 *, size_t, const CoreConsts &,
+			const SeedConsts &, const uint4 *, int) { return cudaErrorInvalidValue; }
 };
 
-// Per-sample (x,y): tries the table-directed kernel on the first floor(n/128)*128 samples.
+// Per-sample (x,y): tries the table-directed kernel on the first floor(n/128)*128 samples.  Suffix directions: IDP.2A
+// word planes when neighbouring samples have neighbouring phases (the NCO mixer: the host knows from the step; a phase
+// stream of 4 Mi samples or more: both kernels are enqueued and probe; ZC_F_SEED_WORDS / ZC_F_SEED_PACKED force), byte
+// rows otherwise.
 template <int SRC>
 static int dirs_rotate_try(const zc_params *p, const CoreConsts &c, const uint32_t *phase, const int32_t *xy_in,
 		int32_t *xy_out, size_t n, int device, int sms, cudaStream_t st, uint32_t flags, size_t &done, int &launches) {
@@ -543,15 +575,40 @@ static int dirs_rotate_try(const zc_params *p, const CoreConsts &c, const uint32
 	if (c.neff < DIRS_M || p->pw < 12) return ZC_OK;
 	CoreConsts key = c;		// the plan does not depend on the input vector
 	for (int q = 0; q < 4; q++) key.cx[q] = key.cy[q] = 0;
-	SeedPlan pl;
-	int rc = seed_plan_get(p, key, device, FL_DIRS, st, pl);
-	if (rc != ZC_OK) return rc;
-	if (!pl.usable) return ZC_OK;
-	cudaError_t e = DirsTable<SRC, SEED_MAX_NS>::launch(pl.NS, sms, pl.s.total_bytes + 16, st, phase, (const int2 *)xy_in,
-		(int2 *)xy_out, nblocks, c, pl.s, (const uint4 *)pl.dev);
+	bool words = (flags & ZC_F_SEED_WORDS) != 0, probe = false;
+	if (!(flags & (ZC_F_SEED_WORDS | ZC_F_SEED_PACKED)) && !(flags & ZC_F_NO_DP2A)) {
+		if (SRC == SRC_MIX) {
+			const int32_t sstep = (int32_t)c.nco_step;
+			const uint32_t mag = (uint32_t)(sstep < 0 ? -(int64_t)sstep : (int64_t)sstep);
+			words = (mag >> c.pshift) < 2u;
+		} else if (n >= ((size_t)1 << 22)) {
+			probe = true;
+		}
+	}
+	SeedPlan pl, plw;
+	int rc = ZC_OK;
+	if (words || probe) {
+		if ((rc = seed_plan_get(p, key, device, FL_DIRS_DP, st, plw)) != ZC_OK) return rc;
+		if (!plw.usable) { words = false; probe = false; }
+	}
+	if (!words) {
+		if ((rc = seed_plan_get(p, key, device, FL_DIRS, st, pl)) != ZC_OK) return rc;
+		if (!pl.usable) return ZC_OK;
+	}
+	const int probe_lim = probe ? 1 : -1;
+	cudaError_t e = cudaSuccess;
+	if (words || probe) {
+		e = DirsTable<SRC, SEED_MAX_NS>::launch(plw.NS, true, sms, plw.s.total_bytes + 16, st, phase, (const int2 *)xy_in,
+			(int2 *)xy_out, nblocks, c, plw.s, (const uint4 *)plw.dev, probe_lim);
+		if (e == cudaSuccess) launches++;
+	}
+	if (e == cudaSuccess && !words) {
+		e = DirsTable<SRC, SEED_MAX_NS>::launch(pl.NS, false, sms, pl.s.total_bytes + 16, st, phase, (const int2 *)xy_in,
+			(int2 *)xy_out, nblocks, c, pl.s, (const uint4 *)pl.dev, probe_lim);
+		if (e == cudaSuccess) launches++;
+	}
 	if (e != cudaSuccess)
 		return set_error(ZC_ECUDA, "launch of k_rotate_dirs failed: %s", cudaGetErrorString(e));
-	launches = 1;
 	done = nblocks << 7;
 	return ZC_OK;
 }

@@ -73,7 +73,7 @@ static bool seed_geometry(const zc_params *p, int neff, int M, int flavour, std:
 	const size_t nres = (size_t)(rmax - rmin + 1);
 	// bytes per TD row slot: 16 (one int4 plane entry) or, packed, one signed byte per stage
 	const int lgrow = (packed && NS <= 8) ? 3 : 4;
-	const size_t b_t1 = (size_t)4 << LB, b_ts = (R * 4 + 15) & ~(size_t)15, b_t2 = R * (flavour == FL_DIRS ? 16 : 32),
+	const size_t b_t1 = (size_t)4 << LB, b_ts = (R * 4 + 15) & ~(size_t)15, b_t2 = R * (fl_dirs(flavour) ? 16 : 32),
 		     b_td = packed ? ((nres << lgrow) + 15) & ~(size_t)15 : nres * (size_t)nsp * 4;
 	const size_t total = b_t1 + b_ts + b_t2 + b_td;
 	if (total + 16 > SEED_SMEM_LIMIT) return false;
@@ -138,6 +138,7 @@ int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, int flavo
 		// IDP.2A multiplies the low 16 bits of x>>sh, y>>sh: exact when |x|,|y| < 2^(WW-1) and sh >= WW-16
 		if (ok && flavour == FL_WORDS_DP && pl.s.M + 1 < p->ww - 16) ok = false;
 	}
+	if (ok && flavour == FL_DIRS_DP && pl.s.M + 1 < p->ww - 16) ok = false;	// same 16-bit condition for the suffix shifts
 	if (ok) {
 		const SeedConsts &s = pl.s;
 		const int pshift = c.pshift;
@@ -158,7 +159,7 @@ int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, int flavo
 			}
 			t1[b] = (uint32_t)(((uint64_t)r << s.lgw) + (uint64_t)(W - off) - ((uint64_t)b << s.lgw)) << s.lgrow;
 		}
-		if (flavour == FL_DIRS) {		// per-interval prefix directions, one signed byte per stage, 16-byte rows
+		if (fl_dirs(flavour)) {		// per-interval prefix directions, one signed byte per stage, 16-byte rows
 			unsigned char *tp = reinterpret_cast<unsigned char *>(host.data()) + s.off_t2;
 			for (size_t k = 0; k < R; k++)
 				for (int j = 0; j < DIRS_M; j++)
@@ -175,7 +176,7 @@ int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, int flavo
 				const bool neg = ph < 0;
 				if (packed)
 					reinterpret_cast<unsigned char *>(td)[((size_t)(res - rmin) << s.lgrow) + j] = (unsigned char)(neg ? 0xff : 0x01);
-				else if (flavour == FL_WORDS_DP)	// bytes 3..0 = {0, d, 0, -d}
+				else if (fl_dp(flavour))	// bytes 3..0 = {0, d, 0, -d}
 					td[((size_t)(j >> 2) * nres + (size_t)(res - rmin)) * 4 + (j & 3)] = neg ? 0x00FF0001u : 0x000100FFu;
 				else
 					td[((size_t)(j >> 2) * nres + (size_t)(res - rmin)) * 4 + (j & 3)] = (uint32_t)(neg ? -1 : 1);

@@ -40,9 +40,11 @@ struct SeedConsts {
 // IDP.2A form: storing the pair (-d, d) per stage and building the multiplier word with one PRMT saves the negation but
 // doubles the rows, and their scattered reads cost more than that: 320 vs 374 Gsamples/s for the constant-vector kernel
 // on random phases, 181 vs 195 for per-sample vectors -- measured, dropped.)
-enum { FL_WORDS = 0, FL_PACKED = 1, FL_DIRS = 2, FL_WORDS_DP = 3 };
+// FL_DIRS_DP: per-interval prefix directions as in FL_DIRS, suffix directions as IDP.2A multiplier words as in FL_WORDS_DP
+enum { FL_WORDS = 0, FL_PACKED = 1, FL_DIRS = 2, FL_WORDS_DP = 3, FL_DIRS_DP = 4 };
 static inline bool fl_packed(int flavour) { return flavour == FL_PACKED || flavour == FL_DIRS; }
-static inline bool fl_dirs(int flavour) { return flavour == FL_DIRS; }
+static inline bool fl_dirs(int flavour) { return flavour == FL_DIRS || flavour == FL_DIRS_DP; }
+static inline bool fl_dp(int flavour) { return flavour == FL_WORDS_DP || flavour == FL_DIRS_DP; }
 constexpr int DIRS_M = 12;	// prefix depth of the FL_DIRS flavour (its kernel unrolls the byte indices)
 
 

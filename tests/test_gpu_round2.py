@@ -76,6 +76,37 @@ def test_nco_comb_chunks_concatenate():
     assert np.array_equal(whole[:1 << 20], zo.nco(op, 131071, 0, 99, 0x01234567, 1 << 20))
 
 
+# ---- per-sample vectors: word-table suffix ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["cfg1", "shipped", "cfg0"])
+def test_rotate_per_sample_word_suffix(name):
+    """zc_rotate with the suffix directions as IDP.2A word planes (forced, and auto-selected by the in-kernel probe for
+    streams of >= 4 Mi samples): sweeps, scattered phases and a sweep with a stride, corner vectors included."""
+    core, op = both_p2r(**P2R_CONFIGS[name])
+    rng = np.random.default_rng(SEED + 25)
+    lim = 1 << (core.IW - 1)
+    n = (1 << 22) + 133
+    xy = rng.integers(-lim, lim, size=(n, 2), dtype=np.int64).astype(np.int32)
+    xy[:4] = [[lim - 1, lim - 1], [-lim, -lim], [0, 0], [-lim, lim - 1]]
+    mask = (1 << core.PW) - 1
+    for pat in ("sweep", "random", "stride3"):
+        ph = (np.arange(n, dtype=np.uint32) & mask) if pat == "sweep" else \
+            rng.integers(0, 1 << core.PW, size=n, dtype=np.uint64).astype(np.uint32) if pat == "random" else \
+            ((np.arange(n, dtype=np.uint64) * 3) & mask).astype(np.uint32)
+        want = zo.rotate(op, xy, ph)
+        for flags in (zc.F_DEFAULT, zc.F_SEED_WORDS, zc.F_SEED_PACKED, zc.F_NO_DP2A):
+            l0 = zc.launch_count()
+            got = host(core.rotate(dev(xy), dev(ph), flags=flags))
+            assert np.array_equal(got, want), (name, pat, flags)
+            if flags == zc.F_DEFAULT and name == "cfg1":
+                # two table launches (one returns at its probe) + the 133-sample rest: 132 on the plain kernel, 1 generic
+                # (cores whose table geometry does not fit -- cfg0's 16-bit phase -- run on the plain kernels: 2 launches)
+                assert zc.launch_count() - l0 == 4, (name, pat)
+    m = (1 << 20) + 7                                  # the NCO mixer: a slow step takes the words, a fast one the bytes
+    for step in (0x40, 0x01234567):
+        phase = (((5 + np.arange(m, dtype=np.uint64) * step) & 0xFFFFFFFF) >> (32 - core.PW)).astype(np.uint32)
+        assert np.array_equal(host(core.mix(dev(xy[:m]), 5, step)), zo.rotate(op, xy[:m], phase)), (name, hex(step))
+
+
 # ---- packed port words -------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["cfg2", "shipped"])
 def test_topolar_i16_equals_topolar(name):

@@ -383,6 +383,37 @@ class Bench:
             return bool(torch.equal(v.to(torch.int32), w["o_val"][:m]))
         return None
 
+    def packed_e2e(self, w, steps=3):
+        """End to end through the packed-port host entry points (pinned buffers, copies inside the timing): what a
+        narrower port word buys on the PCIe-bound host path (VERDICT r1 "Next" #8)."""
+        zc, torch = self.zc, self.torch
+        kind, ne = w["kind"], min(w["nper"], 1 << 28)
+        if kind == "rotate_const_o16":
+            hin, hout = zc.PinnedBuffer(ne, np.uint32), zc.PinnedBuffer(ne, np.int32)     # 4 B in, 2 x int16 out
+            hin.array[:] = w["phase"][:ne].cpu().numpy().view(np.uint32)
+            o16 = hout.array.view(np.int16).reshape(ne, 2)
+
+            def call():
+                w["core"].rotate_const_o16_host(32767, 0, hin.array, o16, device=self.local)
+            bi, bo, api = 4 * ne, 4 * ne, "zc_rotate_const_o16_host"
+        else:
+            hin, hout = zc.PinnedBuffer(ne, np.int32), zc.PinnedBuffer(2 * ne, np.int32)  # int16 x 2 in, mag + phase out
+            hin.array[:] = w["iq"][:ne].cpu().numpy().view(np.int32).reshape(-1)
+            i16 = hin.array.view(np.int16).reshape(ne, 2)
+
+            def call():
+                w["core"].topolar_i16_host(i16, hout.array[:ne], hout.array[ne:].view(np.uint32), device=self.local)
+            bi, bo, api = 4 * ne, 8 * ne, "zc_topolar_i16_host"
+        call()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        hin.free(); hout.free()
+        return {"value": ne * steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
+                "samples_per_gpu_per_step": ne, "steps": steps, "api": api + " (pinned host buffers)"}
+
     def timed(self, step, steps, warmup):
         """W untimed steps, then exactly K steps between CUDA events on the launching stream, barrier +
         synchronize on both sides; returns (ms on this rank, ms max over ranks, host-clock window, launches)."""
@@ -425,11 +456,14 @@ class Bench:
             steps = int(self.max_over_ranks(steps))                 # every rank runs the same count
             ms, ms_max, win, launches = self.timed(w["step"], steps, 0)
             ok = self.spot_check(w, phase_mode)
+            e2e = self.packed_e2e(w) if self.world == 1 and kind in ("rotate_const_o16", "topolar_i16") else None
             out = {"workload": workload, "phase": phase_mode if kind != "nco" else "nco step 0x%08x, n0 = rank * samples_per_gpu" % NCO_STEP,
                    "core": core_name(kind, opts), "samples_per_gpu_per_step": nper, "steps": steps, "warmup": 6,
                    "value": self.world * nper * steps / (ms_max * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_max / steps,
                    "roofline": self.roofline(bytes_per, nper, ms, steps), "launches_per_step": launches / steps,
                    "parity_spot_check": ok}
+            if e2e:
+                out["e2e"] = e2e
             if self.rank == 0:
                 out["clocks"] = self.sampler.window(*win)
             return out

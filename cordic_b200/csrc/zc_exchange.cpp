@@ -78,7 +78,7 @@ void zc_exchange_destroy(zc_exchange *x) {
 }
 
 int zc_exchange_create(const int *devices, int ndev, int transport, size_t max_piece, zc_exchange **out) {
-	if (!devices || !out || ndev < 1 || ndev > 64 || (transport != ZC_XCHG_NCCL && transport != ZC_XCHG_PEER)) return ZC_EINVAL;
+	if (!devices || !out || ndev < 1 || ndev > 64 || transport < ZC_XCHG_NCCL || transport > ZC_XCHG_COPY) return ZC_EINVAL;
 	zc_exchange *x = new zc_exchange();
 	x->ndev = ndev; x->transport = transport; x->max_piece = max_piece;
 	x->d.resize(ndev);
@@ -96,19 +96,26 @@ int zc_exchange_create(const int *devices, int ndev, int transport, size_t max_p
 			e = cudaEventCreateWithFlags(&v.ev_sc[b], cudaEventDisableTiming);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v.ev_k[b], cudaEventDisableTiming);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v.ev_ga[b], cudaEventDisableTiming);
-			if (e == cudaSuccess && transport == ZC_XCHG_NCCL && g > 0) {
+			if (e == cudaSuccess && transport != ZC_XCHG_PEER && g > 0) {
 				e = cudaMalloc((void **)&v.in[b], max_piece * 4);
 				if (e == cudaSuccess) e = cudaMalloc((void **)&v.out[b], max_piece * 8);
 			}
 		}
 		if (e != cudaSuccess) { std::fprintf(stderr, "zc_exchange_create: %s\n", cudaGetErrorString(e)); return fail(ZC_ECUDA); }
-		if (transport == ZC_XCHG_PEER && g > 0) {		// devices[g] reads and writes devices[0]'s memory directly
+		if (transport != ZC_XCHG_NCCL && g > 0) {		// devices[g] reads and writes devices[0]'s memory directly (kernels or copy engines)
 			int can = 0;
 			cudaDeviceCanAccessPeer(&can, v.id, devices[0]);
 			if (!can) { std::fprintf(stderr, "zc_exchange_create: device %d cannot access device %d\n", v.id, devices[0]); return fail(ZC_ENODEV); }
 			e = cudaDeviceEnablePeerAccess(devices[0], 0);
 			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ZC_ECUDA);
 			cudaGetLastError();
+			// and the owner -> peer direction: the copy engines take the direct NVLink path only between mutually mapped devices
+			// (measured at N=4: 128 Gsamples/s after NCCL had mapped both directions, 89 with the peer -> owner mapping alone)
+			if (cudaSetDevice(devices[0]) == cudaSuccess) {
+				e = cudaDeviceEnablePeerAccess(v.id, 0);
+				cudaGetLastError();
+			}
+			cudaSetDevice(v.id);
 		}
 	}
 	if (transport == ZC_XCHG_NCCL && ndev > 1) {
@@ -133,6 +140,8 @@ int zc_scatter_rotate_gather(zc_exchange *x, const zc_params *p, int32_t x0, int
 	cudaGetDevice(&prev);
 	// chunk c = [c0, c1); piece g of it = [c0 + g*len/G, c0 + (g+1)*len/G), boundaries at multiples of 128 samples so
 	// that every piece keeps the alignment (and the table-seeded kernel's block size) of the whole
+	// the peer transport has no stages to overlap: one chunk, the largest pieces
+	if (x->transport == ZC_XCHG_PEER || G == 1) nchunks = 1;
 	const size_t per_chunk = ((n + (size_t)nchunks - 1) / (size_t)nchunks + 127) & ~(size_t)127;
 	auto piece_lo = [&](size_t c0, size_t len, int g) { return g >= G ? c0 + len : c0 + ((len * (size_t)g / (size_t)G) & ~(size_t)127); };
 	int rc = ZC_OK;
@@ -149,7 +158,8 @@ int zc_scatter_rotate_gather(zc_exchange *x, const zc_params *p, int32_t x0, int
 			}
 			continue;
 		}
-		// ---- NCCL transport ---------------------------------------------------------------------------------
+		// ---- staged transports: NCCL send/recv groups, or copy-engine peer copies ---------------------------------
+		const bool copy = x->transport == ZC_XCHG_COPY;
 		for (int g = 1; g < G; g++) {
 			if (piece_lo(c0, len, g + 1) - piece_lo(c0, len, g) > x->max_piece) return ZC_ERANGE;
 			if (ci >= NBUF) {	// staging buffer b of device g: its previous outputs must have left
@@ -157,14 +167,23 @@ int zc_scatter_rotate_gather(zc_exchange *x, const zc_params *p, int32_t x0, int
 				XC(cudaStreamWaitEvent(x->d[g].s_sc, x->d[g].ev_ga[b], 0));
 			}
 		}
-		XN(ncclGroupStart());
-		for (int g = 1; g < G; g++) {
-			const size_t lo = piece_lo(c0, len, g), cnt = piece_lo(c0, len, g + 1) - lo;
-			if (!cnt) continue;
-			XN(ncclSend(phase + lo, cnt, ncclUint32, g, x->comm_sc[0], x->d[0].s_sc));
-			XN(ncclRecv(x->d[g].in[b], cnt, ncclUint32, 0, x->comm_sc[g], x->d[g].s_sc));
+		if (copy) {		// one copy engine transfer per peer, pulled on the peer's own scatter stream
+			for (int g = 1; g < G; g++) {
+				const size_t lo = piece_lo(c0, len, g), cnt = piece_lo(c0, len, g + 1) - lo;
+				if (!cnt) continue;
+				XC(cudaSetDevice(x->d[g].id));
+				XC(cudaMemcpyPeerAsync(x->d[g].in[b], x->d[g].id, phase + lo, x->d[0].id, cnt * 4, x->d[g].s_sc));
+			}
+		} else {
+			XN(ncclGroupStart());
+			for (int g = 1; g < G; g++) {
+				const size_t lo = piece_lo(c0, len, g), cnt = piece_lo(c0, len, g + 1) - lo;
+				if (!cnt) continue;
+				XN(ncclSend(phase + lo, cnt, ncclUint32, g, x->comm_sc[0], x->d[0].s_sc));
+				XN(ncclRecv(x->d[g].in[b], cnt, ncclUint32, 0, x->comm_sc[g], x->d[g].s_sc));
+			}
+			XN(ncclGroupEnd());
 		}
-		XN(ncclGroupEnd());
 		for (int g = 0; g < G && rc == ZC_OK; g++) {
 			const size_t lo = piece_lo(c0, len, g), cnt = piece_lo(c0, len, g + 1) - lo;
 			Dev &v = x->d[g];
@@ -181,14 +200,23 @@ int zc_scatter_rotate_gather(zc_exchange *x, const zc_params *p, int32_t x0, int
 			XC(cudaStreamWaitEvent(v.s_ga, v.ev_k[b], 0));
 		}
 		if (rc != ZC_OK) break;
-		XN(ncclGroupStart());
-		for (int g = 1; g < G; g++) {
-			const size_t lo = piece_lo(c0, len, g), cnt = piece_lo(c0, len, g + 1) - lo;
-			if (!cnt) continue;
-			XN(ncclSend(x->d[g].out[b], 2 * cnt, ncclInt32, 0, x->comm_ga[g], x->d[g].s_ga));
-			XN(ncclRecv(xy + 2 * lo, 2 * cnt, ncclInt32, g, x->comm_ga[0], x->d[0].s_ga));
+		if (copy) {		// pushed by the peer's own gather stream into the owner's output
+			for (int g = 1; g < G; g++) {
+				const size_t lo = piece_lo(c0, len, g), cnt = piece_lo(c0, len, g + 1) - lo;
+				if (!cnt) continue;
+				XC(cudaSetDevice(x->d[g].id));
+				XC(cudaMemcpyPeerAsync(xy + 2 * lo, x->d[0].id, x->d[g].out[b], x->d[g].id, cnt * 8, x->d[g].s_ga));
+			}
+		} else {
+			XN(ncclGroupStart());
+			for (int g = 1; g < G; g++) {
+				const size_t lo = piece_lo(c0, len, g), cnt = piece_lo(c0, len, g + 1) - lo;
+				if (!cnt) continue;
+				XN(ncclSend(x->d[g].out[b], 2 * cnt, ncclInt32, 0, x->comm_ga[g], x->d[g].s_ga));
+				XN(ncclRecv(xy + 2 * lo, 2 * cnt, ncclInt32, g, x->comm_ga[0], x->d[0].s_ga));
+			}
+			XN(ncclGroupEnd());
 		}
-		XN(ncclGroupEnd());
 		for (int g = 1; g < G; g++) {
 			XC(cudaSetDevice(x->d[g].id));
 			XC(cudaEventRecord(x->d[g].ev_ga[b], x->d[g].s_ga));

@@ -4,7 +4,7 @@
 // zc_rotate_const_host end to end, and prints Gsamples/s for both.  bench.py is the driver's contract; this is the
 // same measurement from the reference's own language.
 //   zcordic_bench [-i iw] [-o ow] [-p pw] [-n stages] [-x xtra] [-l lg2(samples)] [-s steps] [-d device] [-g gpus]
-//                 [--scatter] [--transport nccl|peer|both] [--chunks C] [--json] [--pcie-probe]
+//                 [--scatter] [--transport nccl|peer|copy|both] [--chunks C] [--json] [--pcie-probe]
 // -g G: the sample stream is sharded over devices 0..G-1 as independent chunks, one host thread per device (no collective:
 // the path has no exchange step); the figure is all samples over the slowest device's time.
 // -g G --scatter: device 0 owns the whole stream (G * 2^l samples) and every step scatters it over the G devices,
@@ -158,8 +158,8 @@ static int scatter_bench(const zc_params *p, int gpus, size_t n_per, int steps, 
 	double best = 0;
 	std::string best_name, detail;
 	bool parity = true;
-	for (int tr = 0; tr < 2; tr++) {
-		const char *name = tr == ZC_XCHG_NCCL ? "nccl" : "peer";
+	for (int tr = 0; tr < 3; tr++) {
+		const char *name = tr == ZC_XCHG_NCCL ? "nccl" : tr == ZC_XCHG_PEER ? "peer" : "copy";
 		if (transport != "both" && transport != name) continue;
 		zc_exchange *x = nullptr;
 		int rc = zc_exchange_create(devices.data(), gpus, tr, max_piece, &x);
@@ -198,7 +198,7 @@ static int scatter_bench(const zc_params *p, int gpus, size_t n_per, int steps, 
 		std::printf("{\"value\": %.2f, \"unit\": \"Gsamples/s\", \"transport\": \"%s\", \"n_gpus\": %d, \"samples_per_gpu_per_step\": %zu, "
 			"\"steps\": %d, \"chunks\": %d, \"parity\": %s, %s, \"what\": \"device 0 owns the whole phase stream; per step it is scattered over "
 			"the devices, rotated and gathered back (libzcordic_nccl: ncclSend/ncclRecv groups, 3-stage pipeline | kernels on peer "
-			"memory over NVLink); host wall clock around complete calls; parity = output byte-identical to device 0 alone\"}\n",
+			"memory over NVLink | the same pipeline with copy-engine transfers); host wall clock around complete calls; parity = output byte-identical to device 0 alone\"}\n",
 			best, best_name.c_str(), gpus, n_per, steps, chunks, parity ? "true" : "false", detail.c_str());
 	cudaFree(d_phase); cudaFree(d_xy); cudaFree(d_ref);
 	return parity ? 0 : 4;

@@ -12,7 +12,9 @@
  *                 gather(k-1) overlap;
  *   ZC_XCHG_PEER  no staging and no collective at all: with peer access enabled the rotation kernel on devices[g] loads
  *                 its phases from, and stores its outputs to, devices[0]'s memory directly over NVLink -- compute and
- *                 transfer fused in one kernel, overlapped word by word.
+ *                 transfer fused in one kernel, overlapped word by word;
+ *   ZC_XCHG_COPY  the staged pipeline of the NCCL transport with the transfers done by the copy engines
+ *                 (cudaMemcpyPeerAsync on the peers' own streams): no communication kernel competes for the SMs.
  * Single process; the handle owns communicators, streams, events and staging buffers and is not thread-safe.
  */
 #ifndef ZCORDIC_NCCL_H
@@ -24,7 +26,7 @@
 extern "C" {
 #endif
 
-enum { ZC_XCHG_NCCL = 0, ZC_XCHG_PEER = 1 };
+enum { ZC_XCHG_NCCL = 0, ZC_XCHG_PEER = 1, ZC_XCHG_COPY = 2 };
 
 typedef struct zc_exchange zc_exchange;
 
@@ -33,7 +35,8 @@ int  zc_exchange_create(const int *devices, int ndev, int transport, size_t max_
 void zc_exchange_destroy(zc_exchange *x);
 
 /* rtl/cordic.v with constant (i_xval, i_yval) over the n phases at phase_dev0 (device memory of devices[0]); outputs to
- * xy_dev0 (2n words on devices[0]).  nchunks >= 1 pipeline chunks.  Enqueues on the handle's own streams and returns
+ * xy_dev0 (2n words on devices[0]).  nchunks >= 1 pipeline chunks (NCCL transport; the peer transport has no stages to
+ * overlap and always works on the whole stream at once).  Enqueues on the handle's own streams and returns
  * when everything is complete on devices[0]. */
 int  zc_scatter_rotate_gather(zc_exchange *x, const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase_dev0,
 		int32_t *xy_dev0, size_t n, int nchunks);

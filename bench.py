@@ -493,6 +493,8 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the extra BASELINE configurations after the headline")
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--sustained-steps", type=int, default=400)
+    ap.add_argument("--configs-seconds", type=float, default=0.25,
+                    help="device time each extra configuration is held for (0: the minimum of 5 steps, e.g. under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     kind, nper, bytes_per, opts = WORKLOADS[args.workload]
@@ -658,7 +660,7 @@ def main():
             if wl == args.workload and pm == args.phase:
                 continue
             try:
-                configs.append(B.config_pass(wl, pm))
+                configs.append(B.config_pass(wl, pm, min_seconds=args.configs_seconds))
             except Exception as e:                                  # noqa: BLE001 - one pass must not cost the line
                 configs.append({"workload": wl, "phase": pm, "error": repr(e)[:300]})
 

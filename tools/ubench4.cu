@@ -55,7 +55,7 @@ template <int K0, int K1> struct IT { static __device__ __forceinline__ void run
 template <int K1> struct IT<K1, K1> { static __device__ __forceinline__ void run(int &, int &, unsigned &, const K &) {} };
 
 enum { V_INT = 0, V_FP = 1, V_MIX = 2 };
-template <int V> __global__ void __launch_bounds__(256) k(unsigned *out, int iters, const __grid_constant__ K c) {
+template <int V> __global__ void __launch_bounds__(256) kchain(unsigned *out, int iters, const __grid_constant__ K c) {
 	unsigned seed = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
 	unsigned acc = 0;
 	for (int it = 0; it < iters; it++) {
@@ -117,9 +117,9 @@ int main() {
 		cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 		for (int rep = 0; rep < 2; rep++) {	// second launch is the timed one
 			cudaEventRecord(e0);
-			if (v == 0) k<V_INT><<<grid, 256>>>(d[v], iters, c);
-			if (v == 1) k<V_FP><<<grid, 256>>>(d[v], iters, c);
-			if (v == 2) k<V_MIX><<<grid, 256>>>(d[v], iters, c);
+			if (v == 0) kchain<V_INT><<<grid, 256>>>(d[v], iters, c);
+			if (v == 1) kchain<V_FP><<<grid, 256>>>(d[v], iters, c);
+			if (v == 2) kchain<V_MIX><<<grid, 256>>>(d[v], iters, c);
 			cudaEventRecord(e1); cudaEventSynchronize(e1);
 		}
 		float ms; cudaEventElapsedTime(&ms, e0, e1);

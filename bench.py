@@ -456,7 +456,7 @@ class Bench:
             steps = int(self.max_over_ranks(steps))                 # every rank runs the same count
             ms, ms_max, win, launches = self.timed(w["step"], steps, 0)
             ok = self.spot_check(w, phase_mode)
-            e2e = self.packed_e2e(w) if self.world == 1 and kind in ("rotate_const_o16", "topolar_i16") else None
+            e2e = self.packed_e2e(w) if self.world == 1 and not self.args.no_e2e and kind in ("rotate_const_o16", "topolar_i16") else None
             out = {"workload": workload, "phase": phase_mode if kind != "nco" else "nco step 0x%08x, n0 = rank * samples_per_gpu" % NCO_STEP,
                    "core": core_name(kind, opts), "samples_per_gpu_per_step": nper, "steps": steps, "warmup": 6,
                    "value": self.world * nper * steps / (ms_max * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_max / steps,

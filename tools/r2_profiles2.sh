@@ -1,0 +1,20 @@
+#!/bin/bash
+# round 2: --set full captures of the kernels round 2 added or changed (1 GPU, under gpurun); kernels picked by mangled name
+set -u
+mkdir -p gpurun_out
+cap2() {
+  tag=$1; kern=$2; skip=$3; shift 3
+  ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:"$kern" -s $skip -c 1 -f -o gpurun_out/prof_${tag} \
+      python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-configs --no-sustained "$@" > gpurun_out/prof_${tag}.log 2>&1
+  ncu -i gpurun_out/prof_${tag}.ncu-rep --page raw --csv > gpurun_out/prof_${tag}_raw.csv 2>/dev/null
+  python tools/ncu_summary.py gpurun_out/prof_${tag}_raw.csv "ncu --set full --clock-control none, python bench.py --steps 2 --warmup 3 $* (launch 4 of the kernel)" > gpurun_out/prof_${tag}.md 2>/dev/null
+}
+cap2 r2_rotate_cfg1 'k_rotate_seededILi8ELi0ELb1ELi3ELi0ELb0E' 3 --workload rotate_cfg1
+cap2 r2_rotxy_words 'k_rotate_dirsILi8ELi1ELb1ELb1E' 3 --workload rotate_xy_cfg1
+cap2 r2_rotxy_random 'k_rotate_dirsILi8ELi1ELb1ELb0E' 3 --workload rotate_xy_cfg1 --phase random
+cap2 r2_nco_comb 'k_rotate_seededILi8ELi2ELb1ELi3ELi1ELb0E' 3 --workload nco_cfg1 --nco-step 0x80000001
+cap2 r2_nco_cfg4_packed 'k_rotate_seededILi8ELi2ELb1ELi2ELi0ELb0E' 3 --workload nco_cfg1
+cap2 r2_rotate_o16 'k_rotate_seededILi3ELi0ELb1ELi3ELi0ELb1E' 3 --workload rotate_o16_cfg0
+cap2 r2_topolar_i16 'k_topolarILi21ELi10ELb1E' 3 --workload topolar_i16_cfg2
+rm -f gpurun_out/*.ncu-rep
+for t in r2_rotate_cfg1 r2_rotxy_words r2_rotxy_random r2_nco_comb r2_nco_cfg4_packed r2_rotate_o16 r2_topolar_i16; do echo "== $t"; grep "Kernel Name\|time_duration\|dram__bytes\|issue_active.avg.pct\|lsu_wavefronts.sum.pct\|wavefronts_mem_shared.sum \|pipe_alu\|fmaheavy" gpurun_out/prof_$t.md; done

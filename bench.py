@@ -487,6 +487,7 @@ def main():
     ap.add_argument("--no-dp2a", action="store_true", help="seeded word table: IMAD + negation instead of IDP.2A (A/B)")
     ap.add_argument("--no-tail", action="store_true", help="topolar: every stage in its full form (A/B of the short late stages)")
     ap.add_argument("--no-comb", action="store_true", help="NCO: keep the block mapping for every step (A/B of the comb mapping)")
+    ap.add_argument("--no-merge", action="store_true", help="byte table: keep the TS lookup separate (A/B of the merged records)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-exchange", action="store_true", help="skip the NCCL scatter/gather-inclusive figure (N>1)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -513,6 +514,8 @@ def main():
         flags |= zc.F_NO_DP2A
     if args.no_comb:
         flags |= zc.F_NO_COMB
+    if args.no_merge:
+        flags |= zc.F_NO_MERGE
     # ---- headline: synthetic inputs resident in HBM before the timed region (4-12 GiB: far larger than L2) ---------
     w = B.make(args.workload, args.phase, nper, flags=flags, no_tail=args.no_tail, nco_step=args.nco_step)
     time.sleep(0.25)

@@ -28,6 +28,7 @@ F_SEED_WORDS = 32
 F_NO_TAIL = 64
 F_NO_DP2A = 128
 F_NO_COMB = 256
+F_NO_MERGE = 512
 
 MODE_P2R, MODE_R2P = 0, 1
 

@@ -99,7 +99,13 @@ struct Suffix<NS, NS> {
 	static __device__ __forceinline__ void run_reg(int &, int &, int &, const CoreConsts &, const SeedConsts &) {}
 };
 
-enum { TD_TABLE = PROBE_LOCAL, TD_REGS = 1, TD_PACKED = PROBE_SCATTERED, TD_TABLE_DP = 3 };
+// TD_PACKED_M: TD_PACKED on a FL_PACKED_M plan (the TS lookup folded into the (x, y) record)
+enum { TD_TABLE = PROBE_LOCAL, TD_REGS = 1, TD_PACKED = PROBE_SCATTERED, TD_TABLE_DP = 3, TD_PACKED_M = 4 };
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+	uint32_t r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+	return r;
+}
 // Sign-extends byte `b` of w with one PRMT (selector nibble 8|b replicates that byte's sign bit;
 // __byte_perm() masks the replicate bit off, hence the PTX).
 __device__ __forceinline__ int sext_byte(uint32_t w, int b) {
@@ -177,7 +183,8 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 	// Auto-selection: both table flavours are enqueued back to back and every CTA of both evaluates the same probe of
 	// the same input (probe_local: a pure function of the phase stream); the flavour the verdict does not name returns
 	// here, before touching shared memory.  No device-side state is shared between calls, streams or graph replays.
-	if (probe_lim >= 0 && probe_local(phase, nblocks << 7, c.pshift, probe_lim) != (TDM == TD_TABLE_DP ? TD_TABLE : TDM)) return;
+	if (probe_lim >= 0 && probe_local(phase, nblocks << 7, c.pshift, probe_lim) !=
+			(TDM == TD_TABLE_DP ? TD_TABLE : TDM == TD_PACKED_M ? TD_PACKED : TDM)) return;
 	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
 	const uint32_t mbar = sbase + s.total_bytes;		// 8-byte slot after the tables
 
@@ -240,8 +247,15 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 			const uint32_t u16 = tu[k] >> s.ush;				// 16 * reduced phase
 			const uint32_t rank = (T1[tu[k] >> s.bsh] + u16) >> s.rsh;	// carries past the step, if any
 			const int2 xy = T2[__funnelshift_l(tq[k], rank, 2)];		// row rank*4 + quarter turn
-			x[k] = xy.x; y[k] = xy.y;
-			row16[k] = u16 - (uint32_t)TS[rank];		// residual after M stages, as the byte offset of its TD row
+			if (TDM == TD_PACKED_M) {
+				// record words: (x << recsh | low byte of TS), (y << recsh | high byte of TS), TS taken modulo 2^16 -- the
+				// TD table is smaller than that, so the difference below is exact after the mask; one lookup fewer
+				x[k] = xy.x >> s.recsh; y[k] = xy.y >> s.recsh;
+				row16[k] = (u16 - prmt((uint32_t)xy.x, (uint32_t)xy.y, 0x7640u)) & 0xffffu;
+			} else {
+				x[k] = xy.x; y[k] = xy.y;
+				row16[k] = u16 - (uint32_t)TS[rank];	// residual after M stages, as the byte offset of its TD row
+			}
 		}
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
@@ -258,7 +272,7 @@ k_rotate_seeded(const uint32_t *__restrict__ phase, int2 *__restrict__ xyout, si
 						if (j + 3 < SEED_MAX_NS) d[j + 3] = dv.w;
 					}
 					Suffix<NS>::template run<TDM == TD_TABLE_DP ? MA_DP2A : MA_XNEG>(x[k], y[k], d, s);
-				} else if (TDM == TD_PACKED) {
+				} else if (TDM == TD_PACKED || TDM == TD_PACKED_M) {
 					const unsigned char *row = TD + (int)row16[k];	// 8-byte (NS<=8) or 16-byte rows
 					uint32_t w[4] = {0, 0, 0, 0};
 					if (NS <= 8) {
@@ -363,6 +377,7 @@ struct SeedTable {
 			else if (tdm == TD_TABLE_DP) kern = ZC_PICK(TD_TABLE_DP);
 			if constexpr (MAP == MAP_BLOCK) {
 				if (tdm == TD_PACKED) kern = ZC_PICK(TD_PACKED);
+				if (tdm == TD_PACKED_M) kern = ZC_PICK(TD_PACKED_M);
 				if constexpr (!OUT16) { if (tdm == TD_REGS) kern = ZC_PICK(TD_REGS); }
 			}
 #undef ZC_PICK
@@ -452,7 +467,6 @@ k_rotate_dirs(const uint32_t *__restrict__ phase, const int2 *__restrict__ xyin,
 		}
 	}
 	const uint32_t *const T1 = reinterpret_cast<const uint32_t *>(smem);
-	const int32_t *const TS = reinterpret_cast<const int32_t *>(smem + s.off_ts);
 	const uint4 *const TP = reinterpret_cast<const uint4 *>(smem + s.off_t2);
 	const unsigned char *const TD = smem + s.off_td;
 	const uint32_t lane = threadIdx.x & 31u;
@@ -504,13 +518,13 @@ k_rotate_dirs(const uint32_t *__restrict__ phase, const int2 *__restrict__ xyin,
 			const uint32_t tu = (uint32_t)imad((int)ph[k], (int)s.mul_u, (int)0x80000000u);
 			const uint32_t ur = tu >> s.ush;
 			const uint32_t rank = (T1[tu >> s.bsh] + ur) >> s.rsh;
-			const uint32_t row16 = ur - (uint32_t)TS[rank];		// byte offset of the residual's row (or 16-byte plane slot)
+			const uint4 tpv = TP[rank];		// 12 prefix directions (signed bytes) + the interval's row offset in the last word
+			const uint32_t row16 = ur - tpv.w;	// byte offset of the residual's row (or 16-byte plane slot)
 			const unsigned char *row = TD + (int)row16;
 			// rtl/cordic.v:85-86 (extend) and :131-188 (quarter turn selected by the octant)
 			const int ex = (v[k].x << c.in_shl) >> c.in_shr, ey = (v[k].y << c.in_shl) >> c.in_shr;
 			int x, y;
 			quarter_turn((int)(tq >> 30), ex, ey, x, y);
-			const uint4 tpv = TP[rank];
 			const uint32_t tp[4] = {tpv.x, tpv.y, tpv.z, tpv.w};
 			uint32_t td[4] = {0, 0, 0, 0};
 			int wd[SEED_MAX_NS];
@@ -735,14 +749,28 @@ static int seeded_rotate_try(const zc_params *p, const CoreConsts &c, const uint
 	const size_t rest_blocks = (n - off) >> 7;
 	if (off && (rest_blocks << 7) < ((size_t)1 << 20)) { done = off; return ZC_OK; }	// the plain kernels take the tail
 	if (scattered_nco) { tdm = TD_PACKED; have_words = false; }
-	if (tdm == TD_PACKED || tdm == TD_REGS) {
-		if ((rc = seed_plan_get(p, c, device, tdm == TD_PACKED ? FL_PACKED : FL_WORDS, st, pl)) != ZC_OK) return rc;
+	// the byte table comes with the TS lookup folded into the (x, y) records when the core allows (ZC_F_NO_MERGE: A/B)
+	auto packed_plan = [&](SeedPlan &out, int &tdm_out) -> int {
+		tdm_out = TD_PACKED;
+		if (!(flags & ZC_F_NO_MERGE)) {
+			const int prc = seed_plan_get(p, c, device, FL_PACKED_M, st, out);
+			if (prc != ZC_OK) return prc;
+			if (out.usable) { tdm_out = TD_PACKED_M; return ZC_OK; }
+		}
+		return seed_plan_get(p, c, device, FL_PACKED, st, out);
+	};
+	int tdm2 = TD_PACKED;
+	if (tdm == TD_PACKED) {
+		if ((rc = packed_plan(pl, tdm)) != ZC_OK) return rc;
+		if (!pl.usable) { done = off; return ZC_OK; }
+	} else if (tdm == TD_REGS) {
+		if ((rc = seed_plan_get(p, c, device, FL_WORDS, st, pl)) != ZC_OK) return rc;
 		if (!pl.usable) { done = off; return ZC_OK; }
 	} else if (!have_words) {
 		done = off; return ZC_OK;
 	}
 	if (probe) {
-		if ((rc = seed_plan_get(p, c, device, FL_PACKED, st, pl2)) != ZC_OK) return rc;
+		if ((rc = packed_plan(pl2, tdm2)) != ZC_OK) return rc;
 		if (!pl2.usable) probe = false;
 	}
 	CoreConsts cc = c;
@@ -757,7 +785,7 @@ static int seeded_rotate_try(const zc_params *p, const CoreConsts &c, const uint
 	if (e == cudaSuccess) launches++;
 	if (e == cudaSuccess && probe) {
 		L.smem = pl2.s.total_bytes + 16; L.s = &pl2.s; L.tables = (const uint4 *)pl2.dev;
-		e = SeedTable<SRC, SEED_MAX_NS>::template launch<MAP_BLOCK, OUT16>(pl2.NS, TD_PACKED, L);
+		e = SeedTable<SRC, SEED_MAX_NS>::template launch<MAP_BLOCK, OUT16>(pl2.NS, tdm2, L);
 		if (e == cudaSuccess) launches++;
 	}
 	if (e != cudaSuccess)

@@ -104,6 +104,16 @@ static bool seed_geometry(const zc_params *p, int neff, int M, int flavour, std:
 	return true;
 }
 
+// FL_PACKED_M: folds TS mod 2^16 (the byte offset of the interval's first direction row, modulo the table size bound)
+// into the low bytes of the interval's four (x, y) records.
+__global__ void k_seed_pack_records(int2 *__restrict__ t2, const uint32_t *__restrict__ ts, uint32_t R, int recsh) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= 4u * R) return;
+	const uint32_t c = ts[i >> 2] & 0xffffu;
+	const int2 v = t2[i];
+	t2[i] = make_int2((int)(((uint32_t)v.x << recsh) | (c & 0xffu)), (int)(((uint32_t)v.y << recsh) | (c >> 8)));
+}
+
 static std::mutex g_seed_mu;
 static std::vector<SeedPlan> g_seed_cache;
 static uint64_t g_seed_clock = 0;
@@ -139,6 +149,12 @@ int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, int flavo
 		if (ok && flavour == FL_WORDS_DP && pl.s.M + 1 < p->ww - 16) ok = false;
 	}
 	if (ok && flavour == FL_DIRS_DP && pl.s.M + 1 < p->ww - 16) ok = false;	// same 16-bit condition for the suffix shifts
+	if (ok && fl_merged(flavour)) {
+		// eight free bits under x and y, and every TD byte offset below 2^16 (the kernel recovers it modulo 2^16)
+		const size_t td_bytes = (size_t)(rmax - rmin + 1) << pl.s.lgrow;
+		if (p->ww > 24 || td_bytes > 65536) ok = false;
+		pl.s.recsh = 32 - p->ww;
+	}
 	if (ok) {
 		const SeedConsts &s = pl.s;
 		const int pshift = c.pshift;
@@ -168,6 +184,8 @@ int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, int flavo
 		for (size_t k = 0; k < R && ok; k++) {
 			ts[k] = (uint32_t)(int32_t)((iv[k].S + half + rmin) * ((int64_t)1 << s.lgrow));
 			rep[k] = (uint32_t)((uint64_t)iv[k].lo << pshift);
+			// the per-interval direction rows have four spare bytes: the row offset rides there (one lookup fewer)
+			if (fl_dirs(flavour)) host[s.off_t2 / 4 + k * 4 + 3] = ts[k];
 		}
 		const size_t nres = (size_t)(rmax - rmin + 1);
 		for (int64_t res = rmin; res <= rmax && ok; res++) {
@@ -192,6 +210,13 @@ int seed_plan_get(const zc_params *p, const CoreConsts &c, int device, int flavo
 				k_seed_fill_xy<<<(nthreads + 255) / 256, 256, 0, st>>>(
 					reinterpret_cast<const uint32_t *>(pl.dev) + s.total_bytes / 4,
 					reinterpret_cast<int2 *>(reinterpret_cast<char *>(pl.dev) + s.off_t2), (uint32_t)R, s.M, c);
+				e = cudaGetLastError();
+			}
+			if (e == cudaSuccess && fl_merged(flavour)) {
+				const uint32_t nthreads = 4u * (uint32_t)R;
+				k_seed_pack_records<<<(nthreads + 255) / 256, 256, 0, st>>>(
+					reinterpret_cast<int2 *>(reinterpret_cast<char *>(pl.dev) + s.off_t2),
+					reinterpret_cast<const uint32_t *>(reinterpret_cast<char *>(pl.dev) + s.off_ts), (uint32_t)R, s.recsh);
 				e = cudaGetLastError();
 			}
 			if (e == cudaSuccess) e = cudaStreamSynchronize(st);	// tables complete before any stream uses them

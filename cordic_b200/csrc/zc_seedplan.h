@@ -32,6 +32,7 @@ struct SeedConsts {
 	int32_t  td_plane;	// bytes per TD plane (nres*16)
 	uint32_t total_bytes;	// multiple of 16
 	int32_t  sh[SEED_MAX_NS];	// arithmetic shift of suffix stage j: min(M+j+1, 31)
+	int32_t  recsh;		// FL_PACKED_M: 32-WW, the shift that brings x / y down from the top of their record words
 	uint32_t R;
 };
 
@@ -41,8 +42,14 @@ struct SeedConsts {
 // doubles the rows, and their scattered reads cost more than that: 320 vs 374 Gsamples/s for the constant-vector kernel
 // on random phases, 181 vs 195 for per-sample vectors -- measured, dropped.)
 // FL_DIRS_DP: per-interval prefix directions as in FL_DIRS, suffix directions as IDP.2A multiplier words as in FL_WORDS_DP
-enum { FL_WORDS = 0, FL_PACKED = 1, FL_DIRS = 2, FL_WORDS_DP = 3, FL_DIRS_DP = 4 };
-static inline bool fl_packed(int flavour) { return flavour == FL_PACKED || flavour == FL_DIRS; }
+// FL_PACKED_M: FL_PACKED with the interval's TD-row offset merged into its (x, y) record -- (x << recsh | low byte,
+// y << recsh | high byte of TS mod 2^16) -- so that a sample costs three shared-memory lookups (bucket, record, direction
+// row) instead of four; needs WW <= 24 (eight free bits under each of x and y) and a direction table below 64 KB.
+// (The same merge under the IDP.2A word table measured 1 % slower on sweeps and 4 % slower on slow NCOs -- neighbouring
+// lanes share the TS word there, so the lookup it saves was nearly free: profiles/r2_merged_records_ab.txt -- dropped.)
+enum { FL_WORDS = 0, FL_PACKED = 1, FL_DIRS = 2, FL_WORDS_DP = 3, FL_DIRS_DP = 4, FL_PACKED_M = 5 };
+static inline bool fl_packed(int flavour) { return flavour == FL_PACKED || flavour == FL_DIRS || flavour == FL_PACKED_M; }
+static inline bool fl_merged(int flavour) { return flavour == FL_PACKED_M; }
 static inline bool fl_dirs(int flavour) { return flavour == FL_DIRS || flavour == FL_DIRS_DP; }
 static inline bool fl_dp(int flavour) { return flavour == FL_WORDS_DP || flavour == FL_DIRS_DP; }
 constexpr int DIRS_M = 12;	// prefix depth of the FL_DIRS flavour (its kernel unrolls the byte indices)

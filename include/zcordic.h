@@ -95,6 +95,9 @@ enum {
 	ZC_F_NO_DP2A       = 128,	/* seeded kernel, word table: multiply-adds as IMAD with an explicit negation instead of IDP.2A */
 	ZC_F_NO_TAIL       = 64,	/* topolar: every stage in its full form (by default the late stages, where y has provably
 				   converged below the shift, run a shorter instruction sequence with identical results) */
+	ZC_F_NO_MERGE      = 512,	/* seeded kernel, byte table: keep the interval's row offset in its own table (by default it rides in
+				   the low bytes of the (x, y) records when WW <= 24: three dependent shared-memory lookups per
+				   sample instead of four; same results) */
 	ZC_F_NO_COMB       = 256,	/* NCO with a scattering step: keep the block sample mapping + byte table (by default the
 				   engine looks for a comb mapping -- runs K samples apart with K*step ~ 0 mod 2^32 share a
 				   quarter-warp -- under which the lanes of a quarter-warp share word-table rows; same results) */

@@ -76,6 +76,28 @@ def test_nco_comb_chunks_concatenate():
     assert np.array_equal(whole[:1 << 20], zo.nco(op, 131071, 0, 99, 0x01234567, 1 << 20))
 
 
+# ---- byte table with merged records ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(P2R_CONFIGS))
+def test_rotate_const_merged_records(name):
+    """The byte-table kernel with the interval's row offset folded into its (x, y) records (three shared-memory lookups per
+    sample; cores with WW <= 24) against the four-lookup form (ZC_F_NO_MERGE) and the oracle: scattered phases, a sweep,
+    other input vectors, the NCO with a scattering step, packed outputs."""
+    core, op = both_p2r(**P2R_CONFIGS[name])
+    rng = np.random.default_rng(SEED + 26)
+    n = (1 << 20) + 77
+    lim = 1 << (core.IW - 1)
+    for x0, y0 in [(lim - 1, 0), (-lim, lim - 1), (3, -2)]:
+        for pat in ("random", "sweep"):
+            ph = (np.arange(n, dtype=np.uint32) & ((1 << core.PW) - 1)) if pat == "sweep" else \
+                rng.integers(0, 1 << core.PW, size=n, dtype=np.uint64).astype(np.uint32)
+            want = zo.rotate_const(op, x0, y0, ph)
+            for flags in (zc.F_SEED_PACKED | zc.F_FORCE_SEED, zc.F_SEED_PACKED | zc.F_FORCE_SEED | zc.F_NO_MERGE):
+                assert np.array_equal(host(core.rotate_const(x0, y0, dev(ph), flags=flags)), want), (name, x0, y0, pat, flags)
+    want = zo.nco(op, lim - 1, 0, 9, 0x01234567, n, n0=5)
+    for flags in (zc.F_FORCE_SEED, zc.F_FORCE_SEED | zc.F_NO_MERGE):
+        assert np.array_equal(host(core.nco(lim - 1, 0, 9, 0x01234567, n, n0=5, flags=flags)), want), (name, "nco", flags)
+
+
 # ---- per-sample vectors: word-table suffix ---------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["cfg1", "shipped", "cfg0"])
 def test_rotate_per_sample_word_suffix(name):

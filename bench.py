@@ -15,6 +15,7 @@ events and its own slice of the clock record,
   "sustained": the headline held for 400 steps (what the 1 kW power cap leaves of the burst figure).
 """
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -623,7 +624,7 @@ def main():
                         e2e = {"error": repr(e2)[:300]}
                 store.set("zc_e2e_done", "1")
             else:
-                store.wait(["zc_e2e_done"])
+                store.wait(["zc_e2e_done"], datetime.timedelta(seconds=3000))
             B.barrier()
 
     # ---- N>1: the same stream held by device 0, scattered and gathered over NCCL/NVLink each step --------------
@@ -648,7 +649,7 @@ def main():
                 exchange = {"error": repr(e)[:300]}
             store.set("zc_xchg_done", "1")
         else:
-            store.wait(["zc_xchg_done"])
+            store.wait(["zc_xchg_done"], datetime.timedelta(seconds=3000))
         B.barrier()
 
     # ---- the other BASELINE configurations, each with its own timed region ---------------------------------------

@@ -166,6 +166,16 @@ _SIGNATURES = {
                                              ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "zc_lut_qwav_host_multi": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "zc_quadtbl_sin_host_multi": (ctypes.c_int, [ctypes.POINTER(QuadTblParams), ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "zc_nco_mix_host_multi": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                             ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t,
+                                             ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "zc_topolar_i16_host_multi": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "zc_rotate_const_o16_host_multi": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32,
+                                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                      ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
     "zc_host_free": (None, [ctypes.c_void_p]),
     "zc_rotate_const_host": (ctypes.c_int, [ctypes.POINTER(Params), ctypes.c_int32, ctypes.c_int32,
                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
@@ -476,6 +486,20 @@ class Cordic:
                                                 _host_ptr(out, 2 * n), n, arr, nd))
         return out
 
+    def rotate_const_o16_host_multi(self, x0, y0, phase, out, devices):
+        n = phase.size if isinstance(phase, np.ndarray) else phase.numel()
+        arr, nd = _devices(devices)
+        _check(lib().zc_rotate_const_o16_host_multi(ctypes.byref(self.params), int(x0), int(y0), _host_ptr(phase),
+                                                    _host_ptr(out, 2 * n, 2), n, arr, nd))
+        return out
+
+    def mix_host_multi(self, xy, phase0, step, out, devices, n0=0):
+        n = (xy.size if isinstance(xy, np.ndarray) else xy.numel()) // 2
+        arr, nd = _devices(devices)
+        _check(lib().zc_nco_mix_host_multi(ctypes.byref(self.params), _host_ptr(xy, 2 * n), int(phase0) & 0xFFFFFFFF,
+                                           int(step) & 0xFFFFFFFF, int(n0), _host_ptr(out, 2 * n), n, arr, nd))
+        return out
+
     def rotate_host_multi(self, xy, phase, out, devices):
         n = phase.size if isinstance(phase, np.ndarray) else phase.numel()
         arr, nd = _devices(devices)
@@ -541,6 +565,13 @@ class Topolar:
         n = (xy16.size if isinstance(xy16, np.ndarray) else xy16.numel()) // 2
         _check(lib().zc_topolar_i16_host(ctypes.byref(self.params), _host_ptr(xy16, 2 * n, 2), _host_ptr(mag, n),
                                          _host_ptr(phase, n), n, device))
+        return mag, phase
+
+    def topolar_i16_host_multi(self, xy16, mag, phase, devices):
+        n = (xy16.size if isinstance(xy16, np.ndarray) else xy16.numel()) // 2
+        arr, nd = _devices(devices)
+        _check(lib().zc_topolar_i16_host_multi(ctypes.byref(self.params), _host_ptr(xy16, 2 * n, 2), _host_ptr(mag, n),
+                                               _host_ptr(phase, n), n, arr, nd))
         return mag, phase
 
     def topolar_host_multi(self, xy, mag, phase, devices):
@@ -638,4 +669,10 @@ class QuadTbl:
     def lookup_host(self, phase32, out, device=0):
         n = phase32.size if isinstance(phase32, np.ndarray) else phase32.numel()
         _check(lib().zc_quadtbl_sin_host(ctypes.byref(self.params), _host_ptr(phase32), _host_ptr(out, n), n, device))
+        return out
+
+    def lookup_host_multi(self, phase32, out, devices):
+        n = phase32.size if isinstance(phase32, np.ndarray) else phase32.numel()
+        arr, nd = _devices(devices)
+        _check(lib().zc_quadtbl_sin_host_multi(ctypes.byref(self.params), _host_ptr(phase32), _host_ptr(out, n), n, arr, nd))
         return out

@@ -213,4 +213,35 @@ int zc_lut_qwav_host_multi(int pw, int ow, const uint32_t *tbl_host, const uint3
 	});
 }
 
+int zc_quadtbl_sin_host_multi(const zc_quadtbl *q, const uint32_t *phase32, int32_t *out, size_t n, const int *devices, int ndev) {
+	if (n && (!phase32 || !out)) return set_error(ZC_EINVAL, "NULL buffer");
+	return run_sharded(n, devices, ndev, [&](int dev, size_t first, size_t count) {
+		return zc_quadtbl_sin_host(q, phase32 + first, out + first, count, dev);
+	});
+}
+
+int zc_nco_mix_host_multi(const zc_params *p, const int32_t *xy_in, uint32_t phase0, uint32_t step, uint64_t n0,
+		int32_t *xy_out, size_t n, const int *devices, int ndev) {
+	if (n && (!xy_in || !xy_out)) return set_error(ZC_EINVAL, "NULL buffer");
+	return run_sharded(n, devices, ndev, [&](int dev, size_t first, size_t count) {
+		return zc_nco_mix_host(p, xy_in + 2 * first, phase0, step, n0 + first, xy_out + 2 * first, count, dev);
+	});
+}
+
+int zc_topolar_i16_host_multi(const zc_params *p, const int16_t *xy16_in, int32_t *mag, uint32_t *phase, size_t n,
+		const int *devices, int ndev) {
+	if (n && (!xy16_in || !mag || !phase)) return set_error(ZC_EINVAL, "NULL buffer");
+	return run_sharded(n, devices, ndev, [&](int dev, size_t first, size_t count) {
+		return zc_topolar_i16_host(p, xy16_in + 2 * first, mag + first, phase + first, count, dev);
+	});
+}
+
+int zc_rotate_const_o16_host_multi(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int16_t *xy16, size_t n,
+		const int *devices, int ndev) {
+	if (n && (!phase || !xy16)) return set_error(ZC_EINVAL, "NULL buffer");
+	return run_sharded(n, devices, ndev, [&](int dev, size_t first, size_t count) {
+		return zc_rotate_const_o16_host(p, x0, y0, phase + first, xy16 + 2 * first, count, dev);
+	});
+}
+
 } // extern "C"

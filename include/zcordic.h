@@ -278,6 +278,14 @@ int zc_lut_sin_host_multi(int pw, int ow, const uint32_t *tbl_host, const uint32
 		const int *devices, int ndev);
 int zc_lut_qwav_host_multi(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int32_t *out, size_t n,
 		const int *devices, int ndev);
+int zc_quadtbl_sin_host_multi(const zc_quadtbl *q, const uint32_t *phase32, int32_t *out, size_t n, const int *devices,
+		int ndev);
+int zc_nco_mix_host_multi(const zc_params *p, const int32_t *xy_in, uint32_t phase0, uint32_t step, uint64_t n0,
+		int32_t *xy_out, size_t n, const int *devices, int ndev);
+int zc_topolar_i16_host_multi(const zc_params *p, const int16_t *xy16_in, int32_t *mag, uint32_t *phase, size_t n,
+		const int *devices, int ndev);
+int zc_rotate_const_o16_host_multi(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int16_t *xy16, size_t n,
+		const int *devices, int ndev);
 
 /* $readmemh files in the layout hextable() writes (sw/hexfile.cpp:78-89): exchange LUTs with FPGA flows.
  * zc_hex_read returns the number of words read (>= 0) or a negative zc_status. */

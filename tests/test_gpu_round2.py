@@ -184,6 +184,46 @@ def test_rotate_const_o16_refuses_wide_outputs():
     assert e.value.code == -2
 
 
+# ---- full size ---------------------------------------------------------------------------------------------------------
+def test_full_size_scattered_phases_and_nco_properties():
+    """BASELINE sizes (2^30 samples) through the round-2 paths, checked by size-independent properties: scattered phases
+    through the byte table with merged records -- a random permutation-free check: the stream is 64 copies of one 2^24-phase
+    scramble, every copy must equal the first, and the first equals the oracle -- and the NCO (the cfg4 step through the
+    byte table, a near-period step through the comb mapping): both halves of the stream computed as separate shards with
+    n0 offsets equal the whole, the first 2^20 samples equal the oracle, and every sample equals the plain kernel (all 20
+    stages in registers) fed with the accumulator's phases written out explicitly."""
+    core, op = both_p2r(**P2R_CONFIGS["cfg1"])
+    n, period = 1 << 30, 1 << 24
+    base = (torch.arange(period, dtype=torch.int64, device="cuda") * 0x9E3779B1).bitwise_and_(period - 1).to(torch.int32)
+    phase = base.repeat(n // period)
+    out = core.rotate_const(131071, 0, phase)
+    del phase
+    first = out[:period]
+    assert np.array_equal(host(first[:1 << 20]), zo.rotate_const(op, 131071, 0, host(base[:1 << 20]).view(np.uint32)))
+    v = out.view(n // period, period, 2)
+    for k in range(1, n // period):
+        assert torch.equal(v[k], first), k
+    # 0x9E3779B1 is odd: the scramble is a permutation of the 2^24 phases
+    assert int(first[:, 0].sum(dtype=torch.int64)) == -39316 and int(first[:, 1].sum(dtype=torch.int64)) == -39316
+    del out, v, first, base
+    torch.cuda.empty_cache()
+    for step in (0x01234567, 0x80000001):
+        whole = core.nco(131071, 0, 0, step, n)
+        assert np.array_equal(host(whole[:1 << 20]), zo.nco(op, 131071, 0, 0, step, 1 << 20))
+        half = core.nco(131071, 0, 0, step, n // 2, n0=n // 2)
+        assert torch.equal(half, whole[n // 2:]), hex(step)
+        del half
+        piece = 1 << 26
+        for s0 in range(0, n, piece):
+            idx = torch.arange(s0, s0 + piece, dtype=torch.int64, device="cuda")
+            ph = ((idx * step) & 0xFFFFFFFF) >> 8                 # the truncation of bench/cpp/cordic_tb.cpp:128-138
+            ref = core.rotate_const(131071, 0, ph.to(torch.int32), flags=zc.F_NO_SEED)
+            assert torch.equal(ref, whole[s0:s0 + piece]), (hex(step), s0)
+            del idx, ph, ref
+        del whole
+        torch.cuda.empty_cache()
+
+
 # ---- several devices ------------------------------------------------------------------------------------------------
 def all_devices():
     return list(range(zc.lib().zc_device_count()))
@@ -223,6 +263,21 @@ def test_host_multi_entry_points():
     o4 = np.empty(m, dtype=np.int32)
     lut.lookup_host_multi(words, o4, devices)
     assert np.array_equal(o4, zo.lut_qwav(18, 24, zo.quarterwav(18, 24), words))
+    q = zc.QuadTbl(ow=13, phase_bits=18)
+    rc, oq = zo.derive_qtbl(0, 13, 2, 18)
+    q.lookup_host_multi(words, o4, devices)
+    assert np.array_equal(o4, zo.quadtbl(oq, words >> 14))
+    core.mix_host_multi(xy, 7, 0x01234567, out, devices, n0=3)
+    mph = (((7 + (3 + np.arange(m, dtype=np.uint64)) * 0x01234567) & 0xFFFFFFFF) >> 8).astype(np.uint32)
+    assert np.array_equal(out, zo.rotate(op, xy, mph))
+    iq = xy.astype(np.int16)
+    vcore.topolar_i16_host_multi(iq, mag, ph, devices)
+    assert np.array_equal(mag, wm) and np.array_equal(ph, wp)
+    c0, o0 = both_p2r(**P2R_CONFIGS["cfg0"])
+    ph0 = (hin.array[:m] & 0xFFFF).astype(np.uint32)
+    o16 = np.empty((m, 2), dtype=np.int16)
+    c0.rotate_const_o16_host_multi(32767, 0, ph0, o16, devices)
+    assert np.array_equal(o16, zo.rotate_const(o0, 32767, 0, ph0).astype(np.int16))
     hin.free(); hout.free()
     with pytest.raises(zc.ZcError):
         core.rotate_const_host_multi(131071, 0, words, out, [0, 0])          # a device listed twice

@@ -19,11 +19,19 @@
 //                         so that (T1[bucket] + 16*u) >> (lgW+4) is the interval of reduced phase u
 //   TS[R]         i32   interval -> 16*(partial angle sum + 2^(PW-3) + rmin), so that 16*u - TS = byte offset of the TD row
 //   T2[R][4]      int2  (interval, q) -> (x, y) after M stages
-//   TD[NSP/4][nres] int4 residual -> d_M .. d_{M+NS-1} as +1/-1 words, in planes of four stages so that
-//                         consecutive residuals (a phase sweep) read consecutive 16-byte slots: no bank conflicts
-// Sample-to-lane mapping: a warp owns 128 consecutive samples per iteration and lane l takes samples
+//   TD[NSP/4][nres] int4 residual -> d_M .. d_{M+NS-1} as +1/-1 words (or IDP.2A multiplier words {0, d, 0, -d}), in planes
+//                         of four stages so that consecutive residuals (a phase sweep) read consecutive 16-byte slots: no
+//                         bank conflicts.  Byte flavours: one signed byte per stage, 8- or 16-byte rows.
+//   Merged byte flavour (FL_PACKED_M): the T2 words are (x << (32-WW) | low byte of TS), (y << (32-WW) | high byte of TS) with
+//                         TS taken modulo 2^16, and the TS table is not read: three dependent lookups instead of four.
+//   Per-sample-vector flavours (FL_DIRS*): T2 holds one 16-byte row per interval instead -- 12 prefix directions as signed
+//                         bytes and TS in the last word.
+// Sample-to-lane mapping (MAP_BLOCK): a warp owns 128 consecutive samples per iteration and lane l takes samples
 // l, l+32, l+64, l+96 of them, so that for a phase sweep neighbouring lanes read neighbouring table rows
-// (or the same row: a broadcast) and every global access is a fully coalesced 128/256-byte row.
+// (or the same row: a broadcast) and every global access is a fully coalesced 128/256-byte row.  MAP_COMB (NCO with a
+// near-period K): see k_rotate_seeded.
+// What bounds these kernels is the LSU data pipe: wavefronts of 128 bytes of distinct data per access, identical
+// addresses served once, 128-bit accesses split by quarter-warp ("The LSU budget").
 #ifndef ZC_SEEDED_CUH
 #define ZC_SEEDED_CUH
 

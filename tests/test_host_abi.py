@@ -144,13 +144,42 @@ def test_library_exports_every_declared_symbol():
     assert names == zc.EXPORTED_SYMBOLS
 
 
+def test_exchange_library_exports_every_declared_symbol():
+    """include/zcordic_nccl.h -> cordic_b200/libzcordic_nccl.so (the only part that links NCCL): loads without a GPU,
+    exports exactly what the header declares, refuses bad arguments, and has no CPU path either."""
+    import torch          # first: torch must bind its own bundled libnccl.so.2 (2.28) before the system one (2.27) gets loaded
+    src = open(os.path.join(ROOT, "include", "zcordic_nccl.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(zc_[a-z0-9_]+)\s*\(", src)))
+    assert names == ["zc_exchange_create", "zc_exchange_destroy", "zc_scatter_rotate_gather"]
+    path = os.path.join(ROOT, "cordic_b200", "libzcordic_nccl.so")
+    if not os.path.exists(path):
+        import subprocess
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "cordic_b200", "vshim"), path])
+    ctypes.CDLL(zc.LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    L = ctypes.CDLL(path)
+    for n in names:
+        assert hasattr(L, n), "libzcordic_nccl.so does not export %s" % n
+    L.zc_exchange_create.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
+                                     ctypes.POINTER(ctypes.c_void_p)]
+    h = ctypes.c_void_p()
+    devs = (ctypes.c_int * 1)(0)
+    assert L.zc_exchange_create(None, 1, 0, 1024, ctypes.byref(h)) == -1            # ZC_EINVAL
+    assert L.zc_exchange_create(devs, 1, 7, 1024, ctypes.byref(h)) == -1            # unknown transport
+    if not torch.cuda.is_available():
+        assert L.zc_exchange_create(devs, 1, 0, 1024, ctypes.byref(h)) < 0          # no device: no fallback
+    L.zc_scatter_rotate_gather.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    assert L.zc_scatter_rotate_gather(None, None, 0, 0, None, None, 0, 1) == -1
+
+
 def test_header_is_plain_c():
     """The ABI header must compile as C (no torch / C++ types)."""
     import subprocess
     import tempfile
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "t.c")
-        open(c, "w").write('#include "zcordic.h"\nint main(void){zc_params p; (void)p; return sizeof(zc_params)==%d?0:1;}\n'
+        open(c, "w").write('#include "zcordic.h"\n#include "zcordic_nccl.h"\nint main(void){zc_params p; (void)p; return sizeof(zc_params)==%d?0:1;}\n'
                            % ctypes.sizeof(zc.Params))
         subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), c,
                                "-o", os.path.join(td, "t")])

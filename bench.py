@@ -42,6 +42,7 @@ WORKLOADS = {
     "rotate_o16_cfg0": ("rotate_const_o16", 1 << 30, 8, {}),  # packed outputs for an OW<=16 core: 4 B in + 2 x int16 out
     "sintable_p17": ("lut_sin", 1 << 30, 8, {"pw": 17, "ow": 13}),     # configs[3], the shipped table
     "sintable_p23": ("lut_sin", 1 << 30, 8, {"pw": 23, "ow": 16}),     # configs[3], the largest sintable (sw/sintable.cpp:62)
+    "sintable_o16_p17": ("lut_sin_o16", 1 << 30, 6, {"pw": 17, "ow": 13}),   # packed outputs: 4 B phase in + int16 out
     "quarterwav_p18": ("lut_qwav", 1 << 30, 8, {"pw": 18, "ow": 24}),  # configs[3], the shipped table
     "quarterwav_p25": ("lut_qwav", 1 << 30, 8, {"pw": 25, "ow": 16}),  # configs[3], the largest quarterwav (sw/sintable.cpp:190)
     "nco_cfg1": ("nco", 1 << 30, 8, {}),                   # configs[4]  8 B out, no input stream
@@ -57,6 +58,7 @@ CONFIG_PASSES = [
     ("rotate_cfg1", "random"), ("rotate_xy_cfg1", "sweep"), ("rotate_xy_cfg1", "random"),
     ("topolar_cfg2", "random"), ("topolar_i16_cfg2", "random"), ("rotate_o16_cfg0", "sweep"),
     ("sintable_p17", "sweep"), ("sintable_p17", "random"), ("sintable_p23", "sweep"), ("sintable_p23", "random"),
+    ("sintable_o16_p17", "sweep"), ("sintable_o16_p17", "random"),
     ("quarterwav_p18", "sweep"), ("quarterwav_p18", "random"), ("quarterwav_p25", "sweep"), ("quarterwav_p25", "random"),
     ("nco_cfg1", "nco"),
 ]
@@ -144,6 +146,8 @@ def core_name(kind, opts):
         return "r2p IW16 OW16 WW24 PW24 NSTAGES21, inputs packed as int16 x 2"
     if kind in ("lut_sin", "lut_qwav"):
         return "%s PW%d OW%d" % ("sintable" if kind == "lut_sin" else "quarterwav", opts["pw"], opts["ow"])
+    if kind == "lut_sin_o16":
+        return "sintable PW%d OW%d, outputs packed as int16" % (opts["pw"], opts["ow"])
     return "quadtbl PW18 OW13"
 
 
@@ -191,11 +195,12 @@ def cpu_run(kind, n, threads, opts=None):
         t0 = time.perf_counter()
         zo.quadtbl(q, phase)
     else:
-        pw, ow = opts.get("pw", 17 if kind == "lut_sin" else 18), opts.get("ow", 13 if kind == "lut_sin" else 24)
-        tbl = zo.sintable(pw, ow) if kind == "lut_sin" else zo.quarterwav(pw, ow)
+        sin = kind in ("lut_sin", "lut_sin_o16")
+        pw, ow = opts.get("pw", 17 if sin else 18), opts.get("ow", 13 if sin else 24)
+        tbl = zo.sintable(pw, ow) if sin else zo.quarterwav(pw, ow)
         phase = (np.arange(n, dtype=np.uint64) * 4).astype(np.uint32)
         t0 = time.perf_counter()
-        (zo.lut_sin if kind == "lut_sin" else zo.lut_qwav)(pw, ow, tbl, phase)
+        (zo.lut_sin if sin else zo.lut_qwav)(pw, ow, tbl, phase)
     return time.perf_counter() - t0
 
 
@@ -305,18 +310,20 @@ class Bench:
             w["xy"] = torch.randint(-lim, lim, (nper, 2), dtype=torch.int32, device=devname, generator=g)
         if kind == "topolar_i16":
             w["iq"] = torch.randint(-(1 << 15), 1 << 15, (nper, 2), dtype=torch.int16, device=devname, generator=g)
-        if kind in ("lut_sin", "lut_qwav", "lut_quad"):
+        if kind in ("lut_sin", "lut_qwav", "lut_quad", "lut_sin_o16"):
             if phase_mode == "sweep":
                 phase = ((torch.arange(nper, dtype=torch.int64, device=devname) + first) * 4).bitwise_and_(0xFFFFFFFF).to(torch.int32)
             else:
                 phase = torch.randint(-(1 << 31), 1 << 31, (nper,), dtype=torch.int64, device=devname, generator=g).to(torch.int32)
             w["phase"] = phase
-            w["lut"] = (zc.SinTable(phase_bits=opts["pw"], ow=opts["ow"]) if kind == "lut_sin" else
+            w["lut"] = (zc.SinTable(phase_bits=opts["pw"], ow=opts["ow"]) if kind in ("lut_sin", "lut_sin_o16") else
                         zc.QuarterWav(phase_bits=opts["pw"], ow=opts["ow"]) if kind == "lut_qwav" else zc.QuadTbl(ow=13, phase_bits=18))
         if kind in ("topolar", "topolar_i16"):
             w["core"] = zc.Topolar(iw=16, ow=16, xtra=2)
             w["o_mag"] = torch.empty(nper, dtype=torch.int32, device=devname)
             w["o_ph"] = torch.empty(nper, dtype=torch.int32, device=devname)
+        elif kind == "lut_sin_o16":
+            w["o_val16"] = torch.empty(nper, dtype=torch.int16, device=devname)
         elif kind in ("lut_sin", "lut_qwav", "lut_quad"):
             w["o_val"] = torch.empty(nper, dtype=torch.int32, device=devname)
         elif kind == "rotate_const_o16":
@@ -339,6 +346,8 @@ class Bench:
                 w["core"].topolar(w["xy"], mag=w["o_mag"], phase=w["o_ph"], flags=zc.F_NO_TAIL if no_tail else zc.F_DEFAULT)
             elif kind == "topolar_i16":
                 w["core"].topolar_i16(w["iq"], mag=w["o_mag"], phase=w["o_ph"])
+            elif kind == "lut_sin_o16":
+                w["lut"].lookup_o16(w["phase"], out=w["o_val16"])
             else:
                 w["lut"].lookup(w["phase"], out=w["o_val"])
         w["step"] = step
@@ -369,6 +378,8 @@ class Bench:
         if kind == "rotate_const_o16":
             ref = w["core"].rotate_const(32767, 0, w["phase"][:m])
             return bool(torch.equal(ref.to(torch.int16), w["o_xy16"][:m]))
+        if kind == "lut_sin_o16":                      # packed outputs vs the 32-bit entry point
+            return bool(torch.equal(w["lut"].lookup(w["phase"][:m]).to(torch.int16), w["o_val16"][:m]))
         if kind in ("lut_sin", "lut_qwav"):            # the lookup rule of rtl/sintable.v / rtl/quarterwav.v in torch
             pw, ow = w["opts"]["pw"], w["opts"]["ow"]
             tbl = torch.from_numpy(w["lut"].table.astype(np.int64)).to(self.dev)

@@ -127,6 +127,14 @@ _SIGNATURES = {
                                   ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
     "zc_lut_qwav": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                    ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "zc_lut_sin_o16": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "zc_lut_qwav_o16": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "zc_lut_sin_o16_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
+    "zc_lut_qwav_o16_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
     "zc_derive_qtbl": (ctypes.c_int, [ctypes.c_int] * 4 + [ctypes.POINTER(QuadTblParams)]),
     "zc_quadtbl_sin": (ctypes.c_int, [ctypes.POINTER(QuadTblParams), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                       ctypes.c_int, ctypes.c_void_p]),
@@ -617,10 +625,28 @@ class _Lut:
                   _dev_ptr(out, n), n, dev, _stream_ptr(dev, stream)))
         return out
 
+    def lookup_o16(self, phase32, out=None, stream=None):
+        """As lookup for a table with OW <= 16, outputs as an int16 CUDA tensor (zc_lut_sin_o16 / zc_lut_qwav_o16)."""
+        torch = _torch()
+        n = phase32.numel()
+        dev = phase32.device.index or 0
+        if out is None:
+            out = torch.empty(n, dtype=torch.int16, device=phase32.device)
+        fn = lib().zc_lut_qwav_o16 if self.QUARTER else lib().zc_lut_sin_o16
+        _check(fn(self.PW, self.OW, _dev_ptr(self._table_on(phase32.device)), _dev_ptr(phase32),
+                  _dev_ptr(out, n, 2), n, dev, _stream_ptr(dev, stream)))
+        return out
+
     def lookup_host(self, phase32, out, device=0):
         n = phase32.size if isinstance(phase32, np.ndarray) else phase32.numel()
         fn = lib().zc_lut_qwav_host if self.QUARTER else lib().zc_lut_sin_host
         _check(fn(self.PW, self.OW, self.table.ctypes.data, _host_ptr(phase32), _host_ptr(out, n), n, device))
+        return out
+
+    def lookup_o16_host(self, phase32, out, device=0):
+        n = phase32.size if isinstance(phase32, np.ndarray) else phase32.numel()
+        fn = lib().zc_lut_qwav_o16_host if self.QUARTER else lib().zc_lut_sin_o16_host
+        _check(fn(self.PW, self.OW, self.table.ctypes.data, _host_ptr(phase32), _host_ptr(out, n, 2), n, device))
         return out
 
 

@@ -312,11 +312,13 @@ static int launch_topolar(const zc_params *p, const int32_t *xy_in, int32_t *mag
 	return ZC_OK;
 }
 
+// out16: `out` receives int16 words (tables with OW <= 16)
 template <bool QUARTER>
-static int launch_lut(int pw, int ow, const uint32_t *tbl, const uint32_t *phase32, int32_t *out,
-		size_t n, int device, void *stream) {
+static int launch_lut(int pw, int ow, const uint32_t *tbl, const uint32_t *phase32, void *out,
+		size_t n, int device, void *stream, bool out16 = false) {
 	int rc = check_lut(QUARTER, pw, ow);
 	if (rc != ZC_OK) return rc;
+	if (out16 && ow > 16) return set_error(ZC_ERANGE, "packed int16 outputs need OW <= 16 (OW=%d)", ow);
 	if (!tbl || (n && (!phase32 || !out))) return set_error(ZC_EINVAL, "NULL buffer");
 	DeviceInfo di;
 	if ((rc = device_info(device, di)) != ZC_OK) return rc;
@@ -328,7 +330,7 @@ static int launch_lut(int pw, int ow, const uint32_t *tbl, const uint32_t *phase
 	c.pshift = 32 - pw; c.osh = 32 - ow; c.pw = pw;
 	c.lowmask = QUARTER ? ((1u << (pw - 2)) - 1u) : 0u;
 	size_t done = 0;
-	if (aligned16(phase32) && aligned16(out) && n >= 4) {
+	if (aligned16(phase32) && (out16 ? aligned8(out) : aligned16(out)) && n >= 4) {
 		const size_t groups = n / 4;
 		// Large batches of a table that fits shared memory once compressed (int16 half-wave / u16[+u8] magnitudes) go
 		// through the kernel that keeps it there: indifferent to the phase pattern.  ZCORDIC_LUT_SMEM=0 keeps the L2 path.
@@ -342,22 +344,25 @@ static int launch_lut(int pw, int ow, const uint32_t *tbl, const uint32_t *phase
 		// both kernels evaluate the same probe of the same phases (zc_kernels.cuh: probe_local) and exactly one proceeds
 		const int probe_lim = (smem_mode == 1 && fits) ? (int)(1u << (pw < 2 ? 30 : (32 - pw > 30 ? 30 : 32 - pw))) : -1;
 		if (smem_mode != 2 || !fits) {
-			k_lut<QUARTER><<<grid_for(groups, di, 32), 256, 0, st>>>((const int4 *)phase32, (int4 *)out, tbl, groups, c, probe_lim);
+			if (out16) k_lut<QUARTER, true><<<grid_for(groups, di, 32), 256, 0, st>>>((const int4 *)phase32, out, tbl, groups, c, probe_lim);
+			else k_lut<QUARTER, false><<<grid_for(groups, di, 32), 256, 0, st>>>((const int4 *)phase32, out, tbl, groups, c, probe_lim);
 			if ((rc = post_launch("k_lut")) != ZC_OK) return rc;
 		}
 		if (smem_mode != 0 && fits) {
-			typedef void (*kern_t)(const int4 *, int4 *, const uint32_t *, size_t, const LutConsts, int);
-			kern_t kern = hi8 ? (kern_t)k_lut_smem<QUARTER, true> : (kern_t)k_lut_smem<QUARTER, false>;
+			typedef void (*kern_t)(const int4 *, void *, const uint32_t *, size_t, const LutConsts, int);
+			kern_t kern = out16 ? (hi8 ? (kern_t)k_lut_smem<QUARTER, true, true> : (kern_t)k_lut_smem<QUARTER, false, true>)
+					    : (hi8 ? (kern_t)k_lut_smem<QUARTER, true, false> : (kern_t)k_lut_smem<QUARTER, false, false>);
 			cudaError_t e = ensure_dynamic_smem((const void *)kern, smem);
 			if (e != cudaSuccess) return set_error(ZC_ECUDA, "k_lut_smem shared memory: %s", cudaGetErrorString(e));
-			kern<<<di.sms, 1024, smem, st>>>((const int4 *)phase32, (int4 *)out, tbl, groups, c, probe_lim);
+			kern<<<di.sms, 1024, smem, st>>>((const int4 *)phase32, out, tbl, groups, c, probe_lim);
 			if ((rc = post_launch("k_lut_smem")) != ZC_OK) return rc;
 		}
 		done = groups * 4;
 	}
 	if (done < n) {
 		const size_t rest = n - done;
-		k_lut_scalar<QUARTER><<<grid_for(rest, di, 32), 256, 0, st>>>(phase32 + done, out + done, tbl, rest, c);
+		void *tail = out16 ? (void *)((int16_t *)out + done) : (void *)((int32_t *)out + done);
+		k_lut_scalar<QUARTER><<<grid_for(rest, di, 32), 256, 0, st>>>(phase32 + done, tail, tbl, rest, c, out16 ? 1 : 0);
 		if ((rc = post_launch("k_lut_scalar")) != ZC_OK) return rc;
 	}
 	return ZC_OK;
@@ -859,6 +864,15 @@ int zc_lut_qwav(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32
 	return launch_lut<true>(pw, ow, tbl_dev, phase32, out, n, device, stream);
 }
 
+int zc_lut_sin_o16(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int16_t *out, size_t n,
+		int device, void *stream) {
+	return launch_lut<false>(pw, ow, tbl_dev, phase32, out, n, device, stream, true);
+}
+int zc_lut_qwav_o16(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int16_t *out, size_t n,
+		int device, void *stream) {
+	return launch_lut<true>(pw, ow, tbl_dev, phase32, out, n, device, stream, true);
+}
+
 int zc_quadtbl_sin(const zc_quadtbl *q, const uint32_t *phase32, int32_t *out, size_t n, int device, void *stream) {
 	return launch_quadtbl(q, phase32, out, n, device, stream);
 }
@@ -945,9 +959,10 @@ int zc_nco_rotate_host(const zc_params *p, int32_t x0, int32_t y0, uint32_t phas
 }
 
 static int lut_host(bool quarter, int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32,
-		int32_t *out, size_t n, int device) {
+		void *out, size_t n, int device, bool out16 = false) {
 	int rc = check_lut(quarter, pw, ow);
 	if (rc != ZC_OK) return rc;
+	if (out16 && ow > 16) return set_error(ZC_ERANGE, "packed int16 outputs need OW <= 16 (OW=%d)", ow);
 	if (!tbl_host || (n && (!phase32 || !out))) return set_error(ZC_EINVAL, "NULL buffer");
 	DeviceInfo di;
 	if ((rc = device_info(device, di)) != ZC_OK) return rc;
@@ -965,9 +980,12 @@ static int lut_host(bool quarter, int pw, int ow, const uint32_t *tbl_host, cons
 		}
 	}
 	const Lane in[2] = {{4, (const char *)phase32, nullptr}, {0, nullptr, nullptr}};
-	const Lane outl[2] = {{4, nullptr, (char *)out}, {0, nullptr, nullptr}};
+	const Lane outl[2] = {{(size_t)(out16 ? 2 : 4), nullptr, (char *)out}, {0, nullptr, nullptr}};
 	rc = host_pipeline(device, n, in, outl,
 		[&](size_t, size_t cnt, char *i0, char *, char *o0, char *, cudaStream_t st) {
+			if (out16)
+				return quarter ? zc_lut_qwav_o16(pw, ow, tbl_dev, (const uint32_t *)i0, (int16_t *)o0, cnt, device, st)
+					       : zc_lut_sin_o16(pw, ow, tbl_dev, (const uint32_t *)i0, (int16_t *)o0, cnt, device, st);
 			return quarter ? zc_lut_qwav(pw, ow, tbl_dev, (const uint32_t *)i0, (int32_t *)o0, cnt, device, st)
 				       : zc_lut_sin(pw, ow, tbl_dev, (const uint32_t *)i0, (int32_t *)o0, cnt, device, st);
 		});
@@ -1042,6 +1060,14 @@ int zc_lut_sin_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *ph
 int zc_lut_qwav_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int32_t *out,
 		size_t n, int device) {
 	return lut_host(true, pw, ow, tbl_host, phase32, out, n, device);
+}
+int zc_lut_sin_o16_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int16_t *out,
+		size_t n, int device) {
+	return lut_host(false, pw, ow, tbl_host, phase32, out, n, device, true);
+}
+int zc_lut_qwav_o16_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int16_t *out,
+		size_t n, int device) {
+	return lut_host(true, pw, ow, tbl_host, phase32, out, n, device, true);
 }
 
 } // extern "C"

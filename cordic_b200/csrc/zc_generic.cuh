@@ -118,9 +118,15 @@ __device__ __forceinline__ int lut_one(uint32_t phase32, const uint32_t *__restr
 	}
 }
 
-template <bool QUARTER>
+// OUT16 (all three LUT kernels): o_val packed as int16, four samples per 8-byte store (tables with OW <= 16)
+__device__ __forceinline__ void lut_store4(void *out, size_t g, const int4 o, bool out16) {
+	if (out16) stg_stream64(reinterpret_cast<int2 *>(out) + g, make_int2(pack16(o.x, o.y), pack16(o.z, o.w)));
+	else stg_stream(reinterpret_cast<int4 *>(out) + g, o);
+}
+
+template <bool QUARTER, bool OUT16 = false>
 __global__ void __launch_bounds__(256)
-k_lut(const int4 *__restrict__ phase4, int4 *__restrict__ out4, const uint32_t *__restrict__ tbl,
+k_lut(const int4 *__restrict__ phase4, void *__restrict__ out4, const uint32_t *__restrict__ tbl,
 		size_t ngroups, const __grid_constant__ LutConsts c, const int probe_lim) {
 	// the probe (same verdict in every CTA of both kernels) chose the shared-memory kernel for this batch
 	if (probe_lim >= 0 && probe_local(reinterpret_cast<const uint32_t *>(phase4), ngroups << 2, 0, probe_lim) != LUT_GATE_L2) return;
@@ -132,7 +138,7 @@ k_lut(const int4 *__restrict__ phase4, int4 *__restrict__ out4, const uint32_t *
 		o.y = lut_one<QUARTER>((uint32_t)pv.y, tbl, c);
 		o.z = lut_one<QUARTER>((uint32_t)pv.z, tbl, c);
 		o.w = lut_one<QUARTER>((uint32_t)pv.w, tbl, c);
-		stg_stream(out4 + g, o);
+		lut_store4(out4, g, o, OUT16);
 	}
 }
 
@@ -146,9 +152,9 @@ k_lut(const int4 *__restrict__ phase4, int4 *__restrict__ out4, const uint32_t *
 //   quarterwav (rtl/quarterwav.v:92-109) the words are magnitudes below 2^16 (u16) or 2^24 (u16 + u8, HI8).
 // The table is the caller's memory and may hold anything: when a check fails the CTA (every CTA reaches the same
 // verdict, they all read the whole table) serves its samples from global memory exactly as k_lut does.
-template <bool QUARTER, bool HI8>
+template <bool QUARTER, bool HI8, bool OUT16 = false>
 __global__ void __launch_bounds__(1024, 1)
-k_lut_smem(const int4 *__restrict__ phase4, int4 *__restrict__ out4, const uint32_t *__restrict__ tbl,
+k_lut_smem(const int4 *__restrict__ phase4, void *__restrict__ out4, const uint32_t *__restrict__ tbl,
 		size_t ngroups, const __grid_constant__ LutConsts c, const int probe_lim) {
 	if (probe_lim >= 0 && probe_local(reinterpret_cast<const uint32_t *>(phase4), ngroups << 2, 0, probe_lim) != LUT_GATE_SMEM) return;
 	extern __shared__ __align__(16) unsigned char lsm[];
@@ -193,12 +199,12 @@ k_lut_smem(const int4 *__restrict__ phase4, int4 *__restrict__ out4, const uint3
 			for (int k = 0; k < LUT_MLP; k++) pv[k] = ldg_stream(phase4 + g + k * stride);
 #pragma unroll
 			for (int k = 0; k < LUT_MLP; k++)
-				stg_stream(out4 + g + k * stride, make_int4(one((uint32_t)pv[k].x), one((uint32_t)pv[k].y),
-					one((uint32_t)pv[k].z), one((uint32_t)pv[k].w)));
+				lut_store4(out4, g + k * stride, make_int4(one((uint32_t)pv[k].x), one((uint32_t)pv[k].y),
+					one((uint32_t)pv[k].z), one((uint32_t)pv[k].w)), OUT16);
 		}
 		for (; g < ngroups; g += stride) {
 			const int4 pv = ldg_stream(phase4 + g);
-			stg_stream(out4 + g, make_int4(one((uint32_t)pv.x), one((uint32_t)pv.y), one((uint32_t)pv.z), one((uint32_t)pv.w)));
+			lut_store4(out4, g, make_int4(one((uint32_t)pv.x), one((uint32_t)pv.y), one((uint32_t)pv.z), one((uint32_t)pv.w)), OUT16);
 		}
 	} else {
 		for (; g < ngroups; g += stride) {
@@ -208,18 +214,21 @@ k_lut_smem(const int4 *__restrict__ phase4, int4 *__restrict__ out4, const uint3
 			o.y = lut_one<QUARTER>((uint32_t)pv.y, tbl, c);
 			o.z = lut_one<QUARTER>((uint32_t)pv.z, tbl, c);
 			o.w = lut_one<QUARTER>((uint32_t)pv.w, tbl, c);
-			stg_stream(out4 + g, o);
+			lut_store4(out4, g, o, OUT16);
 		}
 	}
 }
 
 template <bool QUARTER>
 __global__ void __launch_bounds__(256)
-k_lut_scalar(const uint32_t *__restrict__ phase, int32_t *__restrict__ out,
-		const uint32_t *__restrict__ tbl, size_t n, const __grid_constant__ LutConsts c) {
+k_lut_scalar(const uint32_t *__restrict__ phase, void *__restrict__ out,
+		const uint32_t *__restrict__ tbl, size_t n, const __grid_constant__ LutConsts c, const int out16) {
 	const size_t stride = (size_t)gridDim.x * blockDim.x;
-	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-		out[i] = lut_one<QUARTER>(phase[i], tbl, c);
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const int v = lut_one<QUARTER>(phase[i], tbl, c);
+		if (out16) reinterpret_cast<short *>(out)[i] = (short)v;
+		else reinterpret_cast<int32_t *>(out)[i] = v;
+	}
 }
 
 } // namespace zc

@@ -159,6 +159,9 @@ __device__ __forceinline__ int4 ldg_stream(const int4 *p) {
 		: "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
 	return r;
 }
+__device__ __forceinline__ void stg_stream64(int2 *p, const int2 v) {
+	asm volatile("st.global.L1::no_allocate.v2.s32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
 __device__ __forceinline__ void stg_stream(int4 *p, const int4 v) {
 	asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
 		:: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");

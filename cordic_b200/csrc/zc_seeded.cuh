@@ -127,9 +127,6 @@ __device__ __forceinline__ uint32_t ldg_stream32(const uint32_t *p) {
 	asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
 	return r;
 }
-__device__ __forceinline__ void stg_stream64(int2 *p, const int2 v) {
-	asm volatile("st.global.L1::no_allocate.v2.s32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
-}
 
 // Convergent rounding on the FMA pipe (the ALU pipe is this kernel's bottleneck).  For |v| < 2^22 the word
 // 0x4B400000+v IS the float 1.5*2^23+v; one fused multiply-add forms 1.5*2^23 + v/2^D exactly and rounds it

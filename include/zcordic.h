@@ -214,7 +214,13 @@ int zc_lut_qwav(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32
  *                        mag / phase as in zc_topolar.  12 algorithmic bytes per sample instead of 16.
  *   zc_rotate_const_o16  xy16[2i] = o_xval, xy16[2i+1] = o_yval as int16 (OW <= 16: the sign-extended port value
  *                        fits).  8 algorithmic bytes per sample instead of 12.
- * Buffers must be 4-byte aligned. */
+ *   zc_lut_sin_o16 / zc_lut_qwav_o16   out[i] = o_val as int16 (tables with OW <= 16: rtl/sintable.v:53-58,
+ *                        rtl/quarterwav.v:54-59).  6 algorithmic bytes per sample instead of 8.
+ * Buffers must be 4-byte aligned (2-byte for the LUT outputs). */
+int zc_lut_sin_o16(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int16_t *out, size_t n,
+		int device, void *stream);
+int zc_lut_qwav_o16(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int16_t *out, size_t n,
+		int device, void *stream);
 int zc_topolar_i16(const zc_params *p, const int16_t *xy16_in, int32_t *mag, uint32_t *phase, size_t n,
 		int device, void *stream);
 int zc_rotate_const_o16(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int16_t *xy16,
@@ -250,6 +256,10 @@ int zc_quadtbl_sin_host(const zc_quadtbl *q, const uint32_t *phase32, int32_t *o
 int zc_nco_mix_host(const zc_params *p, const int32_t *xy_in, uint32_t phase0, uint32_t step, uint64_t n0,
 		int32_t *xy_out, size_t n, int device);
 
+int zc_lut_sin_o16_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int16_t *out, size_t n,
+		int device);
+int zc_lut_qwav_o16_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int16_t *out, size_t n,
+		int device);
 int zc_topolar_i16_host(const zc_params *p, const int16_t *xy16_in, int32_t *mag, uint32_t *phase, size_t n,
 		int device);
 int zc_rotate_const_o16_host(const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase, int16_t *xy16,

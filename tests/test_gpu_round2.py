@@ -177,6 +177,37 @@ def test_rotate_const_o16_equals_rotate_const(name):
     assert np.array_equal(out, zo.rotate_const(op, x0, 0, ph).astype(np.int16))
 
 
+@pytest.mark.parametrize("kind,pw,ow", [("tbl", 17, 13), ("tbl", 23, 16), ("tbl", 10, 8), ("qtr", 25, 16), ("qtr", 18, 13), ("qtr", 12, 16)])
+def test_lut_o16_equals_lut(kind, pw, ow):
+    """zc_lut_sin_o16 / zc_lut_qwav_o16: the same o_val words as int16 -- sweeps (L2 kernel), scattered phases (shared-memory
+    kernel where the table fits), ragged sizes and odd alignments (scalar kernel), the host entry point."""
+    lut = (zc.SinTable if kind == "tbl" else zc.QuarterWav)(phase_bits=pw, ow=ow)
+    tbl = (zo.sintable if kind == "tbl" else zo.quarterwav)(pw, ow)
+    ref = zo.lut_sin if kind == "tbl" else zo.lut_qwav
+    rng = np.random.default_rng(SEED + 27)
+    for n, pat in [(7, "rand"), (4099, "rand"), ((1 << 22) + 6, "sweep"), ((1 << 22) + 6, "rand")]:
+        w = ((np.arange(n, dtype=np.uint64) * 1024) & 0xFFFFFFFF).astype(np.uint32) if pat == "sweep" else \
+            rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+        want = ref(pw, ow, tbl, w).astype(np.int16)
+        got = lut.lookup_o16(dev(w))
+        assert got.dtype == torch.int16 and np.array_equal(host(got), want), (kind, pw, ow, n, pat)
+        if n > 100:
+            got = lut.lookup_o16(dev(w)[4:], out=torch.empty(n - 3, dtype=torch.int16, device="cuda")[1:])   # 2-byte aligned only
+            assert np.array_equal(host(got), want[4:])
+    m = (5 << 20) + 3
+    w = rng.integers(0, 1 << 32, size=m, dtype=np.uint64).astype(np.uint32)
+    out = np.empty(m, dtype=np.int16)
+    lut.lookup_o16_host(w, out)
+    assert np.array_equal(out, ref(pw, ow, tbl, w).astype(np.int16))
+
+
+def test_lut_o16_refuses_wide_tables():
+    lut = zc.QuarterWav(phase_bits=18, ow=24)
+    with pytest.raises(zc.ZcError) as e:
+        lut.lookup_o16(torch.zeros(8, dtype=torch.int32, device="cuda"))
+    assert e.value.code == -2
+
+
 def test_rotate_const_o16_refuses_wide_outputs():
     core = zc.Cordic(18, 18, 2, 24, 20)
     with pytest.raises(zc.ZcError) as e:

@@ -46,6 +46,8 @@ WORKLOADS = {
     "quarterwav_p18": ("lut_qwav", 1 << 30, 8, {"pw": 18, "ow": 24}),  # configs[3], the shipped table
     "quarterwav_p25": ("lut_qwav", 1 << 30, 8, {"pw": 25, "ow": 16}),  # configs[3], the largest quarterwav (sw/sintable.cpp:190)
     "nco_cfg1": ("nco", 1 << 30, 8, {}),                   # configs[4]  8 B out, no input stream
+    "nco_sintable_p17": ("nco_lut", 1 << 30, 4, {"pw": 17, "ow": 13, "q": False}),     # the same NCO through rtl/sintable.v: 4 B out
+    "nco_quarterwav_p18": ("nco_lut", 1 << 30, 4, {"pw": 18, "ow": 24, "q": True}),    # ... through rtl/quarterwav.v
     "quadtbl_p18": ("lut_quad", 1 << 30, 8, {}),           # rtl/quadtbl.v, PW18/OW13
 }
 CFG1 = dict(iw=18, ow=18, xtra=2, phase_bits=24, nstages=20)
@@ -60,7 +62,7 @@ CONFIG_PASSES = [
     ("sintable_p17", "sweep"), ("sintable_p17", "random"), ("sintable_p23", "sweep"), ("sintable_p23", "random"),
     ("sintable_o16_p17", "sweep"), ("sintable_o16_p17", "random"),
     ("quarterwav_p18", "sweep"), ("quarterwav_p18", "random"), ("quarterwav_p25", "sweep"), ("quarterwav_p25", "random"),
-    ("nco_cfg1", "nco"),
+    ("nco_cfg1", "nco"), ("nco_sintable_p17", "nco"), ("nco_quarterwav_p18", "nco"),
 ]
 
 
@@ -148,13 +150,15 @@ def core_name(kind, opts):
         return "%s PW%d OW%d" % ("sintable" if kind == "lut_sin" else "quarterwav", opts["pw"], opts["ow"])
     if kind == "lut_sin_o16":
         return "sintable PW%d OW%d, outputs packed as int16" % (opts["pw"], opts["ow"])
+    if kind == "nco_lut":
+        return "%s PW%d OW%d fed by the NCO accumulator" % ("quarterwav" if opts["q"] else "sintable", opts["pw"], opts["ow"])
     return "quadtbl PW18 OW13"
 
 
 def config_for(workload, kind, opts, nper, phase, bytes_per):
     """The workload-defining keys, identical for the `ours` and the `reference` arm."""
     return {"workload": workload, "core": core_name(kind, opts), "samples_per_gpu_per_step": nper,
-            "phase": phase if kind != "nco" else "nco step 0x%08x" % NCO_STEP,
+            "phase": phase if kind not in ("nco", "nco_lut") else "nco step 0x%08x" % NCO_STEP,
             "sharding": "independent shards, no data-path collective",
             "l2": "inputs+outputs per step are %.1f GiB per GPU, far larger than the 126 MB L2" % (bytes_per * nper / 2**30)}
 
@@ -194,6 +198,11 @@ def cpu_run(kind, n, threads, opts=None):
         phase = (np.arange(n, dtype=np.uint32) & 0x3FFFF)
         t0 = time.perf_counter()
         zo.quadtbl(q, phase)
+    elif kind == "nco_lut":
+        tbl = zo.quarterwav(opts["pw"], opts["ow"]) if opts["q"] else zo.sintable(opts["pw"], opts["ow"])
+        phase = ((np.arange(n, dtype=np.uint64) * NCO_STEP) & 0xFFFFFFFF).astype(np.uint32)
+        t0 = time.perf_counter()
+        (zo.lut_qwav if opts["q"] else zo.lut_sin)(opts["pw"], opts["ow"], tbl, phase)
     else:
         sin = kind in ("lut_sin", "lut_sin_o16")
         pw, ow = opts.get("pw", 17 if sin else 18), opts.get("ow", 13 if sin else 24)
@@ -324,6 +333,9 @@ class Bench:
             w["o_ph"] = torch.empty(nper, dtype=torch.int32, device=devname)
         elif kind == "lut_sin_o16":
             w["o_val16"] = torch.empty(nper, dtype=torch.int16, device=devname)
+        elif kind == "nco_lut":
+            w["lut"] = (zc.QuarterWav if opts["q"] else zc.SinTable)(phase_bits=opts["pw"], ow=opts["ow"])
+            w["o_val"] = torch.empty(nper, dtype=torch.int32, device=devname)
         elif kind in ("lut_sin", "lut_qwav", "lut_quad"):
             w["o_val"] = torch.empty(nper, dtype=torch.int32, device=devname)
         elif kind == "rotate_const_o16":
@@ -348,6 +360,8 @@ class Bench:
                 w["core"].topolar_i16(w["iq"], mag=w["o_mag"], phase=w["o_ph"])
             elif kind == "lut_sin_o16":
                 w["lut"].lookup_o16(w["phase"], out=w["o_val16"])
+            elif kind == "nco_lut":
+                w["lut"].nco(0, nco_step, nper, n0=first, out=w["o_val"])
             else:
                 w["lut"].lookup(w["phase"], out=w["o_val"])
         w["step"] = step
@@ -378,6 +392,10 @@ class Bench:
         if kind == "rotate_const_o16":
             ref = w["core"].rotate_const(32767, 0, w["phase"][:m])
             return bool(torch.equal(ref.to(torch.int16), w["o_xy16"][:m]))
+        if kind == "nco_lut":                          # phases generated in registers vs the same phases written out
+            idx = torch.arange(m, dtype=torch.int64, device=self.dev) + w["first"]
+            ph = ((idx * NCO_STEP) & 0xFFFFFFFF).to(torch.int32)
+            return bool(torch.equal(w["lut"].lookup(ph), w["o_val"][:m]))
         if kind == "lut_sin_o16":                      # packed outputs vs the 32-bit entry point
             return bool(torch.equal(w["lut"].lookup(w["phase"][:m]).to(torch.int16), w["o_val16"][:m]))
         if kind in ("lut_sin", "lut_qwav"):            # the lookup rule of rtl/sintable.v / rtl/quarterwav.v in torch
@@ -469,7 +487,7 @@ class Bench:
             ms, ms_max, win, launches = self.timed(w["step"], steps, 0)
             ok = self.spot_check(w, phase_mode)
             e2e = self.packed_e2e(w) if self.world == 1 and not self.args.no_e2e and kind in ("rotate_const_o16", "topolar_i16") else None
-            out = {"workload": workload, "phase": phase_mode if kind != "nco" else "nco step 0x%08x, n0 = rank * samples_per_gpu" % NCO_STEP,
+            out = {"workload": workload, "phase": phase_mode if kind not in ("nco", "nco_lut") else "nco step 0x%08x, n0 = rank * samples_per_gpu" % NCO_STEP,
                    "core": core_name(kind, opts), "samples_per_gpu_per_step": nper, "steps": steps, "warmup": 6,
                    "value": self.world * nper * steps / (ms_max * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_max / steps,
                    "roofline": self.roofline(bytes_per, nper, ms, steps), "launches_per_step": launches / steps,

@@ -127,6 +127,14 @@ _SIGNATURES = {
                                   ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
     "zc_lut_qwav": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                    ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "zc_nco_lut_sin": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                      ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "zc_nco_lut_qwav": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                       ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "zc_nco_lut_sin_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                           ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
+    "zc_nco_lut_qwav_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                            ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
     "zc_lut_sin_o16": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
     "zc_lut_qwav_o16": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -623,6 +631,24 @@ class _Lut:
         fn = lib().zc_lut_qwav if self.QUARTER else lib().zc_lut_sin
         _check(fn(self.PW, self.OW, _dev_ptr(self._table_on(phase32.device)), _dev_ptr(phase32),
                   _dev_ptr(out, n), n, dev, _stream_ptr(dev, stream)))
+        return out
+
+    def nco(self, phase0, step, n, n0=0, out=None, device=None, stream=None):
+        """Streaming NCO through the table: phase32 = phase0 + (n0+i)*step, no input stream (zc_nco_lut_sin / _qwav)."""
+        torch = _torch()
+        if out is None:
+            out = torch.empty(n, dtype=torch.int32, device=device if device is not None else "cuda")
+        dev = out.device.index or 0
+        fn = lib().zc_nco_lut_qwav if self.QUARTER else lib().zc_nco_lut_sin
+        _check(fn(self.PW, self.OW, _dev_ptr(self._table_on(out.device)), int(phase0) & 0xFFFFFFFF, int(step) & 0xFFFFFFFF,
+                  int(n0), _dev_ptr(out, n), n, dev, _stream_ptr(dev, stream)))
+        return out
+
+    def nco_host(self, phase0, step, out, n0=0, device=0):
+        n = out.size if isinstance(out, np.ndarray) else out.numel()
+        fn = lib().zc_nco_lut_qwav_host if self.QUARTER else lib().zc_nco_lut_sin_host
+        _check(fn(self.PW, self.OW, self.table.ctypes.data, int(phase0) & 0xFFFFFFFF, int(step) & 0xFFFFFFFF, int(n0),
+                  _host_ptr(out, n), n, device))
         return out
 
     def lookup_o16(self, phase32, out=None, stream=None):

@@ -312,14 +312,15 @@ static int launch_topolar(const zc_params *p, const int32_t *xy_in, int32_t *mag
 	return ZC_OK;
 }
 
-// out16: `out` receives int16 words (tables with OW <= 16)
+// out16: `out` receives int16 words (tables with OW <= 16).  nco: no phase stream, the 32-bit accumulator
+// nco[0] + (nco[2] + i) * nco[1] is generated in registers (zc_nco_lut_*).
 template <bool QUARTER>
 static int launch_lut(int pw, int ow, const uint32_t *tbl, const uint32_t *phase32, void *out,
-		size_t n, int device, void *stream, bool out16 = false) {
+		size_t n, int device, void *stream, bool out16 = false, const uint32_t *nco = nullptr) {
 	int rc = check_lut(QUARTER, pw, ow);
 	if (rc != ZC_OK) return rc;
 	if (out16 && ow > 16) return set_error(ZC_ERANGE, "packed int16 outputs need OW <= 16 (OW=%d)", ow);
-	if (!tbl || (n && (!phase32 || !out))) return set_error(ZC_EINVAL, "NULL buffer");
+	if (!tbl || (n && ((!nco && !phase32) || !out))) return set_error(ZC_EINVAL, "NULL buffer");
 	DeviceInfo di;
 	if ((rc = device_info(device, di)) != ZC_OK) return rc;
 	if (n == 0) return ZC_OK;
@@ -329,8 +330,10 @@ static int launch_lut(int pw, int ow, const uint32_t *tbl, const uint32_t *phase
 	LutConsts c;
 	c.pshift = 32 - pw; c.osh = 32 - ow; c.pw = pw;
 	c.lowmask = QUARTER ? ((1u << (pw - 2)) - 1u) : 0u;
+	c.nco = nco ? 1 : 0;
+	c.nco_phase0 = nco ? nco[0] : 0u; c.nco_step = nco ? nco[1] : 0u; c.nco_n0 = nco ? nco[2] : 0u;
 	size_t done = 0;
-	if (aligned16(phase32) && (out16 ? aligned8(out) : aligned16(out)) && n >= 4) {
+	if ((nco || aligned16(phase32)) && (out16 ? aligned8(out) : aligned16(out)) && n >= 4) {
 		const size_t groups = n / 4;
 		// Large batches of a table that fits shared memory once compressed (int16 half-wave / u16[+u8] magnitudes) go
 		// through the kernel that keeps it there: indifferent to the phase pattern.  ZCORDIC_LUT_SMEM=0 keeps the L2 path.
@@ -342,13 +345,21 @@ static int launch_lut(int pw, int ow, const uint32_t *tbl, const uint32_t *phase
 		static const int smem_mode = std::getenv("ZCORDIC_LUT_SMEM") ? std::atoi(std::getenv("ZCORDIC_LUT_SMEM")) : 1;
 		const bool fits = n >= ((size_t)1 << 22) && smem <= 200 * 1024 && (QUARTER ? ow <= 25 : ow <= 16);
 		// both kernels evaluate the same probe of the same phases (zc_kernels.cuh: probe_local) and exactly one proceeds
-		const int probe_lim = (smem_mode == 1 && fits) ? (int)(1u << (pw < 2 ? 30 : (32 - pw > 30 ? 30 : 32 - pw))) : -1;
-		if (smem_mode != 2 || !fits) {
+		const int entry = (int)(1u << (pw < 2 ? 30 : (32 - pw > 30 ? 30 : 32 - pw)));	// one table entry, in 32-bit phase units
+		int probe_lim = (smem_mode == 1 && fits) ? entry : -1;
+		bool use_l2 = (smem_mode != 2 || !fits), use_smem = (smem_mode != 0 && fits);
+		if (nco) {		// the host knows the pattern: neighbouring samples within one table entry keep the L2 kernel
+			const int32_t sstep = (int32_t)nco[1];
+			const bool local = sstep >= -entry && sstep <= entry;
+			probe_lim = -1;
+			if (smem_mode == 1 && fits) { use_l2 = local; use_smem = !local; }
+		}
+		if (use_l2) {
 			if (out16) k_lut<QUARTER, true><<<grid_for(groups, di, 32), 256, 0, st>>>((const int4 *)phase32, out, tbl, groups, c, probe_lim);
 			else k_lut<QUARTER, false><<<grid_for(groups, di, 32), 256, 0, st>>>((const int4 *)phase32, out, tbl, groups, c, probe_lim);
 			if ((rc = post_launch("k_lut")) != ZC_OK) return rc;
 		}
-		if (smem_mode != 0 && fits) {
+		if (use_smem) {
 			typedef void (*kern_t)(const int4 *, void *, const uint32_t *, size_t, const LutConsts, int);
 			kern_t kern = out16 ? (hi8 ? (kern_t)k_lut_smem<QUARTER, true, true> : (kern_t)k_lut_smem<QUARTER, false, true>)
 					    : (hi8 ? (kern_t)k_lut_smem<QUARTER, true, false> : (kern_t)k_lut_smem<QUARTER, false, false>);
@@ -362,7 +373,8 @@ static int launch_lut(int pw, int ow, const uint32_t *tbl, const uint32_t *phase
 	if (done < n) {
 		const size_t rest = n - done;
 		void *tail = out16 ? (void *)((int16_t *)out + done) : (void *)((int32_t *)out + done);
-		k_lut_scalar<QUARTER><<<grid_for(rest, di, 32), 256, 0, st>>>(phase32 + done, tail, tbl, rest, c, out16 ? 1 : 0);
+		c.nco_n0 += (uint32_t)done;
+		k_lut_scalar<QUARTER><<<grid_for(rest, di, 32), 256, 0, st>>>(phase32 ? phase32 + done : nullptr, tail, tbl, rest, c, out16 ? 1 : 0);
 		if ((rc = post_launch("k_lut_scalar")) != ZC_OK) return rc;
 	}
 	return ZC_OK;
@@ -873,6 +885,17 @@ int zc_lut_qwav_o16(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *pha
 	return launch_lut<true>(pw, ow, tbl_dev, phase32, out, n, device, stream, true);
 }
 
+int zc_nco_lut_sin(int pw, int ow, const uint32_t *tbl_dev, uint32_t phase0, uint32_t step, uint64_t n0, int32_t *out,
+		size_t n, int device, void *stream) {
+	const uint32_t nco[3] = {phase0, step, (uint32_t)n0};		// arithmetic is mod 2^32
+	return launch_lut<false>(pw, ow, tbl_dev, nullptr, out, n, device, stream, false, nco);
+}
+int zc_nco_lut_qwav(int pw, int ow, const uint32_t *tbl_dev, uint32_t phase0, uint32_t step, uint64_t n0, int32_t *out,
+		size_t n, int device, void *stream) {
+	const uint32_t nco[3] = {phase0, step, (uint32_t)n0};
+	return launch_lut<true>(pw, ow, tbl_dev, nullptr, out, n, device, stream, false, nco);
+}
+
 int zc_quadtbl_sin(const zc_quadtbl *q, const uint32_t *phase32, int32_t *out, size_t n, int device, void *stream) {
 	return launch_quadtbl(q, phase32, out, n, device, stream);
 }
@@ -958,12 +981,13 @@ int zc_nco_rotate_host(const zc_params *p, int32_t x0, int32_t y0, uint32_t phas
 		});
 }
 
+// nco: {phase0, step} and n0 instead of a phase stream (zc_nco_lut_*_host)
 static int lut_host(bool quarter, int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32,
-		void *out, size_t n, int device, bool out16 = false) {
+		void *out, size_t n, int device, bool out16 = false, const uint32_t *nco = nullptr, uint64_t n0 = 0) {
 	int rc = check_lut(quarter, pw, ow);
 	if (rc != ZC_OK) return rc;
 	if (out16 && ow > 16) return set_error(ZC_ERANGE, "packed int16 outputs need OW <= 16 (OW=%d)", ow);
-	if (!tbl_host || (n && (!phase32 || !out))) return set_error(ZC_EINVAL, "NULL buffer");
+	if (!tbl_host || (n && ((!nco && !phase32) || !out))) return set_error(ZC_EINVAL, "NULL buffer");
 	DeviceInfo di;
 	if ((rc = device_info(device, di)) != ZC_OK) return rc;
 	if (n == 0) return ZC_OK;
@@ -979,10 +1003,13 @@ static int lut_host(bool quarter, int pw, int ow, const uint32_t *tbl_host, cons
 			return set_error(ZC_ECUDA, "table upload failed: %s", cudaGetErrorString(e));
 		}
 	}
-	const Lane in[2] = {{4, (const char *)phase32, nullptr}, {0, nullptr, nullptr}};
+	const Lane in[2] = {{(size_t)(nco ? 0 : 4), (const char *)phase32, nullptr}, {0, nullptr, nullptr}};
 	const Lane outl[2] = {{(size_t)(out16 ? 2 : 4), nullptr, (char *)out}, {0, nullptr, nullptr}};
 	rc = host_pipeline(device, n, in, outl,
-		[&](size_t, size_t cnt, char *i0, char *, char *o0, char *, cudaStream_t st) {
+		[&](size_t off, size_t cnt, char *i0, char *, char *o0, char *, cudaStream_t st) {
+			if (nco)
+				return quarter ? zc_nco_lut_qwav(pw, ow, tbl_dev, nco[0], nco[1], n0 + off, (int32_t *)o0, cnt, device, st)
+					       : zc_nco_lut_sin(pw, ow, tbl_dev, nco[0], nco[1], n0 + off, (int32_t *)o0, cnt, device, st);
 			if (out16)
 				return quarter ? zc_lut_qwav_o16(pw, ow, tbl_dev, (const uint32_t *)i0, (int16_t *)o0, cnt, device, st)
 					       : zc_lut_sin_o16(pw, ow, tbl_dev, (const uint32_t *)i0, (int16_t *)o0, cnt, device, st);
@@ -1060,6 +1087,16 @@ int zc_lut_sin_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *ph
 int zc_lut_qwav_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int32_t *out,
 		size_t n, int device) {
 	return lut_host(true, pw, ow, tbl_host, phase32, out, n, device);
+}
+int zc_nco_lut_sin_host(int pw, int ow, const uint32_t *tbl_host, uint32_t phase0, uint32_t step, uint64_t n0, int32_t *out,
+		size_t n, int device) {
+	const uint32_t nco[2] = {phase0, step};
+	return lut_host(false, pw, ow, tbl_host, nullptr, out, n, device, false, nco, n0);
+}
+int zc_nco_lut_qwav_host(int pw, int ow, const uint32_t *tbl_host, uint32_t phase0, uint32_t step, uint64_t n0, int32_t *out,
+		size_t n, int device) {
+	const uint32_t nco[2] = {phase0, step};
+	return lut_host(true, pw, ow, tbl_host, nullptr, out, n, device, false, nco, n0);
 }
 int zc_lut_sin_o16_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int16_t *out,
 		size_t n, int device) {

@@ -206,6 +206,16 @@ int zc_lut_sin(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32,
 int zc_lut_qwav(int pw, int ow, const uint32_t *tbl_dev, const uint32_t *phase32, int32_t *out,
 		size_t n, int device, void *stream);
 
+/* NCO -> LUT core: the 32-bit phase accumulator of zc_nco_rotate feeding rtl/sintable.v / rtl/quarterwav.v instead of
+ * rtl/cordic.v (the table-based oscillator the generator's -t tbl / -t qtr cores are built for; BASELINE configs[3] asks
+ * for the LUT modes "head to head with the CORDIC kernel", configs[4] for the streaming NCO).  Sample i uses
+ * phase32 = phase0 + (n0+i)*step (mod 2^32), i_phase = phase32 >> (32-pw); out[i] = o_val.  No input stream: 4
+ * algorithmic bytes per sample, all written. */
+int zc_nco_lut_sin(int pw, int ow, const uint32_t *tbl_dev, uint32_t phase0, uint32_t step, uint64_t n0, int32_t *out,
+		size_t n, int device, void *stream);
+int zc_nco_lut_qwav(int pw, int ow, const uint32_t *tbl_dev, uint32_t phase0, uint32_t step, uint64_t n0, int32_t *out,
+		size_t n, int device, void *stream);
+
 /* ---- packed port words ("report separately") ----------------------------------------------
  * The ports of the generated cores are IW / OW bits wide (rtl/cordic.v:58-63, rtl/topolar.v:59-64); the entry points
  * above carry each port in a 32-bit word.  For cores with IW <= 16 / OW <= 16 these variants carry a pair of ports
@@ -256,6 +266,10 @@ int zc_quadtbl_sin_host(const zc_quadtbl *q, const uint32_t *phase32, int32_t *o
 int zc_nco_mix_host(const zc_params *p, const int32_t *xy_in, uint32_t phase0, uint32_t step, uint64_t n0,
 		int32_t *xy_out, size_t n, int device);
 
+int zc_nco_lut_sin_host(int pw, int ow, const uint32_t *tbl_host, uint32_t phase0, uint32_t step, uint64_t n0,
+		int32_t *out, size_t n, int device);
+int zc_nco_lut_qwav_host(int pw, int ow, const uint32_t *tbl_host, uint32_t phase0, uint32_t step, uint64_t n0,
+		int32_t *out, size_t n, int device);
 int zc_lut_sin_o16_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int16_t *out, size_t n,
 		int device);
 int zc_lut_qwav_o16_host(int pw, int ow, const uint32_t *tbl_host, const uint32_t *phase32, int16_t *out, size_t n,

@@ -201,6 +201,30 @@ def test_lut_o16_equals_lut(kind, pw, ow):
     assert np.array_equal(out, ref(pw, ow, tbl, w).astype(np.int16))
 
 
+@pytest.mark.parametrize("kind,pw,ow", [("tbl", 17, 13), ("tbl", 23, 16), ("qtr", 18, 24), ("qtr", 25, 16), ("qtr", 10, 8)])
+def test_nco_through_the_lut_cores(kind, pw, ow):
+    """zc_nco_lut_sin / _qwav: the accumulator's phases generated in registers must give what the lookup gives on the same
+    phases written out -- slow steps (L2 kernel), scattering steps (shared-memory kernel), 64-bit sample offsets, shards that
+    concatenate, ragged sizes, the host entry point."""
+    lut = (zc.SinTable if kind == "tbl" else zc.QuarterWav)(phase_bits=pw, ow=ow)
+    tbl = (zo.sintable if kind == "tbl" else zo.quarterwav)(pw, ow)
+    ref = zo.lut_sin if kind == "tbl" else zo.lut_qwav
+    for n, phase0, step, n0 in [(5, 1, 3, 0), (4099, 0xDEADBEEF, 0x01234567, 7), ((1 << 22) + 3, 0, 0x100, (1 << 33) + 5),
+                                ((1 << 22) + 3, 99, 0x01234567, 123456789), ((1 << 22) + 1, 5, 0xFFFFFF00, 0)]:
+        w = ((phase0 + (n0 + np.arange(n, dtype=np.uint64)) * step) & 0xFFFFFFFF).astype(np.uint32)
+        want = ref(pw, ow, tbl, w)
+        assert np.array_equal(host(lut.nco(phase0, step, n, n0=n0)), want), (kind, pw, ow, n, hex(step))
+    n = 1 << 20
+    whole = host(lut.nco(3, 0x01234567, n))
+    parts = [host(lut.nco(3, 0x01234567, n // 4, n0=r * (n // 4))) for r in range(4)]
+    assert np.array_equal(np.concatenate(parts), whole)
+    m = (5 << 20) + 2
+    out = np.empty(m, dtype=np.int32)
+    lut.nco_host(7, 0x01234567, out, n0=11)
+    w = ((7 + (11 + np.arange(m, dtype=np.uint64)) * 0x01234567) & 0xFFFFFFFF).astype(np.uint32)
+    assert np.array_equal(out, ref(pw, ow, tbl, w))
+
+
 def test_lut_o16_refuses_wide_tables():
     lut = zc.QuarterWav(phase_bits=18, ow=24)
     with pytest.raises(zc.ZcError) as e:

@@ -2,7 +2,7 @@
 # tools/bench_all.sh -- every workload of bench.py once (sweep; random where the phase pattern matters) plus the A/B
 # switches the design document quotes; under gpurun.
 fmt='import sys,json; d=json.loads(sys.stdin.read()); print(sys.argv[1], round(d["value"],1), "GS/s", round(d["roofline"]["achieved"]), "GB/s frac", round(d["roofline"]["frac"],3), "sm", d["clocks"]["sm_mhz_min_under_load"], d["clocks"]["reasons"], d["parity_spot_check"])'
-b() { python bench.py --no-cpu --no-e2e "$@" 2>&1 | tail -1 | python -c "$fmt" "$*"; }
+b() { python bench.py --no-cpu --no-e2e --no-configs --no-sustained "$@" 2>&1 | tail -1 | python -c "$fmt" "$*"; }
 for w in rotate_cfg1 rotate_cfg1_noseed rotate_xy_cfg1 topolar_cfg2 nco_cfg1 sintable_p17 quarterwav_p18 quadtbl_p18; do
   b --steps 10 --warmup 3 --workload $w
 done

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 for rep in 1 2; do
 for st in ${STEPS:-20}; do
 for lib in "" $(ls exp/*.so); do
-  ZCORDIC_LIB=$lib python bench.py --steps $st --warmup 3 --no-cpu --no-e2e --seed-mode words $EXTRA 2>&1 | tail -1 | python -c "$fmt" "$st steps lib=${lib:-product}"
+  ZCORDIC_LIB=$lib python bench.py --steps $st --warmup 3 --no-cpu --no-e2e --no-configs --no-sustained --seed-mode words $EXTRA 2>&1 | tail -1 | python -c "$fmt" "$st steps lib=${lib:-product}"
 done
 done
 done | tee gpurun_out/exp.txt

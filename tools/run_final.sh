@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 ( time python -m pytest tests -m gpu -x -q ) > gpurun_out/final_pytest_gpu.log 2>&1; tail -4 gpurun_out/final_pytest_gpu.log
 bash tools/bench_all.sh > gpurun_out/final_bench_all.txt 2>&1
 fmt='import sys,json; d=json.loads(sys.stdin.read()); print(sys.argv[1], round(d["value"],1), "GS/s", round(d["roofline"]["achieved"]), "GB/s frac", round(d["roofline"]["frac"],3), "sm", d["clocks"]["sm_mhz"], d["clocks"]["reasons"], d["parity_spot_check"])'
-b() { python bench.py --no-cpu --no-e2e "$@" 2>&1 | tail -1 | python -c "$fmt" "$*" >> gpurun_out/final_bench_all.txt; }
+b() { python bench.py --no-cpu --no-e2e --no-configs --no-sustained "$@" 2>&1 | tail -1 | python -c "$fmt" "$*" >> gpurun_out/final_bench_all.txt; }
 b --steps 10 --warmup 3 --workload topolar_cfg2 --no-tail
 b --steps 10 --warmup 3 --seed-mode words --no-dp2a
 b --steps 10 --warmup 3 --workload nco_cfg1 --nco-step 0x100

@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 cap() { # tag regex bench-args...
   tag=$1; re=$2; shift 2
-  ncu --set full --clock-control none --import-source on -k regex:"$re" -s 2 -c 1 -f -o gpurun_out/prof_$tag python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e "$@" > gpurun_out/prof_$tag.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:"$re" -s 2 -c 1 -f -o gpurun_out/prof_$tag python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-configs --no-sustained "$@" > gpurun_out/prof_$tag.log 2>&1
   ncu -i gpurun_out/prof_$tag.ncu-rep --page raw --csv > gpurun_out/prof_${tag}_raw.csv 2>/dev/null
   python tools/ncu_summary.py gpurun_out/prof_${tag}_raw.csv "$tag: $*" > gpurun_out/ncu_$tag.md
   rm -f gpurun_out/prof_$tag.ncu-rep

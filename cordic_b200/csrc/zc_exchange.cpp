@@ -132,12 +132,22 @@ int zc_exchange_create(const int *devices, int ndev, int transport, size_t max_p
 	return ZC_OK;
 }
 
+static int scatter_rotate_gather(zc_exchange *x, const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase,
+		int32_t *xy, size_t n, int nchunks);
+
 int zc_scatter_rotate_gather(zc_exchange *x, const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase,
 		int32_t *xy, size_t n, int nchunks) {
 	if (!x || !p || (n && (!phase || !xy)) || nchunks < 1) return ZC_EINVAL;
-	const int G = x->ndev;
 	int prev = 0;
 	cudaGetDevice(&prev);
+	const int rc = scatter_rotate_gather(x, p, x0, y0, phase, xy, n, nchunks);	// every exit restores the caller's device
+	cudaSetDevice(prev);
+	return rc;
+}
+
+static int scatter_rotate_gather(zc_exchange *x, const zc_params *p, int32_t x0, int32_t y0, const uint32_t *phase,
+		int32_t *xy, size_t n, int nchunks) {
+	const int G = x->ndev;
 	// chunk c = [c0, c1); piece g of it = [c0 + g*len/G, c0 + (g+1)*len/G), boundaries at multiples of 128 samples so
 	// that every piece keeps the alignment (and the table-seeded kernel's block size) of the whole
 	// the peer transport has no stages to overlap: one chunk, the largest pieces
@@ -229,7 +239,6 @@ int zc_scatter_rotate_gather(zc_exchange *x, const zc_params *p, int32_t x0, int
 		if (e == cudaSuccess) e = cudaStreamSynchronize(x->d[g].s_ga);
 		if (e != cudaSuccess && rc == ZC_OK) { std::fprintf(stderr, "zc_exchange: %s\n", cudaGetErrorString(e)); rc = ZC_ECUDA; }
 	}
-	cudaSetDevice(prev);
 	return rc;
 }
 

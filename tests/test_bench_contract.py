@@ -43,3 +43,23 @@ def test_ours_arm_needs_a_gpu():
     r = run_bench(["--steps", "1", "--warmup", "3", "--samples", "4096"])
     assert r.returncode != 0
     assert "no CPU path" in (r.stderr + r.stdout)
+
+
+def test_config_passes_and_arms_agree():
+    """Every extra configuration the `ours` arm measures names a known workload, and both arms build the `config` object
+    from the same function, so that the driver's `same_config` check compares like with like."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("zc_bench", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    for wl, pm in b.CONFIG_PASSES:
+        assert wl in b.WORKLOADS and pm in ("sweep", "random", "nco"), (wl, pm)
+        kind, nper, bytes_per, opts = b.WORKLOADS[wl]
+        assert nper >= 1 << 28 and bytes_per in (4, 6, 8, 12, 16, 20)
+        assert b.core_name(kind, opts)
+    kind, nper, bytes_per, opts = b.WORKLOADS["rotate_cfg1"]
+    cfg = b.config_for("rotate_cfg1", kind, opts, nper, "sweep", bytes_per)
+    assert cfg["samples_per_gpu_per_step"] == 1 << 30 and cfg["workload"] == "rotate_cfg1"
+    r = run_bench(["--impl", "reference", "--steps", "1", "--warmup", "1", "--samples", str(1 << 22)])
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert set(d["config"]) == set(cfg)                       # same keys; the values differ only through --samples here
